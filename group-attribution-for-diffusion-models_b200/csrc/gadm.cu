@@ -1,0 +1,289 @@
+// C ABI (include/gadm.h) over the sm_100a kernels.  Single translation unit: the kernel headers are
+// included here so that device-side globals (watchdog word) exist exactly once.
+#include "../../include/gadm.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gadm_ptx.cuh"
+#include "philox.cuh"
+#include "project.cuh"
+
+struct gadm_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int64_t launches = 0;
+  PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define GADM_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(GADM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define GADM_REQUIRE(cond, ...)                       \
+  do {                                                \
+    if (!(cond)) return fail(GADM_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// 2-D row-major tensor map: inner dimension `cols` (contiguous), outer `rows`, pitch in bytes.
+int make_tmap_2d(gadm_handle h, CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base,
+                 uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  GADM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor base %p is not 16-byte aligned", base);
+  GADM_REQUIRE(pitch_bytes % 16 == 0, "row pitch %llu B is not a multiple of 16", (unsigned long long)pitch_bytes);
+  GADM_REQUIRE(box_cols * elem_bytes == 128, "box inner extent must be 128 B for SWIZZLE_128B");
+  CUresult r = h->encode_tiled(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GADM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GADM_OK;
+}
+
+struct ProjPlan {
+  uint32_t n_tiles, n_splits, n_units, nkb_total, n_acc, unit_rows, n_clusters;
+  int64_t ws_bytes;
+};
+
+int plan_projection(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_dim, int cta_group, ProjPlan* p) {
+  GADM_REQUIRE(cta_group == 1 || cta_group == 2, "cta_group must be 1 or 2, got %d", cta_group);
+  GADM_REQUIRE(proj_dim > 0 && proj_dim % gadm::proj::kTileN == 0, "proj_dim %lld must be a positive multiple of 256",
+               (long long)proj_dim);
+  GADM_REQUIRE(d_pad > 0 && d_pad % gadm::proj::kBlockK == 0, "d_pad %lld must be a positive multiple of 64",
+               (long long)d_pad);
+  const int64_t max_rows = (int64_t)gadm::proj::kNumAcc * gadm::proj::kAccRows * cta_group;
+  GADM_REQUIRE(m_rows > 0 && m_rows <= max_rows, "m_rows %lld out of range (1..%lld) for cta_group %d",
+               (long long)m_rows, (long long)max_rows, cta_group);
+  p->n_tiles = (uint32_t)(proj_dim / gadm::proj::kTileN);
+  p->nkb_total = (uint32_t)(d_pad / gadm::proj::kBlockK);
+  p->n_acc = (m_rows > (int64_t)gadm::proj::kAccRows * cta_group) ? 2u : 1u;
+  p->unit_rows = p->n_acc * gadm::proj::kAccRows * cta_group;
+  p->n_clusters = (uint32_t)(h->num_sms / cta_group);
+  // smallest D-split count whose unit count fills whole waves of clusters to >= 97% (units of one
+  // wave cover consecutive splits x all column tiles, so a gradient tile is re-read from L2, not HBM)
+  uint32_t best = 1;
+  double best_eff = 0.0;
+  const uint32_t max_splits = p->nkb_total < 128u ? p->nkb_total : 128u;
+  for (uint32_t s = 1; s <= max_splits; ++s) {
+    const uint64_t units = (uint64_t)p->n_tiles * s;
+    const uint64_t waves = (units + p->n_clusters - 1) / p->n_clusters;
+    const double eff = (double)units / (double)(waves * p->n_clusters);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    if (eff >= 0.97) break;
+  }
+  p->n_splits = best;
+  p->n_units = p->n_tiles * p->n_splits;
+  p->ws_bytes = (int64_t)p->n_units * p->unit_rows * gadm::proj::kTileN * (int64_t)sizeof(float);
+  return GADM_OK;
+}
+
+template <int kCtaGroup>
+int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Args& args, uint32_t n_clusters,
+                   cudaStream_t stream) {
+  using C = gadm::proj::Cfg<kCtaGroup>;
+  auto kernel = gadm::proj::project_kernel<kCtaGroup>;
+  GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  cudaLaunchConfig_t cfg{};
+  const uint32_t clusters = args.n_units < n_clusters ? args.n_units : n_clusters;
+  cfg.gridDim = dim3(clusters * kCtaGroup);
+  cfg.blockDim = dim3(gadm::proj::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, args));
+  h->launches++;
+  return GADM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gadm_version(void) { return 100; }
+
+const char* gadm_last_error(void) { return g_last_error.c_str(); }
+
+int gadm_create(gadm_handle* out, int device) {
+  if (!out) return fail(GADM_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int count = 0;
+  GADM_CUDA(cudaGetDeviceCount(&count));
+  GADM_REQUIRE(device >= 0 && device < count, "device %d out of range (%d devices)", device, count);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  GADM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(GADM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)",
+                device, prop.major, prop.minor);
+  GADM_CUDA(cudaFree(0));  // make sure the primary context exists
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  GADM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(GADM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  gadm_ctx* h = new gadm_ctx();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  *out = h;
+  return GADM_OK;
+}
+
+int gadm_destroy(gadm_handle h) {
+  delete h;
+  return GADM_OK;
+}
+
+int64_t gadm_launch_count(gadm_handle h) { return h ? h->launches : 0; }
+
+int gadm_watchdog_code(gadm_handle h, unsigned int* code) {
+  GADM_REQUIRE(h && code, "null argument");
+  DeviceGuard guard(h->device);
+  unsigned int zero = 0;
+  GADM_CUDA(cudaMemcpyFromSymbol(code, gadm::g_watchdog_code, sizeof(unsigned int)));
+  GADM_CUDA(cudaMemcpyToSymbol(gadm::g_watchdog_code, &zero, sizeof(unsigned int)));
+  return GADM_OK;
+}
+
+int64_t gadm_project_workspace_bytes(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_dim, int cta_group) {
+  if (!h) return fail(GADM_ERR_INVALID, "null handle");
+  ProjPlan p;
+  int rc = plan_projection(h, m_rows, d_pad, proj_dim, cta_group, &p);
+  if (rc != GADM_OK) return rc;
+  return p.ws_bytes;
+}
+
+int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, int64_t numel, int64_t src_stride,
+                    void* staged, int64_t ld, int64_t row0, int64_t col0, float scale, void* stream) {
+  GADM_REQUIRE(h && src && staged, "null argument");
+  GADM_REQUIRE(batch > 0 && numel > 0 && src_stride >= numel && ld >= col0 + numel && row0 >= 0 && col0 >= 0,
+               "bad block geometry (batch %lld numel %lld stride %lld ld %lld row0 %lld col0 %lld)", (long long)batch,
+               (long long)numel, (long long)src_stride, (long long)ld, (long long)row0, (long long)col0);
+  DeviceGuard guard(h->device);
+  const int threads = 256;
+  int64_t bx = (numel + threads * 8 - 1) / (threads * 8);
+  if (bx > 4096) bx = 4096;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)batch);
+  auto* dst = reinterpret_cast<__nv_bfloat16*>(staged);
+  if (dtype == GADM_DTYPE_F32)
+    gadm::proj::pack_block_kernel<float><<<grid, threads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float*>(src), src_stride, numel, batch, dst, ld, row0, col0, scale);
+  else if (dtype == GADM_DTYPE_BF16)
+    gadm::proj::pack_block_kernel<__nv_bfloat16><<<grid, threads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src), src_stride, numel, batch, dst, ld, row0, col0, scale);
+  else if (dtype == GADM_DTYPE_F16)
+    gadm::proj::pack_block_kernel<__half><<<grid, threads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __half*>(src), src_stride, numel, batch, dst, ld, row0, col0, scale);
+  else
+    return fail(GADM_ERR_INVALID, "unknown dtype %d", dtype);
+  GADM_CUDA(cudaGetLastError());
+  h->launches++;
+  return GADM_OK;
+}
+
+int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t ld, int64_t p_base,
+                        int64_t proj_dim, uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate,
+                        void* workspace, int64_t workspace_bytes, int cta_group, void* stream) {
+  GADM_REQUIRE(h && staged && out && workspace, "null argument");
+  GADM_REQUIRE(proj_type == GADM_PROJ_NORMAL || proj_type == GADM_PROJ_RADEMACHER, "unknown proj_type %d", proj_type);
+  GADM_REQUIRE(p_base >= 0 && p_base % 64 == 0, "p_base %lld must be a non-negative multiple of 64", (long long)p_base);
+  GADM_REQUIRE(ld >= d_pad && ld % 8 == 0, "ld %lld must be >= d_pad and a multiple of 8", (long long)ld);
+  GADM_REQUIRE(ld_out >= proj_dim && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "out must be 16-byte aligned with pitch %% 4 == 0");
+  GADM_REQUIRE((p_base + d_pad) / 8 < (1ll << 32), "parameter index exceeds the 2^35 counter range");
+  ProjPlan p;
+  int rc = plan_projection(h, m_rows, d_pad, proj_dim, cta_group, &p);
+  if (rc != GADM_OK) return rc;
+  if (workspace_bytes < p.ws_bytes)
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes,
+                (long long)p.ws_bytes);
+  GADM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  DeviceGuard guard(h->device);
+  CUtensorMap tmap;
+  rc = make_tmap_2d(h, &tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, staged, (uint64_t)d_pad, (uint64_t)m_rows,
+                    (uint64_t)ld * 2, gadm::proj::kBlockK, gadm::proj::kAccRows);
+  if (rc != GADM_OK) return rc;
+  gadm::proj::Args a;
+  a.partial = reinterpret_cast<float*>(workspace);
+  a.n_tiles = p.n_tiles;
+  a.n_splits = p.n_splits;
+  a.n_units = p.n_units;
+  a.nkb_total = p.nkb_total;
+  a.n_acc = p.n_acc;
+  a.unit_rows = p.unit_rows;
+  a.key0 = (uint32_t)(seed64 & 0xFFFFFFFFull);
+  a.key1 = (uint32_t)(seed64 >> 32);
+  a.proj_type = (uint32_t)proj_type;
+  a.p_base_div64 = (uint32_t)(p_base / 64);
+  cudaStream_t st = as_stream(stream);
+  rc = (cta_group == 2) ? launch_project<2>(h, tmap, a, p.n_clusters, st) : launch_project<1>(h, tmap, a, p.n_clusters, st);
+  if (rc != GADM_OK) return rc;
+  dim3 rgrid((unsigned)((proj_dim / 4 + 127) / 128), (unsigned)m_rows);
+  gadm::proj::project_reduce_kernel<<<rgrid, 128, 0, st>>>(a.partial, out, ld_out, (uint32_t)m_rows, p.n_tiles,
+                                                          p.n_splits, p.unit_rows, accumulate);
+  GADM_CUDA(cudaGetLastError());
+  h->launches++;
+  return GADM_OK;
+}
+
+int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_dim, uint64_t seed64, int proj_type,
+                       float* out, void* stream) {
+  GADM_REQUIRE(h && out, "null argument");
+  GADM_REQUIRE(row0 >= 0 && nrows > 0 && proj_dim > 0, "bad shape");
+  GADM_REQUIRE(proj_type == GADM_PROJ_NORMAL || proj_type == GADM_PROJ_RADEMACHER, "unknown proj_type %d", proj_type);
+  DeviceGuard guard(h->device);
+  const int64_t total = nrows * proj_dim;
+  const int threads = 256;
+  gadm::proj::materialize_p_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
+      out, row0, nrows, proj_dim, (uint32_t)(seed64 & 0xFFFFFFFFull), (uint32_t)(seed64 >> 32), proj_type);
+  GADM_CUDA(cudaGetLastError());
+  h->launches++;
+  return GADM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// JL projection  Phi[M, k] = G[M, D] * P[D, k]  with P generated on the fly (never stored).
+//
+// Replaces fast_jl.project_{normal,rademacher}_{8,16,32} behind trak.projectors.CudaProjector.project
+// (reference call sites: src/attributions/methods/d_trak_grad.py:776,
+// text_to_image/grad_text_to_image_lora.py:765,813).
+//
+// Kernel shape (sm_100a):
+//   * one CTA pair (cluster of 2, tcgen05 cta_group::2) per "unit" = (256-column tile of Phi, D-split);
+//     UMMA 256x256x16 bf16 -> fp32, two accumulators (2 x 256 TMEM columns) so that a generated P
+//     tile feeds up to 512 staged gradient rows;
+//   * A operand (staged bf16 gradients, K-major) arrives by TMA into 128B-swizzled smem;
+//   * B operand (P tile, K-major, 128B swizzle) is *written by generator warps* straight into the
+//     UMMA smem layout from Philox4x32-10 (see philox.cuh), then published to the async proxy;
+//   * warp roles: 0 = TMA, 1 = MMA issue (leader CTA, one thread), 2 = TMEM alloc, 4-7 = epilogue
+//     (TMEM -> registers -> split-K partial tile in HBM), 8-15 = generators (4 groups of 2 warps,
+//     each group owns every 4th pipeline slot);
+//   * split-K partials are reduced in a fixed order by project_reduce_kernel => results do not
+//     depend on the schedule, the SM count or atomics.
+// kCtaGroup == 1 is the single-CTA variant of the same code (UMMA 128x256x16, 3 stages).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "gadm_ptx.cuh"
+#include "philox.cuh"
+
+namespace gadm {
+namespace proj {
+
+constexpr int kBlockK = 64;   // bf16 elements per smem row = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kTileN = 256;   // Phi columns per unit
+constexpr int kAccRows = 128; // gradient rows per CTA per accumulator
+constexpr int kNumAcc = 2;
+constexpr int kGenWarps = 8;
+constexpr int kWarpsPerGroup = 2;
+constexpr int kGenGroups = kGenWarps / kWarpsPerGroup;
+constexpr int kGroupThreads = kWarpsPerGroup * 32;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kFirstGenWarp = 8;
+constexpr int kThreads = (kFirstGenWarp + kGenWarps) * 32;
+constexpr int kTmemCols = 512;
+
+template <int kCtaGroup>
+struct Cfg {
+  static constexpr int kBRows = kTileN / kCtaGroup;                    // P rows (Phi columns) generated per CTA
+  static constexpr int kATileBytes = kAccRows * kBlockK * 2;           // 16 KiB
+  static constexpr int kABytes = kNumAcc * kATileBytes;                // 32 KiB
+  static constexpr int kBBytes = kBRows * kBlockK * 2;                 // 16 / 32 KiB
+  static constexpr int kStageBytes = kABytes + kBBytes;                // 48 / 64 KiB
+  static constexpr int kStages = (kCtaGroup == 2) ? 4 : 3;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kUnitRows = kNumAcc * kAccRows * kCtaGroup;     // rows of a full partial tile (512 / 256)
+};
+
+struct Args {
+  float* partial;       // [n_units][unit_rows][256] fp32 split-K partial tiles
+  uint32_t n_tiles;     // k / 256
+  uint32_t n_splits;    // D-splits
+  uint32_t n_units;     // n_tiles * n_splits
+  uint32_t nkb_total;   // D_pad / 64
+  uint32_t n_acc;       // accumulators in use (1 or 2)
+  uint32_t unit_rows;   // n_acc * 128 * cta_group
+  uint32_t key0, key1;  // Philox key = seed64
+  uint32_t proj_type;   // ProjType
+  uint32_t p_base_div64;  // canonical index of staged column 0, / 64
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// Fill one B stage (kBRows x 64 bf16, K-major, 128B swizzle) with Rademacher signs.
+//   smem_b: stage base (1024-aligned); p_div32: canonical p of stage column 0, / 32; j0: first Phi column
+template <int kBRows>
+__device__ __forceinline__ void gen_rademacher_stage(uint32_t smem_b, uint32_t p_div32, uint32_t j0, uint32_t k0,
+                                                     uint32_t k1, int tig, int lane) {
+  constexpr int kJGroups = kBRows / 4;
+  constexpr int kCalls = kJGroups * 2;
+  const int rot = (lane >> 1) & 3;
+#pragma unroll
+  for (int c = tig; c < kCalls; c += kGroupThreads) {
+    const int jg = c % kJGroups;
+    const int pg = c / kJGroups;
+    uint4 w = rademacher_call(p_div32 + pg, (j0 >> 2) + jg, k0, k1);
+    // rotate the four words by `rot` so that the 8 lanes of a quarter-warp store to 8 distinct rows mod 8
+    if (rot & 1) { const uint32_t t = w.x; w.x = w.y; w.y = w.z; w.z = w.w; w.w = t; }
+    if (rot & 2) { uint32_t t = w.x; w.x = w.z; w.z = t; t = w.y; w.y = w.w; w.w = t; }
+    const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = 4 * jg + ((i + rot) & 3);
+      const uint32_t row_addr = smem_b + row * 128;
+      const uint32_t sw = row & 7;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t byte = (words[i] >> (8 * cc)) & 0xFFu;
+        const uint32_t chunk = 4 * pg + cc;
+        st_shared_v4(row_addr + ((chunk ^ sw) << 4), rademacher_expand8(byte));
+      }
+    }
+  }
+}
+
+// Fill one B stage with bf16 N(0,1) values.  p_div8: canonical p of stage column 0, / 8.
+template <int kBRows>
+__device__ __forceinline__ void gen_normal_stage(uint32_t smem_b, uint32_t p_div8, uint32_t j0, uint32_t k0,
+                                                 uint32_t k1, int tig) {
+  constexpr int kCalls = kBRows * 8;
+#pragma unroll 4
+  for (int e = tig; e < kCalls; e += kGroupThreads) {
+    const int row = e % kBRows;
+    const int c = e / kBRows;
+    const uint4 v = normal_chunk(p_div8 + c, j0 + row, k0, k1);
+    st_shared_v4(smem_b + row * 128 + ((c ^ (row & 7)) << 4), v);
+  }
+}
+
+template <int kCtaGroup>
+__global__ void __launch_bounds__(kThreads, 1)
+project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
+  using C = Cfg<kCtaGroup>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::kStages);
+  const uint32_t tmem_empty_bar = tmem_full_bar + 8u;
+  const uint32_t tmem_slot = tmem_empty_bar + 8u;
+  auto smem_a = [&](int s, int acc) { return smem_base + s * C::kStageBytes + acc * C::kATileBytes; };
+  auto smem_b = [&](int s) { return smem_base + s * C::kStageBytes + C::kABytes; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cid = blockIdx.x / kCtaGroup;
+  const uint32_t n_clusters = gridDim.x / kCtaGroup;
+
+  if (warp == 0 && lane == 0) prefetch_tensormap(&tmap_g);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1 + kWarpsPerGroup * kCtaGroup);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 4 * kCtaGroup);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kCtaGroup>(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_arrive_wait(); else __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto kb_begin = [&](uint32_t split) {
+    return static_cast<uint32_t>((static_cast<uint64_t>(split) * a.nkb_total) / a.n_splits);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: staged gradient tiles (A operand)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
+        const uint32_t split = u / a.n_tiles;
+        const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
+        for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u, 0x100 + s);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), a.n_acc * C::kATileBytes * kCtaGroup);
+          for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
+            const int32_t row = acc * (kAccRows * kCtaGroup) + rank * kAccRows;
+            if constexpr (kCtaGroup == 2)
+              tma_load_2d_cg2(smem_a(s, acc), &tmap_g, mapa(full_bar(s), 0), kb * kBlockK, row);
+            else
+              tma_load_2d(smem_a(s, acc), &tmap_g, full_bar(s), kb * kBlockK, row);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread)
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc(UMMA_FMT_BF16, kAccRows * kCtaGroup, kTileN);
+      uint32_t it = 0, unit_iter = 0;
+      for (uint32_t u = cid; u < a.n_units; u += n_clusters, ++unit_iter) {
+        const uint32_t split = u / a.n_tiles;
+        const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
+        if (unit_iter > 0) mbar_wait(tmem_empty_bar, (unit_iter - 1) & 1u, 0x200);
+        tcgen05_fence_after();
+        for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1u;
+          mbar_wait(full_bar(s), ph, 0x300 + s);
+          tcgen05_fence_after();
+          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b(s));
+          for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
+            const uint64_t adesc = umma_desc_kmajor_sw128(smem_a(s, acc));
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advancing K by 16 bf16 = 32 B inside the 128B swizzle row: +2 in the (addr >> 4) field
+              umma_f16<kCtaGroup>(tmem_base + acc * kTileN, adesc + 2u * k, bdesc + 2u * k, idesc,
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          }
+          if constexpr (kCtaGroup == 2) umma_commit_cg2_mcast(empty_bar(s), 0x3); else umma_commit(empty_bar(s));
+        }
+        if constexpr (kCtaGroup == 2) umma_commit_cg2_mcast(tmem_full_bar, 0x3); else umma_commit(tmem_full_bar);
+      }
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstGenWarp) {
+    // ===================== epilogue: TMEM -> registers -> split-K partial tile
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t unit_iter = 0;
+    for (uint32_t u = cid; u < a.n_units; u += n_clusters, ++unit_iter) {
+      mbar_wait(tmem_full_bar, unit_iter & 1u, 0x400);
+      tcgen05_fence_after();
+      for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
+        const uint32_t row = acc * (kAccRows * kCtaGroup) + rank * kAccRows + q * 32 + lane;
+        float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
+#pragma unroll 1
+        for (int c = 0; c < kTileN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<uint4*>(dst + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 2) mbar_arrive_cluster(mapa(tmem_empty_bar, 0)); else mbar_arrive(tmem_empty_bar);
+      }
+    }
+  } else if (warp >= kFirstGenWarp) {
+    // ===================== generators: P tile (B operand) straight into the UMMA smem layout
+    const int gw = warp - kFirstGenWarp;
+    const int group = gw / kWarpsPerGroup;
+    const int tig = (gw % kWarpsPerGroup) * 32 + lane;
+    uint32_t it = 0;
+    for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
+      const uint32_t split = u / a.n_tiles;
+      const uint32_t tile = u % a.n_tiles;
+      const uint32_t j0 = tile * kTileN + rank * C::kBRows;
+      const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
+      for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
+        if (static_cast<int>(it % kGenGroups) != group) continue;
+        const int s = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u, 0x500 + s);
+        const uint32_t p_div64 = a.p_base_div64 + kb;
+        if (a.proj_type == kProjRademacher)
+          gen_rademacher_stage<C::kBRows>(smem_b(s), p_div64 * 2u, j0, a.key0, a.key1, tig, lane);
+        else
+          gen_normal_stage<C::kBRows>(smem_b(s), p_div64 * 8u, j0, a.key0, a.key1, tig);
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the UMMA (async proxy) reads
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtaGroup == 2) mbar_arrive_cluster(mapa(full_bar(s), 0)); else mbar_arrive(full_bar(s));
+        }
+      }
+    }
+  }
+
+  // ===================== teardown
+  __syncwarp();  // single-lane roles: reconverge before the .aligned barriers below
+  tcgen05_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_arrive_wait(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+}
+
+// out[m, tile*256 + c] (+)= sum over splits of partial[split*n_tiles + tile][m][c], fixed order.
+__global__ void project_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t ld_out,
+                                      uint32_t M, uint32_t n_tiles, uint32_t n_splits, uint32_t unit_rows,
+                                      int accumulate) {
+  const uint32_t col4 = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column index over k/4
+  const uint32_t m = blockIdx.y;
+  if (col4 >= n_tiles * (kTileN / 4) || m >= M) return;
+  const uint32_t tile = col4 / (kTileN / 4);
+  const uint32_t c4 = col4 % (kTileN / 4);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t s = 0; s < n_splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(
+        partial + (static_cast<size_t>(s * n_tiles + tile) * unit_rows + m) * kTileN + c4 * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float* o = out + static_cast<size_t>(m) * ld_out + tile * kTileN + c4 * 4;
+  if (accumulate) { o[0] += acc.x; o[1] += acc.y; o[2] += acc.z; o[3] += acc.w; }
+  else { o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w; }
+}
+
+// Oracle hook: P[row0 + r, j] for r < nrows, j < k as fp32, using the very device functions the
+// projection kernel uses (so a host-side G @ P reproduces the kernel up to summation order).
+__global__ void materialize_p_kernel(float* __restrict__ out, int64_t row0, int64_t nrows, int64_t k, uint32_t key0,
+                                     uint32_t key1, int proj_type) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nrows * k) return;
+  const int64_t r = idx / k, j = idx % k;
+  const uint64_t p = static_cast<uint64_t>(row0 + r);
+  float v;
+  if (proj_type == kProjRademacher) {
+    const uint4 w = rademacher_call(static_cast<uint32_t>(p >> 5), static_cast<uint32_t>(j >> 2), key0, key1);
+    const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    const uint32_t word = words[j & 3];
+    const uint32_t byte = (word >> (8 * ((p & 31) >> 3))) & 0xFFu;
+    const uint4 e = rademacher_expand8(byte);
+    const uint32_t pk[4] = {e.x, e.y, e.z, e.w};
+    const uint32_t h = (pk[(p & 7) >> 1] >> (16 * (p & 1))) & 0xFFFFu;
+    v = __uint_as_float(h << 16);
+  } else {
+    const uint4 c = normal_chunk(static_cast<uint32_t>(p >> 3), static_cast<uint32_t>(j), key0, key1);
+    const uint32_t pk[4] = {c.x, c.y, c.z, c.w};
+    const uint32_t h = (pk[(p & 7) >> 1] >> (16 * (p & 1))) & 0xFFFFu;
+    v = __uint_as_float(h << 16);
+  }
+  out[idx] = v;
+}
+
+// fp32 / bf16 gradient block -> bf16 staging buffer.  src: [B, numel] with row pitch src_stride
+// (elements); dst: staged [rows, ld_dst] bf16, written at (row0 + b, col0 + i).
+template <typename T>
+__global__ void pack_block_kernel(const T* __restrict__ src, int64_t src_stride, int64_t numel, int64_t B,
+                                  __nv_bfloat16* __restrict__ dst, int64_t ld_dst, int64_t row0, int64_t col0,
+                                  float scale) {
+  const int64_t b = blockIdx.y;
+  const T* s = src + b * src_stride;
+  __nv_bfloat16* d = dst + (row0 + b) * ld_dst + col0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    d[i] = __float2bfloat16_rn(static_cast<float>(s[i]) * scale);
+  }
+}
+
+}  // namespace proj
+}  // namespace gadm
