@@ -1,8 +1,14 @@
 """Public names of the package (import as ``gadm_b200``)."""
 from .projectors import BasicProjector, CudaProjector, DeferredProjection, ProjectionType, is_not_buffer  # noqa: F401
+from .aggregation import (PackedMasks, bootstrap_statistic, data_banzhaf, data_banzhaf_batched, data_shapley,  # noqa: F401
+                          data_shapley_batched, evaluate_lds, group_reduce, lds_per_test_set, spearman_matrix,
+                          stable_rank, sym_pinv)
 from ._lib import GadmError, load_library  # noqa: F401
 
 __all__ = [
     "BasicProjector", "CudaProjector", "DeferredProjection", "ProjectionType", "is_not_buffer",
+    "PackedMasks", "bootstrap_statistic", "data_banzhaf", "data_banzhaf_batched", "data_shapley",
+    "data_shapley_batched", "evaluate_lds", "group_reduce", "lds_per_test_set", "spearman_matrix", "stable_rank",
+    "sym_pinv",
     "GadmError", "load_library",
 ]

@@ -26,6 +26,19 @@ _SIGNATURES = {
     "gadm_project_staged": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_i64,
                                       C.c_int, c_vp, c_i64, C.c_int, c_vp]),
     "gadm_materialize_p": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_vp]),
+    "gadm_pack_masks": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "gadm_mask_gram": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
+    "gadm_mask_xty": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, C.c_double, C.c_double, c_vp, c_vp]),
+    "gadm_mask_times_matrix": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "gadm_sym_pinv_workspace_bytes": (c_i64, [c_i64]),
+    "gadm_sym_pinv": (C.c_int, [c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),
+    "gadm_dgemm_dk": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_double, c_vp, c_vp]),
+    "gadm_shapley_rhs": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gadm_lds_spearman": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "gadm_lds_mean": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "gadm_group_reduce": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
+    "gadm_stable_rank_desc": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "gadm_row_mean": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,399 @@
+// Subset-mask regressions (Shapley / Banzhaf), LDS rank correlations, group reductions, stable ranks.
+// All fp64 / integer SIMT kernels: the problems are HBM/L2- and latency-bound (12.9 MB at
+// BASELINE config 5), so the rules that matter are coalesced loads, bit-packed masks and fixed
+// summation orders -- no tensor cores.
+//
+// Reference arithmetic restated here:
+//   data_shapley   src/attributions/methods/datashapley.py:8-48
+//   data_banzhaf   src/attributions/methods/databanzhaf.py:5-26
+//   evaluate_lds   text_to_image/shapley_lds.py:138-150, lds.py:158-170 (scipy.stats.spearmanr)
+//   bootstrap stat lds.py:458-476
+//   group sums     text_to_image/traks.py:188-204 ; ranks traks.py:216-218, shapley_lds.py:294
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gadm {
+namespace agg {
+
+// ------------------------------------------------------------------ mask packing
+// X: [n, d] uint8 (0/1).  rowbits: [n, wd] (bit i%32 of word i/32 = X[r, i]); colbits: [d, wn].
+__global__ void pack_masks_kernel(const uint8_t* __restrict__ X, int64_t n, int64_t d, uint32_t* __restrict__ rowbits,
+                                  int64_t wd, uint32_t* __restrict__ colbits, int64_t wn) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // first n*wd threads build row words, the next d*wn threads build column words
+  if (tid < n * wd) {
+    const int64_t r = tid / wd, w = tid % wd;
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int64_t i = w * 32 + b;
+      if (i < d && X[r * d + i]) bits |= (1u << b);
+    }
+    rowbits[tid] = bits;
+  } else if (tid < n * wd + d * wn) {
+    const int64_t t = tid - n * wd;
+    const int64_t w = t / d, i = t % d;  // consecutive threads -> consecutive i (coalesced bytes)
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int64_t r = w * 32 + b;
+      if (r < n && X[r * d + i]) bits |= (1u << b);
+    }
+    colbits[i * wn + w] = bits;
+  }
+}
+
+// ------------------------------------------------------------------ normal equations
+// mode 0 (Shapley):  A[i,j] = N11(i,j) / n                        (datashapley.py:29)
+// mode 1 (Banzhaf):  A[i,j] = N11 - (c_i + c_j)/2 + n/4           (databanzhaf.py:20-22, (X-1/2)^T (X-1/2))
+// N11 = co-occurrence count (exact integer), c_i = column count.
+__global__ void mask_gram_kernel(const uint32_t* __restrict__ colbits, int64_t d, int64_t wn, int64_t n, int mode,
+                                 double* __restrict__ A) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= d * d) return;
+  const int64_t i = tid / d, j = tid % d;
+  int64_t n11 = 0, ci = 0, cj = 0;
+  for (int64_t w = 0; w < wn; ++w) {
+    const uint32_t a = colbits[i * wn + w], b = colbits[j * wn + w];
+    n11 += __popc(a & b);
+    ci += __popc(a);
+    cj += __popc(b);
+  }
+  if (mode == 0) A[tid] = static_cast<double>(n11) / static_cast<double>(n);
+  else A[tid] = static_cast<double>(n11) - 0.5 * static_cast<double>(ci + cj) + 0.25 * static_cast<double>(n);
+}
+
+// out[i, k] = ( sum_r X[r,i] * (Y[r,k] - shift[k]) - half * sum_r (Y[r,k] - shift[k]) ) * scale
+//   Shapley: shift = v0, half = 0, scale = 1/n   (datashapley.py:30)
+//   Banzhaf: shift = 0 (null), half = 0.5, scale = 1   (databanzhaf.py:23)
+// Also serves X_test @ phi (evaluate_lds) through the transposed call mask_times_matrix_kernel below.
+constexpr int kXtyI = 8;  // players per thread
+__global__ void mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ Y,
+                                int64_t n, int64_t d, int64_t K, const double* __restrict__ shift, double half,
+                                double scale, double* __restrict__ out) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kXtyI;
+  if (k >= K) return;
+  const double sh = shift ? shift[k] : 0.0;
+  double acc[kXtyI];
+#pragma unroll
+  for (int t = 0; t < kXtyI; ++t) acc[t] = 0.0;
+  double tot = 0.0;
+  const int64_t word = i0 >> 5;
+  const int bit0 = static_cast<int>(i0 & 31);
+  for (int64_t r = 0; r < n; ++r) {
+    const double y = Y[r * K + k] - sh;
+    const uint32_t bits = rowbits[r * wd + word] >> bit0;  // kXtyI divides 32: the 8 players share a word
+    tot += y;
+#pragma unroll
+    for (int t = 0; t < kXtyI; ++t)
+      if ((bits >> t) & 1u) acc[t] += y;
+  }
+#pragma unroll
+  for (int t = 0; t < kXtyI; ++t)
+    if (i0 + t < d) out[(i0 + t) * K + k] = (acc[t] - half * tot) * scale;
+}
+
+// out[r, k] = sum_i X[r,i] * M[i,k]   (x_test @ attrs, shapley_lds.py:145)
+__global__ void mask_times_matrix_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ M,
+                                         int64_t m, int64_t d, int64_t K, double* __restrict__ out) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (k >= K || r >= m) return;
+  double acc = 0.0;
+  for (int64_t w = 0; w < wd; ++w) {
+    uint32_t bits = rowbits[r * wd + w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      acc += M[(w * 32 + b) * K + k];
+    }
+  }
+  out[r * K + k] = acc;
+}
+
+// ------------------------------------------------------------------ symmetric pseudo-inverse
+// One-sided (Hestenes) Jacobi SVD of a symmetric matrix, fp64, one CTA.  Rows of G start as the rows
+// (= columns) of A and are rotated until mutually orthogonal; Vt accumulates the rotations.  Then
+//   pinv(A) = sum_{i: sigma_i > rcond * sigma_max} v_i g_i^T / sigma_i^2 ,  sigma_i = ||g_i||
+// which is numpy.linalg.pinv's SVD formula with its cutoff (datashapley.py:37 uses the default
+// rcond = 1e-15; numpy.linalg.lstsq(rcond=None) in databanzhaf.py:20-25 uses eps * d).
+// work: 2 * dp * dp doubles (dp = d rounded up to even) + dp doubles; lives in smem when it fits.
+constexpr int kPinvThreads = 1024;
+constexpr int kPinvMaxSweeps = 40;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kPinvThreads, 1)
+sym_pinv_kernel(const double* __restrict__ A, int d, double rcond, double* __restrict__ out, double* gwork,
+                int use_smem, int* __restrict__ info) {
+  extern __shared__ double pinv_smem[];
+  const int dp = (d + 1) & ~1;
+  double* G = use_smem ? pinv_smem : gwork;
+  double* Vt = G + static_cast<size_t>(dp) * dp;
+  double* sig2 = Vt + static_cast<size_t>(dp) * dp;
+  __shared__ int s_rot;
+  __shared__ double s_max;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kPinvThreads / 32;
+
+  for (int idx = tid; idx < dp * dp; idx += kPinvThreads) {
+    const int i = idx / dp, j = idx % dp;
+    G[idx] = (i < d && j < d) ? A[i * d + j] : 0.0;
+    Vt[idx] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  const int npairs = dp / 2;
+  int sweep = 0;
+  for (; sweep < kPinvMaxSweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int round = 0; round < dp - 1; ++round) {
+      // round-robin tournament: dp/2 disjoint pairs per round, every pair once per sweep
+      for (int pr = warp; pr < npairs; pr += nwarps) {
+        // circle method: (dp-1, round) and every {a, b} with a + b == 2*round (mod dp-1)
+        const int a = (pr == 0) ? dp - 1 : (round + pr) % (dp - 1);
+        const int b = (pr == 0) ? round : (round - pr + (dp - 1)) % (dp - 1);
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        double* gp = G + static_cast<size_t>(p) * dp;
+        double* gq = G + static_cast<size_t>(q) * dp;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int j = lane; j < dp; j += 32) {
+          const double x = gp[j], y = gq[j];
+          alpha += x * x; beta += y * y; gamma += x * y;
+        }
+        alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+        if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && gamma != 0.0) {
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          double* vp = Vt + static_cast<size_t>(p) * dp;
+          double* vq = Vt + static_cast<size_t>(q) * dp;
+          for (int j = lane; j < dp; j += 32) {
+            const double x = gp[j], y = gq[j];
+            gp[j] = c * x - s * y; gq[j] = s * x + c * y;
+            const double vx = vp[j], vy = vq[j];
+            vp[j] = c * vx - s * vy; vq[j] = s * vx + c * vy;
+          }
+          if (lane == 0) atomicAdd(&s_rot, 1);
+        }
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (rot == 0) break;
+  }
+
+  // singular values
+  if (tid == 0) s_max = 0.0;
+  __syncthreads();
+  for (int i = warp; i < dp; i += nwarps) {
+    double a = 0.0;
+    for (int j = lane; j < dp; j += 32) { const double x = G[static_cast<size_t>(i) * dp + j]; a += x * x; }
+    a = warp_sum(a);
+    if (lane == 0) sig2[i] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = 0.0;
+    for (int i = 0; i < dp; ++i) mx = fmax(mx, sig2[i]);
+    s_max = mx;
+    if (info) { info[0] = sweep; }
+  }
+  __syncthreads();
+  const double cut = rcond * sqrt(s_max);
+  int rank = 0;
+  for (int idx = tid; idx < d * d; idx += kPinvThreads) {
+    const int a = idx / d, b = idx % d;
+    double acc = 0.0;
+    for (int i = 0; i < dp; ++i) {
+      const double s2 = sig2[i];
+      if (sqrt(s2) > cut) acc += Vt[static_cast<size_t>(i) * dp + a] * G[static_cast<size_t>(i) * dp + b] / s2;
+    }
+    out[idx] = acc;
+  }
+  if (tid == 0 && info) {
+    for (int i = 0; i < dp; ++i) rank += (sqrt(sig2[i]) > cut) ? 1 : 0;
+    info[1] = rank;
+  }
+}
+
+// ------------------------------------------------------------------ small fp64 GEMM with epilogues
+// C[i, k] = sum_j A[i, j] * B[j, k]   (A: [d, d] row-major, B/C: [d, K]);  |C| < zero_below -> 0
+// (datashapley.py:45 `coef[np.abs(coef) < 1e-10] = 0`).  Fixed j order: deterministic.
+constexpr int kDgemmTile = 32;
+__global__ void dgemm_dk_kernel(const double* __restrict__ A, const double* __restrict__ B, int64_t d, int64_t K,
+                                double zero_below, double* __restrict__ Cout) {
+  __shared__ double sA[kDgemmTile][kDgemmTile + 1];
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // blockDim = (32, 8)
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kDgemmTile;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // rows i0 + threadIdx.y + {0, 8, 16, 24}
+  for (int64_t j0 = 0; j0 < d; j0 += kDgemmTile) {
+    for (int t = threadIdx.y; t < kDgemmTile; t += 8) {
+      const int64_t i = i0 + t, j = j0 + threadIdx.x;
+      sA[t][threadIdx.x] = (i < d && j < d) ? A[i * d + j] : 0.0;
+    }
+    __syncthreads();
+    const int64_t jmax = (d - j0 < kDgemmTile) ? (d - j0) : kDgemmTile;
+    if (k < K) {
+      for (int64_t jj = 0; jj < jmax; ++jj) {
+        const double b = B[(j0 + jj) * K + k];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] += sA[threadIdx.y + 8 * t][jj] * b;
+      }
+    }
+    __syncthreads();
+  }
+  if (k < K) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int64_t i = i0 + threadIdx.y + 8 * t;
+      if (i < d) {
+        double v = acc[t];
+        if (fabs(v) < zero_below) v = 0.0;
+        Cout[i * K + k] = v;
+      }
+    }
+  }
+}
+
+// Shapley constraint step (datashapley.py:38-43):
+//   colsum = 1^T Ainv ; dd = 1^T Ainv 1 ; c_k = colsum . b[:,k] - v1_k + v0_k ; rhs[:,k] = b[:,k] - c_k / dd
+__global__ void shapley_colsum_kernel(const double* __restrict__ Ainv, int64_t d, double* __restrict__ colsum) {
+  // one block; colsum[d] holds dd
+  __shared__ double s_tot;
+  if (threadIdx.x == 0) s_tot = 0.0;
+  __syncthreads();
+  for (int64_t j = threadIdx.x; j < d; j += blockDim.x) {
+    double a = 0.0;
+    for (int64_t i = 0; i < d; ++i) a += Ainv[i * d + j];
+    colsum[j] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int64_t j = 0; j < d; ++j) t += colsum[j];
+    colsum[d] = t;
+  }
+}
+__global__ void shapley_rhs_kernel(const double* __restrict__ colsum, const double* __restrict__ b, int64_t d, int64_t K,
+                                   const double* __restrict__ v1, const double* __restrict__ v0,
+                                   double* __restrict__ rhs) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double c = 0.0;
+  for (int64_t i = 0; i < d; ++i) c += colsum[i] * b[i * K + k];
+  c = c - v1[k] + v0[k];
+  const double corr = c / colsum[d];
+  for (int64_t i = 0; i < d; ++i) rhs[i * K + k] = b[i * K + k] - corr;
+}
+
+// ------------------------------------------------------------------ Spearman / LDS
+// rho[e, k] = Spearman( pred[idx[e, :], k], y[idx[e, :], k] )  (average ranks for ties; NaN when a
+// side is constant -- scipy.stats.spearmanr semantics).  idx == nullptr: identity over the m rows.
+// One warp per (e, k); m_r <= kLdsMaxRows rows.
+constexpr int kLdsMaxRows = 1024;
+constexpr int kLdsPerLane = kLdsMaxRows / 32;
+__global__ void lds_spearman_kernel(const double* __restrict__ pred, const double* __restrict__ y, int64_t m, int64_t K,
+                                    const int32_t* __restrict__ idx, int64_t R, int64_t mr, double* __restrict__ rho) {
+  extern __shared__ double lds_smem[];  // [warps][2][mr]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t job = static_cast<int64_t>(blockIdx.x) * nw + warp;
+  if (job >= R * K) return;
+  const int64_t e = job / K, k = job % K;
+  double* sa = lds_smem + static_cast<size_t>(warp) * 2 * mr;
+  double* sb = sa + mr;
+  for (int64_t r = lane; r < mr; r += 32) {
+    const int64_t row = idx ? idx[e * mr + r] : r;
+    sa[r] = pred[row * K + k];
+    sb[r] = y[row * K + k];
+  }
+  __syncwarp();
+  const double mean = 0.5 * (static_cast<double>(mr) + 1.0);
+  double sab = 0.0, saa = 0.0, sbb = 0.0;
+  for (int64_t r = lane; r < mr; r += 32) {
+    const double a = sa[r], b = sb[r];
+    int la = 0, ea = 0, lb = 0, eb = 0;
+    for (int64_t t = 0; t < mr; ++t) {
+      const double at = sa[t], bt = sb[t];
+      la += (at < a); ea += (at == a);
+      lb += (bt < b); eb += (bt == b);
+    }
+    const double ra = la + 0.5 * (ea + 1) - mean;  // average rank (1-based) minus the mean rank
+    const double rb = lb + 0.5 * (eb + 1) - mean;
+    sab += ra * rb; saa += ra * ra; sbb += rb * rb;
+  }
+  sab = warp_sum(sab); saa = warp_sum(saa); sbb = warp_sum(sbb);
+  if (lane == 0) rho[job] = (sab / sqrt(saa)) / sqrt(sbb);  // corrcoef's two-step normalisation; 0/0 -> NaN
+}
+
+// lds[e] = mean_k(rho[e, k]) * 100  (sequential, fixed order)
+__global__ void lds_mean_kernel(const double* __restrict__ rho, int64_t R, int64_t K, double* __restrict__ out) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= R) return;
+  double s = 0.0;
+  for (int64_t k = 0; k < K; ++k) s += rho[e * K + k] * 100.0;
+  out[e] = s / static_cast<double>(K);
+}
+
+// ------------------------------------------------------------------ group reductions and ranks
+// out[g] = sum / mean / max over {values[i] : group[i] == g}, accumulated in fp64 in index order
+// (traks.py:188-204; attribution_utils.py:15-48).  One warp per group, lanes take strided slices and
+// are combined in a fixed tree => deterministic.
+template <typename T>
+__global__ void group_reduce_kernel(const T* __restrict__ values, const int32_t* __restrict__ group, int64_t N,
+                                    int64_t G, int mode, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= G) return;
+  double s = 0.0, mx = -INFINITY;
+  int64_t cnt = 0;
+  for (int64_t i = lane; i < N; i += 32) {
+    if (group[i] == g) {
+      const double v = static_cast<double>(values[i]);
+      s += v; mx = fmax(mx, v); ++cnt;
+    }
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) out[g] = (mode == 0) ? s : (mode == 1 ? s / static_cast<double>(cnt) : mx);
+}
+
+// rank[pos] = i where pos = #{j : x_j > x_i} + #{j < i : x_j == x_i}  == np.argsort(-x, kind="stable")
+// (NaNs sort last, in index order, as numpy does).
+__global__ void stable_rank_desc_kernel(const double* __restrict__ x, int64_t n, int64_t* __restrict__ rank) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double xi = x[i];
+  const bool nan_i = isnan(xi);
+  int64_t pos = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    const double xj = x[j];
+    const bool nan_j = isnan(xj);
+    bool before;
+    if (nan_i) before = !nan_j || j < i;
+    else before = !nan_j && (xj > xi || (xj == xi && j < i));
+    pos += before ? 1 : 0;
+  }
+  rank[pos] = i;
+}
+
+// row means of a [n, K] fp64 matrix (attrs_all.mean(axis=-1) before ranking, shapley_lds.py:294)
+__global__ void row_mean_kernel(const double* __restrict__ x, int64_t n, int64_t K, double* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int64_t k = 0; k < K; ++k) s += x[i * K + k];
+  out[i] = s / static_cast<double>(K);
+}
+
+}  // namespace agg
+}  // namespace gadm

@@ -14,6 +14,7 @@
 #include "gadm_ptx.cuh"
 #include "philox.cuh"
 #include "project.cuh"
+#include "aggregate.cuh"
 
 struct gadm_ctx {
   int device = 0;
@@ -283,6 +284,157 @@ int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_
       out, row0, nrows, proj_dim, (uint32_t)(seed64 & 0xFFFFFFFFull), (uint32_t)(seed64 >> 32), proj_type);
   GADM_CUDA(cudaGetLastError());
   h->launches++;
+  return GADM_OK;
+}
+
+// ------------------------------------------------------------------ aggregation
+
+#define GADM_LAUNCHED(h)           \
+  do {                             \
+    GADM_CUDA(cudaGetLastError()); \
+    (h)->launches++;               \
+  } while (0)
+
+int gadm_pack_masks(gadm_handle h, const uint8_t* x, int64_t n, int64_t d, uint32_t* rowbits, uint32_t* colbits,
+                    void* stream) {
+  GADM_REQUIRE(h && x && rowbits && colbits && n > 0 && d > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  const int64_t wd = (d + 31) / 32, wn = (n + 31) / 32;
+  const int64_t total = n * wd + d * wn;
+  gadm::agg::pack_masks_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, n, d, rowbits, wd,
+                                                                                             colbits, wn);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_mask_gram(gadm_handle h, const uint32_t* colbits, int64_t n, int64_t d, int mode, double* a, void* stream) {
+  GADM_REQUIRE(h && colbits && a && n > 0 && d > 0 && (mode == 0 || mode == 1), "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::agg::mask_gram_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, as_stream(stream)>>>(colbits, d, (n + 31) / 32,
+                                                                                            n, mode, a);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_mask_xty(gadm_handle h, const uint32_t* rowbits, const double* y, int64_t n, int64_t d, int64_t k,
+                  const double* shift, double half, double scale, double* out, void* stream) {
+  GADM_REQUIRE(h && rowbits && y && out && n > 0 && d > 0 && k > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  dim3 grid((unsigned)((k + 127) / 128), (unsigned)((d + gadm::agg::kXtyI - 1) / gadm::agg::kXtyI));
+  gadm::agg::mask_xty_kernel<<<grid, 128, 0, as_stream(stream)>>>(rowbits, (d + 31) / 32, y, n, d, k, shift, half,
+                                                                  scale, out);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_mask_times_matrix(gadm_handle h, const uint32_t* rowbits, const double* mat, int64_t m, int64_t d, int64_t k,
+                           double* out, void* stream) {
+  GADM_REQUIRE(h && rowbits && mat && out && m > 0 && d > 0 && k > 0 && m < 65536, "bad argument");
+  DeviceGuard guard(h->device);
+  dim3 grid((unsigned)((k + 127) / 128), (unsigned)m);
+  gadm::agg::mask_times_matrix_kernel<<<grid, 128, 0, as_stream(stream)>>>(rowbits, (d + 31) / 32, mat, m, d, k, out);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int64_t gadm_sym_pinv_workspace_bytes(int64_t d) {
+  const int64_t dp = (d + 1) & ~1ll;
+  return (2 * dp * dp + dp) * (int64_t)sizeof(double);
+}
+
+int gadm_sym_pinv(gadm_handle h, const double* a, int64_t d, double rcond, double* out, void* workspace,
+                  int64_t workspace_bytes, int* info, void* stream) {
+  GADM_REQUIRE(h && a && out && workspace && d > 0 && d <= 8192, "bad argument");
+  const int64_t need = gadm_sym_pinv_workspace_bytes(d);
+  if (workspace_bytes < need)
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)need);
+  DeviceGuard guard(h->device);
+  const int use_smem = need <= 200 * 1024;
+  auto kernel = gadm::agg::sym_pinv_kernel;
+  if (use_smem) GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  kernel<<<1, gadm::agg::kPinvThreads, use_smem ? (size_t)need : 0, as_stream(stream)>>>(
+      a, (int)d, rcond, out, reinterpret_cast<double*>(workspace), use_smem, info);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_dgemm_dk(gadm_handle h, const double* a, const double* b, int64_t d, int64_t k, double zero_below, double* c,
+                  void* stream) {
+  GADM_REQUIRE(h && a && b && c && d > 0 && k > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  dim3 grid((unsigned)((k + 31) / 32), (unsigned)((d + gadm::agg::kDgemmTile - 1) / gadm::agg::kDgemmTile));
+  gadm::agg::dgemm_dk_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(a, b, d, k, zero_below, c);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_shapley_rhs(gadm_handle h, const double* ainv, const double* b, int64_t d, int64_t k, const double* v1,
+                     const double* v0, double* colsum_work, double* rhs, void* stream) {
+  GADM_REQUIRE(h && ainv && b && v1 && v0 && colsum_work && rhs && d > 0 && k > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::agg::shapley_colsum_kernel<<<1, 256, 0, as_stream(stream)>>>(ainv, d, colsum_work);
+  GADM_LAUNCHED(h);
+  gadm::agg::shapley_rhs_kernel<<<(unsigned)((k + 127) / 128), 128, 0, as_stream(stream)>>>(colsum_work, b, d, k, v1, v0,
+                                                                                          rhs);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_lds_spearman(gadm_handle h, const double* pred, const double* y, int64_t m, int64_t k, const int32_t* idx,
+                      int64_t n_eval, int64_t rows_per_eval, double* rho, void* stream) {
+  GADM_REQUIRE(h && pred && y && rho && m > 0 && k > 0 && n_eval > 0, "bad argument");
+  if (!idx) GADM_REQUIRE(n_eval == 1 && rows_per_eval == m, "identity evaluation needs n_eval = 1, rows_per_eval = m");
+  GADM_REQUIRE(rows_per_eval > 0 && rows_per_eval <= gadm::agg::kLdsMaxRows, "rows_per_eval %lld out of range (1..%d)",
+               (long long)rows_per_eval, gadm::agg::kLdsMaxRows);
+  DeviceGuard guard(h->device);
+  int warps = 8;
+  while (warps > 1 && (size_t)warps * 2 * rows_per_eval * sizeof(double) > 48 * 1024) warps /= 2;
+  const size_t smem = (size_t)warps * 2 * rows_per_eval * sizeof(double);
+  const int64_t jobs = n_eval * k;
+  gadm::agg::lds_spearman_kernel<<<(unsigned)((jobs + warps - 1) / warps), warps * 32, smem, as_stream(stream)>>>(
+      pred, y, m, k, idx, n_eval, rows_per_eval, rho);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_lds_mean(gadm_handle h, const double* rho, int64_t n_eval, int64_t k, double* out, void* stream) {
+  GADM_REQUIRE(h && rho && out && n_eval > 0 && k > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::agg::lds_mean_kernel<<<(unsigned)((n_eval + 63) / 64), 64, 0, as_stream(stream)>>>(rho, n_eval, k, out);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_group_reduce(gadm_handle h, const void* values, int dtype, const int32_t* group, int64_t n, int64_t n_groups,
+                      int mode, double* out, void* stream) {
+  GADM_REQUIRE(h && values && group && out && n > 0 && n_groups > 0 && mode >= 0 && mode <= 2, "bad argument");
+  DeviceGuard guard(h->device);
+  const unsigned blocks = (unsigned)((n_groups + 3) / 4);
+  if (dtype == GADM_DTYPE_F32)
+    gadm::agg::group_reduce_kernel<float><<<blocks, 128, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float*>(values), group, n, n_groups, mode, out);
+  else if (dtype == GADM_DTYPE_F64)
+    gadm::agg::group_reduce_kernel<double><<<blocks, 128, 0, as_stream(stream)>>>(
+        reinterpret_cast<const double*>(values), group, n, n_groups, mode, out);
+  else
+    return fail(GADM_ERR_INVALID, "group_reduce supports f32 / f64 values, got dtype %d", dtype);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_stable_rank_desc(gadm_handle h, const double* x, int64_t n, int64_t* rank, void* stream) {
+  GADM_REQUIRE(h && x && rank && n > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::agg::stable_rank_desc_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(x, n, rank);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_row_mean(gadm_handle h, const double* x, int64_t n, int64_t k, double* out, void* stream) {
+  GADM_REQUIRE(h && x && out && n > 0 && k > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::agg::row_mean_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(x, n, k, out);
+  GADM_LAUNCHED(h);
   return GADM_OK;
 }
 

@@ -13,7 +13,7 @@
 //     UMMA smem layout from Philox4x32-10 (see philox.cuh), then published to the async proxy;
 //   * warp roles: 0 = TMA, 1 = MMA issue (leader CTA, one thread), 2 = TMEM alloc, 4-7 = epilogue
 //     (TMEM -> registers -> split-K partial tile in HBM), 8-15 = generators (4 groups of 2 warps,
-//     each group owns every 4th pipeline slot);
+//     group g owns pipeline slot g);
 //   * split-K partials are reduced in a fixed order by project_reduce_kernel => results do not
 //     depend on the schedule, the SM count or atomics.
 // kCtaGroup == 1 is the single-CTA variant of the same code (UMMA 128x256x16, 3 stages).
@@ -35,7 +35,6 @@ constexpr int kAccRows = 128; // gradient rows per CTA per accumulator
 constexpr int kNumAcc = 2;
 constexpr int kGenWarps = 8;
 constexpr int kWarpsPerGroup = 2;
-constexpr int kGenGroups = kGenWarps / kWarpsPerGroup;
 constexpr int kGroupThreads = kWarpsPerGroup * 32;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kFirstGenWarp = 8;
@@ -50,6 +49,9 @@ struct Cfg {
   static constexpr int kBBytes = kBRows * kBlockK * 2;                 // 16 / 32 KiB
   static constexpr int kStageBytes = kABytes + kBBytes;                // 48 / 64 KiB
   static constexpr int kStages = (kCtaGroup == 2) ? 4 : 3;
+  // One generator group per pipeline slot: a group only ever waits for the *next* phase of its own
+  // slot's barriers (mbarrier parity waits must never run more than one phase ahead).
+  static constexpr int kGenGroups = kStages;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
   static constexpr int kUnitRows = kNumAcc * kAccRows * kCtaGroup;     // rows of a full partial tile (512 / 256)
@@ -242,7 +244,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp >= kFirstGenWarp) {
     // ===================== generators: P tile (B operand) straight into the UMMA smem layout
     const int gw = warp - kFirstGenWarp;
-    const int group = gw / kWarpsPerGroup;
+    const int group = gw / kWarpsPerGroup;  // groups >= kGenGroups (single-CTA variant) stay idle
     const int tig = (gw % kWarpsPerGroup) * 32 + lane;
     uint32_t it = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
@@ -251,8 +253,8 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
       const uint32_t j0 = tile * kTileN + rank * C::kBRows;
       const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
       for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-        if (static_cast<int>(it % kGenGroups) != group) continue;
-        const int s = it % C::kStages;
+        if (static_cast<int>(it % C::kGenGroups) != group) continue;
+        const int s = group;
         const uint32_t ph = (it / C::kStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x500 + s);
         const uint32_t p_div64 = a.p_base_div64 + kb;

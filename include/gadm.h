@@ -83,6 +83,52 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
 int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_dim, uint64_t seed64, int proj_type,
                        float* out, void* stream);
 
+/* ---------------------------------------------------------------- subset-mask aggregation (fp64) */
+
+enum { GADM_GRAM_SHAPLEY = 0, GADM_GRAM_BANZHAF = 1 };
+enum { GADM_GROUP_SUM = 0, GADM_GROUP_MEAN = 1, GADM_GROUP_MAX = 2 };
+enum { GADM_DTYPE_F64 = 3 };
+
+/* X: uint8 [n, d] (0/1 subset masks as built at shapley_lds.py:114-119) -> bit-packed
+ * rowbits uint32 [n, ceil(d/32)] and colbits uint32 [d, ceil(n/32)] */
+int gadm_pack_masks(gadm_handle h, const uint8_t* x, int64_t n, int64_t d, uint32_t* rowbits, uint32_t* colbits,
+                    void* stream);
+/* A [d, d] fp64: mode SHAPLEY  A = X^T X / n (datashapley.py:29);
+ *                mode BANZHAF  A = (X - 1/2)^T (X - 1/2) (databanzhaf.py:19-22) -- exact from popcounts */
+int gadm_mask_gram(gadm_handle h, const uint32_t* colbits, int64_t n, int64_t d, int mode, double* a, void* stream);
+/* out[i, k] = (sum_r X[r,i] * (Y[r,k] - shift[k]) - half * sum_r (Y[r,k] - shift[k])) * scale ; Y [n, K], out [d, K]
+ * Shapley b_hat: shift = v0, half = 0, scale = 1/n ; Banzhaf rhs: shift = NULL, half = 0.5, scale = 1 */
+int gadm_mask_xty(gadm_handle h, const uint32_t* rowbits, const double* y, int64_t n, int64_t d, int64_t k,
+                  const double* shift, double half, double scale, double* out, void* stream);
+/* out[r, k] = sum_i X[r,i] * M[i,k]  (x_test @ attrs_all, shapley_lds.py:145) ; M [d, K], out [m, K] */
+int gadm_mask_times_matrix(gadm_handle h, const uint32_t* rowbits, const double* mat, int64_t m, int64_t d, int64_t k,
+                           double* out, void* stream);
+/* Moore-Penrose inverse of a symmetric matrix by one-sided Jacobi SVD; singular values <= rcond * max are
+ * dropped (numpy.linalg.pinv / lstsq cut-off semantics).  info (device int[2], may be NULL) = {sweeps, rank}. */
+int64_t gadm_sym_pinv_workspace_bytes(int64_t d);
+int gadm_sym_pinv(gadm_handle h, const double* a, int64_t d, double rcond, double* out, void* workspace,
+                  int64_t workspace_bytes, int* info, void* stream);
+/* C[i, k] = sum_j A[i, j] * B[j, k]; |C| < zero_below -> 0 (datashapley.py:45).  A [d, d], B and C [d, K]. */
+int gadm_dgemm_dk(gadm_handle h, const double* a, const double* b, int64_t d, int64_t k, double zero_below, double* c,
+                  void* stream);
+/* Efficiency-constraint step of closed-form KernelSHAP (datashapley.py:38-43):
+ * rhs[:, k] = b[:, k] - (1^T Ainv b[:, k] - v1[k] + v0[k]) / (1^T Ainv 1) ; colsum_work: d + 1 doubles */
+int gadm_shapley_rhs(gadm_handle h, const double* ainv, const double* b, int64_t d, int64_t k, const double* v1,
+                     const double* v0, double* colsum_work, double* rhs, void* stream);
+/* rho[e, k] = Spearman(pred[idx[e, :], k], y[idx[e, :], k]) with average ranks (scipy.stats.spearmanr);
+ * pred, y: [m, K]; idx: int32 [n_eval, rows_per_eval] or NULL (identity, n_eval = 1, rows_per_eval = m) */
+int gadm_lds_spearman(gadm_handle h, const double* pred, const double* y, int64_t m, int64_t k, const int32_t* idx,
+                      int64_t n_eval, int64_t rows_per_eval, double* rho, void* stream);
+/* out[e] = 100 * mean_k rho[e, k] */
+int gadm_lds_mean(gadm_handle h, const double* rho, int64_t n_eval, int64_t k, double* out, void* stream);
+/* out[g] = sum | mean | max of values[i] with group[i] == g, accumulated in fp64 (traks.py:188-204) */
+int gadm_group_reduce(gadm_handle h, const void* values, int dtype, const int32_t* group, int64_t n, int64_t n_groups,
+                      int mode, double* out, void* stream);
+/* rank = argsort(-x, kind="stable") as int64 (traks.py:218, shapley_lds.py:294) */
+int gadm_stable_rank_desc(gadm_handle h, const double* x, int64_t n, int64_t* rank, void* stream);
+/* out[i] = mean_k x[i, k] */
+int gadm_row_mean(gadm_handle h, const double* x, int64_t n, int64_t k, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

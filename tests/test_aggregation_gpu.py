@@ -1,0 +1,159 @@
+"""GPU parity of the Shapley / Banzhaf / LDS kernels against the reference-generated golden vectors and
+the CPU oracle.  Tolerances: attribution values |diff| <= 1e-9 * max(1, |ref|) (fp64, different summation
+order and a Jacobi instead of a LAPACK SVD); Spearman / LDS |diff| <= 1e-9; rankings and top-k indices
+bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import aggregation as oagg
+from oracle import scorer as oscore
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _close(got, want, tol=1e-9):
+    scale = np.maximum(1.0, np.abs(want))
+    assert np.all(np.abs(got - want) <= tol * scale), float(np.max(np.abs(got - want) / scale))
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_golden_shapley_banzhaf_lds(case):
+    import gadm_b200 as G
+
+    g = np.load(os.path.join(GOLDEN, "aggregation_golden.npz"))
+    Xs, Ys, Xu, Yu = g[f"{case}_Xs"], g[f"{case}_Ys"], g[f"{case}_Xu"], g[f"{case}_Yu"]
+    v0, v1 = g[f"{case}_v0"], g[f"{case}_v1"]
+    d, K = Xs.shape[1], Ys.shape[1]
+    phi_s = G.data_shapley_batched(Xs, Ys, v1, v0)
+    phi_b = G.data_banzhaf_batched(Xu, Yu)
+    tol = 1e-9 if case != "c" else 1e-7  # c: n < d, rank-deficient normal equations (pinv / min-norm lstsq)
+    _close(phi_s, g[f"{case}_phi_shapley"], tol)
+    _close(phi_b, g[f"{case}_phi_banzhaf"], tol)
+    # per-behaviour wrappers with the reference signatures and return shapes
+    one = G.data_shapley(d, Xs, Ys[:, 1], v1[1], v0[1])
+    assert one.shape == (d, 1)
+    _close(one[:, 0], g[f"{case}_phi_shapley"][:, 1], tol)
+    oneb = G.data_banzhaf(x_train=Xu, y_train=Yu[:, 2])
+    assert oneb.shape == (d,)
+    _close(oneb, g[f"{case}_phi_banzhaf"][:, 2], tol)
+    # LDS on the reference's attributions (isolates the Spearman path) and on ours
+    tests = [(g[f"{case}_Xt{t}"], g[f"{case}_Yt{t}"]) for t in range(3)]
+    _close(np.array(G.evaluate_lds(g[f"{case}_phi_shapley"], tests, K)), g[f"{case}_lds_shapley"], 1e-9)
+    _close(np.array(G.evaluate_lds(g[f"{case}_phi_banzhaf"], tests, K)), g[f"{case}_lds_banzhaf"], 1e-9)
+    _close(np.array(G.evaluate_lds(phi_s, tests, K)), g[f"{case}_lds_shapley"], 1e-6)
+    # rankings bit-exact (shapley_lds.py:294)
+    np.testing.assert_array_equal(G.stable_rank(phi_s), oscore.stable_rank(g[f"{case}_phi_shapley"]))
+    np.testing.assert_array_equal(G.stable_rank(g[f"{case}_phi_banzhaf"]), oscore.stable_rank(g[f"{case}_phi_banzhaf"]))
+
+
+def test_lds_py_convention_and_bootstrap_statistic():
+    import gadm_b200 as G
+
+    g = np.load(os.path.join(GOLDEN, "lds_py_golden.npz"))
+    attrs = g["attrs"]
+    tests = [(g[f"Xt{t}"], g[f"Yt{t}"]) for t in range(3)]
+    got = G.evaluate_lds(list(attrs), tests, attrs.shape[0])
+    _close(np.array(got), g["lds"], 1e-9)
+    got2 = G.evaluate_lds(attrs, tests, attrs.shape[0], index_first=True)
+    _close(np.array(got2), g["lds"], 1e-9)
+    # vectorised bootstrap statistic == the reference's closure (lds.py:460-471) on the same index rows
+    X, Y = tests[0]
+    stat = G.bootstrap_statistic(X, Y, list(attrs))
+    rng = np.random.RandomState(0)
+    idx = rng.randint(0, X.shape[0], size=(7, X.shape[0]))
+    want = []
+    from scipy.stats import spearmanr
+    for row in idx:
+        want.append(np.mean([spearmanr(X[row] @ attrs[i], Y[row, i]).statistic * 100 for i in range(attrs.shape[0])]))
+    _close(stat(idx), np.array(want), 1e-9)
+    assert stat(idx[0]).shape == ()
+
+
+def test_spearman_ties_and_constant_input():
+    import gadm_b200 as G
+    from scipy.stats import spearmanr
+
+    rng = np.random.RandomState(3)
+    m, d, K = 57, 9, 6
+    X = (rng.rand(m, d) > 0.5).astype(float)
+    attrs = np.round(rng.normal(size=(d, K)), 1)  # ties in the predictions
+    attrs[:, 4] = 0.0  # constant prediction -> NaN
+    Y = np.round(rng.normal(size=(m, K)), 0)  # heavy ties
+    Y[:, 5] = 2.0  # constant behaviour -> NaN
+    got = G.spearman_matrix(X, Y, attrs)[0]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.array([spearmanr(X @ attrs[:, k], Y[:, k]).statistic for k in range(K)])
+    assert np.isnan(got[4]) and np.isnan(got[5]) and np.isnan(want[4]) and np.isnan(want[5])
+    _close(got[:4], want[:4], 1e-12)
+
+
+def test_config5_size_against_oracle():
+    """BASELINE config 5: 1k masks x 100 contributors x 1k behaviours, 3 x 100 test subsets."""
+    import gadm_b200 as G
+
+    n, d, K, m = 1000, 100, 1000, 100
+    rng = np.random.RandomState(0)
+    Xs = oagg.shapley_masks(d, list(range(n)))
+    Xu = oagg.uniform_masks(d, list(range(n)))
+    w = rng.normal(size=(d, K))
+    Ys = Xs @ w + 0.1 * rng.normal(size=(n, K))
+    Yu = Xu @ w + 0.1 * rng.normal(size=(n, K))
+    v0 = np.zeros(K)
+    v1 = w.sum(axis=0)
+    phi_s = G.data_shapley_batched(Xs, Ys, v1, v0)
+    phi_b = G.data_banzhaf_batched(Xu, Yu)
+    ks = [0, 1, 17, 500, 999]
+    for k in ks:
+        _close(phi_s[:, k], oagg.data_shapley(d, Xs, Ys[:, k], v1[k], v0[k]).flatten(), 1e-9)
+        _close(phi_b[:, k], oagg.data_banzhaf(Xu, Yu[:, k]), 1e-9)
+    assert np.max(np.abs(phi_s.sum(axis=0) - (v1 - v0))) < 1e-9  # efficiency
+    tests = []
+    for t in range(3):
+        Xt = oagg.datamodel_masks(d, list(range(5000 + 100 * t, 5000 + 100 * t + m)))
+        tests.append((Xt, Xt @ w + 0.5 * rng.normal(size=(m, K))))
+    got = G.evaluate_lds(phi_s, tests, K)
+    want = oagg.evaluate_lds(phi_s, tests, K)
+    _close(np.array(got), np.array(want), 1e-9)
+    np.testing.assert_array_equal(G.stable_rank(phi_s), oscore.stable_rank(phi_s))
+
+
+def test_sym_pinv_rank_deficient_and_large():
+    import torch
+    import gadm_b200 as G
+
+    rng = np.random.RandomState(1)
+    for d, r in ((30, 12), (130, 130), (258, 200)):
+        B = rng.normal(size=(d, r))
+        A = B @ B.T / r
+        got, info = G.sym_pinv(torch.as_tensor(A).cuda(), 1e-15, return_info=True)
+        want = np.linalg.pinv(A)
+        scale = np.abs(want).max()
+        assert np.abs(got.cpu().numpy() - want).max() <= 1e-8 * scale, (d, r)
+        assert int(info[1]) == r
+
+
+def test_group_reduce_and_ranks_vs_traks_golden():
+    import gadm_b200 as G
+
+    g = np.load(os.path.join(GOLDEN, "traks_golden.npz"))
+    groups = g["in_groups"]
+    ngroups = int(groups.max()) + 1
+    ref = oscore.score_torch(g["in_train_loss"], g["in_gen_loss"], journey_grads=g["in_journey"])
+    for name in ("trak", "relative_influence", "renorm_influence", "journey_trak"):
+        got = G.group_reduce(ref[name], groups, ngroups, "sum")
+        want = g[f"out_artist_{name}"][:, 0]
+        assert np.all(np.abs(got - want) <= 2e-5 * np.maximum(1e-3, np.abs(want)))
+        np.testing.assert_array_equal(G.stable_rank(g[f"out_artist_{name}"]),
+                                      g[f"out_all_generated_images_artist_rank_{name}"])
+    got_avg = G.group_reduce(ref["grad_sim"], groups, ngroups, "mean")
+    got_max = G.group_reduce(ref["grad_sim"], groups, ngroups, "max")
+    assert np.allclose(got_avg, g["out_artist_avg_grad_sim"][:, 0], rtol=2e-5, atol=1e-7)
+    assert np.allclose(got_max, g["out_artist_max_grad_sim"][:, 0], rtol=2e-5, atol=1e-7)
+    # ties resolve to the lower index; NaNs last
+    x = np.array([1.0, 3.0, 3.0, np.nan, -2.0, 3.0, 1.0])
+    np.testing.assert_array_equal(G.stable_rank(x), np.argsort(-x, kind="stable"))
