@@ -1,0 +1,301 @@
+// fp32-grade GEMM on the 5th-gen tensor cores:  C[M, N] = alpha * A[M, K] * B[N, K]^T + beta * C
+// A and B are plain fp32, row-major with the contraction index contiguous ("TN" form, both K-major).
+//
+// Used for every dense product of the TRAK scorer (text_to_image/traks.py:141-186 torch.matmul calls;
+// src/attributions/methods/compute_gradient_score.py:75-79,108-126): Gram Phi^T Phi, Cholesky trailing
+// updates and triangular solves, Z = Phi_gen K^-1 and the score GEMM S = Z Phi^T.
+//
+// Precision: the reference computes these in fp32 (fp64 for the unconditional inverse), so a single
+// TF32 pass (10-bit mantissa) is not enough.  Each operand tile is split in shared memory into
+// hi = x & 0xffffe000 (exactly representable in TF32) and lo = x - hi (exact in fp32), and the MMA warp
+// issues three tcgen05.mma.kind::tf32 per K-step: hi*hi + hi*lo + lo*hi (the lo*lo term, <= 2^-20
+// relative, is dropped) -- "3xTF32", fp32 accumulation in TMEM.
+//
+// Pipeline per CTA (one 128 x 128 output tile, 3 stages of K = 32):
+//   warp 0   TMA: raw fp32 tiles of A and B (128B swizzle)            -> raw_full[s]
+//   warps 8-15 split raw -> hi (in place) + lo, fence.proxy.async     -> split_full[s]
+//   warp 1   MMA issue (one thread), tcgen05.commit                   -> empty[s], acc_full
+//   warps 4-7 epilogue: tcgen05.ld -> alpha/beta/diag-shift -> global
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "gadm_ptx.cuh"
+
+namespace gadm {
+namespace gemm {
+
+constexpr int kBM = 128;
+constexpr int kBN = 128;
+constexpr int kBK = 32;     // fp32 elements per smem row = 128 B
+constexpr int kUmmaK = 8;   // tf32
+constexpr int kStages = 3;
+constexpr int kTileBytes = kBM * kBK * 4;                 // 16 KiB (A and B tiles have the same shape)
+constexpr int kStageBytes = 4 * kTileBytes;               // rawA(hi) | rawB(hi) | loA | loB
+constexpr int kSplitWarps = 8;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kFirstSplitWarp = 8;
+constexpr int kThreads = (kFirstSplitWarp + kSplitWarps) * 32;
+constexpr int kTmemCols = 128;
+constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+
+struct Args {
+  float* C;
+  int64_t ldc;
+  int32_t M, N, K;
+  float alpha, beta;
+  float diag_add;     // added to C[i, i] (global indices, after alpha/beta)
+  int32_t lower_only; // skip tiles entirely above the diagonal
+};
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = x & 0xFFFFE000u;
+  lo = __float_as_uint(__fsub_rn(__uint_as_float(x), __uint_as_float(hi)));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  if (a.lower_only && tile_n * kBN > tile_m * kBM + (kBM - 1)) return;  // whole CTA exits together
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };
+  auto split_full = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  const uint32_t acc_full = bar_base + 8u * (3 * kStages);
+  const uint32_t tmem_slot = acc_full + 8u;
+  auto hi_a = [&](int s) { return smem_base + s * kStageBytes; };
+  auto hi_b = [&](int s) { return smem_base + s * kStageBytes + kTileBytes; };
+  auto lo_a = [&](int s) { return smem_base + s * kStageBytes + 2 * kTileBytes; };
+  auto lo_b = [&](int s) { return smem_base + s * kStageBytes + 3 * kTileBytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (a.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(split_full(s), kSplitWarps);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u, 0x1100 + s);
+        mbar_arrive_expect_tx(raw_full(s), 2 * kTileBytes);
+        tma_load_2d(hi_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM);
+        tma_load_2d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, kBM, kBN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1u;
+        mbar_wait(split_full(s), ph, 0x1200 + s);
+        tcgen05_fence_after();
+        const uint64_t dha = umma_desc_kmajor_sw128(hi_a(s)), dhb = umma_desc_kmajor_sw128(hi_b(s));
+        const uint64_t dla = umma_desc_kmajor_sw128(lo_a(s)), dlb = umma_desc_kmajor_sw128(lo_b(s));
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+          umma_tf32(tmem_base, dla + 2u * k, dhb + 2u * k, idesc, first);  // small terms first
+          umma_tf32(tmem_base, dha + 2u * k, dlb + 2u * k, idesc, 1u);
+          umma_tf32(tmem_base, dha + 2u * k, dhb + 2u * k, idesc, 1u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstSplitWarp) {
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0, 0x1300);
+    tcgen05_fence_after();
+    const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
+    const int64_t col0 = static_cast<int64_t>(tile_n) * kBN;
+#pragma unroll 1
+    for (int c = 0; c < kBN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (row < a.M) {
+        float* crow = a.C + row * a.ldc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int64_t col = col0 + c + i;
+          if (col < a.N) {
+            float r = a.alpha * __uint_as_float(v[i]);
+            if (a.beta != 0.f) r += a.beta * crow[col];
+            if (col == row) r += a.diag_add;
+            crow[col] = r;
+          }
+        }
+      }
+    }
+  } else if (warp >= kFirstSplitWarp) {
+    const int t = threadIdx.x - kFirstSplitWarp * 32;  // 0..255
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1u;
+      mbar_wait(raw_full(s), ph, 0x1400 + s);
+      // raw A|B are contiguous (2 * kTileBytes), lo A|B follow at +2*kTileBytes: purely elementwise, the
+      // swizzle is a function of the address bits inside each 1024-B atom and is identical for hi and lo.
+      const uint32_t raw = hi_a(s);
+#pragma unroll 4
+      for (int i = 0; i < (2 * kTileBytes) / 16 / (kSplitWarps * 32); ++i) {
+        const uint32_t off = (static_cast<uint32_t>(i) * (kSplitWarps * 32) + t) * 16u;
+        const uint4 x = ld_shared_v4(raw + off);
+        uint4 hi, lo;
+        split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
+        split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+        st_shared_v4(raw + off, hi);
+        st_shared_v4(raw + 2 * kTileBytes + off, lo);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(split_full(s));
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------ helpers around the GEMM
+
+// out[c, r] = in[r, c]; in: [R, C] pitch ld_in; out: [C, R_pad] pitch ld_out (columns R..ld_out untouched)
+__global__ void transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t ld_in,
+                                 float* __restrict__ out, int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32, r0 = static_cast<int64_t>(blockIdx.y) * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Ccols) ? in[r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Ccols && r < R) out[c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+// Cholesky of one nb x nb diagonal block (nb <= 128), in place (lower; strict upper zeroed), plus the
+// inverse of the factor and its transpose (dense nb x nb, pitch 128) for the GEMM-based panel solves.
+constexpr int kPotrfNb = 128;
+constexpr int kPotrfLd = kPotrfNb + 1;
+constexpr int kPotrfSmem = 2 * kPotrfNb * kPotrfLd * 4;
+__global__ void __launch_bounds__(kPotrfNb, 1)
+potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__ linv, float* __restrict__ linv_t,
+                  int* __restrict__ info, int block_index) {
+  extern __shared__ float potrf_smem[];
+  float* L = potrf_smem;                       // [nb][kPotrfLd]
+  float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse
+  const int i = threadIdx.x;
+  for (int r = 0; r < nb; ++r)
+    if (i < nb) L[r * kPotrfLd + i] = A[static_cast<int64_t>(r) * ld + i];
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    double s = 0.0;
+    if (i >= j && i < nb) {
+      s = static_cast<double>(L[i * kPotrfLd + j]);
+      for (int t = 0; t < j; ++t) s -= static_cast<double>(L[i * kPotrfLd + t]) * static_cast<double>(L[j * kPotrfLd + t]);
+    }
+    __shared__ double s_diag;
+    if (i == j) {
+      if (!(s > 0.0)) { if (info) atomicMax(info, block_index * kPotrfNb + j + 1); s = 1.0; }
+      s_diag = sqrt(s);
+    }
+    __syncthreads();
+    if (i >= j && i < nb) L[i * kPotrfLd + j] = (i == j) ? static_cast<float>(s_diag) : static_cast<float>(s / s_diag);
+    __syncthreads();
+  }
+  // inverse of the lower factor, column i per thread (forward substitution)
+  if (i < nb) {
+    for (int r = 0; r < nb; ++r) {
+      double s = (r == i) ? 1.0 : 0.0;
+      if (r < i) { X[r * kPotrfLd + i] = 0.f; continue; }
+      for (int t = i; t < r; ++t) s -= static_cast<double>(L[r * kPotrfLd + t]) * static_cast<double>(X[t * kPotrfLd + i]);
+      X[r * kPotrfLd + i] = static_cast<float>(s / static_cast<double>(L[r * kPotrfLd + r]));
+    }
+  }
+  __syncthreads();
+  for (int r = 0; r < kPotrfNb; ++r) {
+    const bool in = (r < nb && i < nb);
+    if (in) A[static_cast<int64_t>(r) * ld + i] = (i <= r) ? L[r * kPotrfLd + i] : 0.f;
+    const float x = in ? X[r * kPotrfLd + i] : ((r == i) ? 1.f : 0.f);  // identity padding keeps the block invertible
+    linv[r * kPotrfNb + i] = x;
+    linv_t[i * kPotrfNb + r] = x;
+  }
+}
+
+// out[r] = ||x[r, :]||_2 (or its reciprocal), fp32 data, fp64 accumulation; one warp per row
+__global__ void row_norms_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int reciprocal,
+                                 float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  double s = 0.0;
+  for (int64_t c = lane; c < cols; c += 32) { const double v = x[r * ld + c]; s += v * v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = static_cast<float>(reciprocal ? 1.0 / sqrt(s) : sqrt(s));
+}
+
+// out[n] = mean_t S[t, n] * row_scale[t] * col_scale[n]   (traks.py:146,157,162-168), fp64 accumulation
+__global__ void col_mean_scaled_kernel(const float* __restrict__ S, int64_t T, int64_t N, int64_t ld,
+                                       const float* __restrict__ row_scale, const float* __restrict__ col_scale,
+                                       float* __restrict__ out) {
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double s = 0.0;
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = S[t * ld + n];
+    s += row_scale ? static_cast<double>(v) * row_scale[t] : static_cast<double>(v);
+  }
+  s /= static_cast<double>(T);
+  if (col_scale) s *= col_scale[n];
+  out[n] = static_cast<float>(s);
+}
+
+// S[t, n] *= row_scale[t] * col_scale[n]  (compute_gradient_score.py:114-126 "scores / magnitude")
+__global__ void scale_rows_cols_kernel(float* __restrict__ S, int64_t T, int64_t N, int64_t ld,
+                                       const float* __restrict__ row_scale, const float* __restrict__ col_scale) {
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t t = blockIdx.y;
+  if (n >= N || t >= T) return;
+  float v = S[t * ld + n];
+  if (row_scale) v *= row_scale[t];
+  if (col_scale) v *= col_scale[n];
+  S[t * ld + n] = v;
+}
+
+}  // namespace gemm
+}  // namespace gadm
