@@ -3,6 +3,9 @@ from .projectors import BasicProjector, CudaProjector, DeferredProjection, Proje
 from .aggregation import (PackedMasks, bootstrap_statistic, data_banzhaf, data_banzhaf_batched, data_shapley,  # noqa: F401
                           data_shapley_batched, evaluate_lds, group_reduce, lds_per_test_set, spearman_matrix,
                           stable_rank, sym_pinv)
+from .scoring import (TrakScorer, aggregate_by_class, col_mean_scaled, compute_dtrak_trak_scores,  # noqa: F401
+                      compute_gradient_scores, gemm_tn, gradient_scores, group_and_rank, row_norms, trak_scores,
+                      transpose)
 from ._lib import GadmError, load_library  # noqa: F401
 
 __all__ = [
@@ -10,5 +13,7 @@ __all__ = [
     "PackedMasks", "bootstrap_statistic", "data_banzhaf", "data_banzhaf_batched", "data_shapley",
     "data_shapley_batched", "evaluate_lds", "group_reduce", "lds_per_test_set", "spearman_matrix", "stable_rank",
     "sym_pinv",
+    "TrakScorer", "aggregate_by_class", "col_mean_scaled", "compute_dtrak_trak_scores", "compute_gradient_scores",
+    "gemm_tn", "gradient_scores", "group_and_rank", "row_norms", "trak_scores", "transpose",
     "GadmError", "load_library",
 ]

@@ -26,6 +26,15 @@ _SIGNATURES = {
     "gadm_project_staged": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_i64,
                                       C.c_int, c_vp, c_i64, C.c_int, c_vp]),
     "gadm_materialize_p": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_vp]),
+    "gadm_gemm_tn": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_float, C.c_float,
+                               C.c_float, C.c_int, c_vp]),
+    "gadm_transpose": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "gadm_cholesky_workspace_bytes": (c_i64, [c_i64]),
+    "gadm_cholesky": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),
+    "gadm_solve_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
+    "gadm_row_norms": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp]),
+    "gadm_col_mean_scaled": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "gadm_scale_rows_cols": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "gadm_pack_masks": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "gadm_mask_gram": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
     "gadm_mask_xty": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, C.c_double, C.c_double, c_vp, c_vp]),

@@ -15,6 +15,7 @@
 #include "philox.cuh"
 #include "project.cuh"
 #include "aggregate.cuh"
+#include "gemm.cuh"
 
 struct gadm_ctx {
   int device = 0;
@@ -47,6 +48,12 @@ int fail(int code, const char* fmt, ...) {
 #define GADM_REQUIRE(cond, ...)                       \
   do {                                                \
     if (!(cond)) return fail(GADM_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define GADM_LAUNCHED(h)           \
+  do {                             \
+    GADM_CUDA(cudaGetLastError()); \
+    (h)->launches++;               \
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -287,13 +294,154 @@ int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_
   return GADM_OK;
 }
 
-// ------------------------------------------------------------------ aggregation
+// ------------------------------------------------------------------ scorer
 
-#define GADM_LAUNCHED(h)           \
-  do {                             \
-    GADM_CUDA(cudaGetLastError()); \
-    (h)->launches++;               \
+#define GADM_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != GADM_OK) return _rc; \
   } while (0)
+
+int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
+                 int64_t m, int64_t n, int64_t k, float alpha, float beta, float diag_add, int lower_only,
+                 void* stream) {
+  GADM_REQUIRE(h && a && b && c, "null argument");
+  GADM_REQUIRE(m > 0 && n > 0 && k > 0 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "bad shape");
+  GADM_REQUIRE(lda >= k && ldb >= k && ldc >= n && lda % 4 == 0 && ldb % 4 == 0, "bad leading dimension");
+  DeviceGuard guard(h->device);
+  CUtensorMap ta, tb;
+  GADM_TRY(make_tmap_2d(h, &ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda * 4,
+                        gadm::gemm::kBK, gadm::gemm::kBM));
+  GADM_TRY(make_tmap_2d(h, &tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb * 4,
+                        gadm::gemm::kBK, gadm::gemm::kBN));
+  gadm::gemm::Args args;
+  args.C = c; args.ldc = ldc;
+  args.M = (int32_t)m; args.N = (int32_t)n; args.K = (int32_t)k;
+  args.alpha = alpha; args.beta = beta; args.diag_add = diag_add; args.lower_only = lower_only;
+  auto kernel = gadm::gemm::gemm_tn_3xtf32_kernel;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((n + gadm::gemm::kBN - 1) / gadm::gemm::kBN), (unsigned)((m + gadm::gemm::kBM - 1) / gadm::gemm::kBM));
+  GADM_REQUIRE(grid.y < 65536, "too many row tiles (%u)", grid.y);
+  kernel<<<grid, gadm::gemm::kThreads, gadm::gemm::kSmemBytes, as_stream(stream)>>>(ta, tb, args);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                   int64_t ld_out, void* stream) {
+  GADM_REQUIRE(h && in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "bad argument");
+  DeviceGuard guard(h->device);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  GADM_REQUIRE(grid.y < 65536, "too many row tiles");
+  gadm::gemm::transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, rows, cols, ld_in, out, ld_out);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int64_t gadm_cholesky_workspace_bytes(int64_t k) {
+  const int64_t nblk = (k + gadm::gemm::kPotrfNb - 1) / gadm::gemm::kPotrfNb;
+  return 2 * nblk * gadm::gemm::kPotrfNb * gadm::gemm::kPotrfNb * (int64_t)sizeof(float);
+}
+
+int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, int64_t blocks_bytes, int* info,
+                  void* stream) {
+  GADM_REQUIRE(h && a && blocks && k > 0 && ld >= k && ld % 4 == 0, "bad argument");
+  if (blocks_bytes < gadm_cholesky_workspace_bytes(k))
+    return fail(GADM_ERR_WORKSPACE, "blocks workspace %lld B < required %lld B", (long long)blocks_bytes,
+                (long long)gadm_cholesky_workspace_bytes(k));
+  DeviceGuard guard(h->device);
+  constexpr int NB = gadm::gemm::kPotrfNb;
+  const int64_t nblk = (k + NB - 1) / NB;
+  float* linv = reinterpret_cast<float*>(blocks);
+  float* linv_t = linv + nblk * NB * NB;
+  auto potrf = gadm::gemm::potrf_diag_kernel;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GADM_CUDA(cudaFuncSetAttribute(potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kPotrfSmem));
+    attr_set = true;
+  }
+  if (info) GADM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), as_stream(stream)));
+  for (int64_t b = 0; b < nblk; ++b) {
+    const int64_t j0 = b * NB;
+    const int nb = (int)((k - j0) < NB ? (k - j0) : NB);
+    potrf<<<1, NB, gadm::gemm::kPotrfSmem, as_stream(stream)>>>(a + j0 * ld + j0, ld, nb, linv + b * NB * NB,
+                                                               linv_t + b * NB * NB, info, (int)b);
+    GADM_LAUNCHED(h);
+    const int64_t rem = k - (j0 + nb);
+    if (rem > 0) {
+      float* panel = a + (j0 + nb) * ld + j0;
+      // panel <- panel * L_jj^-T   (in place: one column tile, each CTA owns its rows)
+      GADM_TRY(gadm_gemm_tn(h, panel, ld, linv + b * NB * NB, NB, panel, ld, rem, nb, nb, 1.f, 0.f, 0.f, 0, stream));
+      // trailing update (lower tiles only): A22 -= panel * panel^T
+      float* trail = a + (j0 + nb) * ld + (j0 + nb);
+      GADM_TRY(gadm_gemm_tn(h, panel, ld, panel, ld, trail, ld, rem, rem, nb, -1.f, 1.f, 0.f, 1, stream));
+    }
+  }
+  return GADM_OK;
+}
+
+int gadm_solve_rows(gadm_handle h, const float* l, int64_t ldl, const float* u, int64_t ldu, const void* blocks,
+                    int64_t k, float* y, int64_t ldy, int64_t m, void* stream) {
+  GADM_REQUIRE(h && l && u && blocks && y && k > 0 && m > 0, "bad argument");
+  GADM_REQUIRE(ldl >= k && ldu >= k && ldy >= k && ldl % 4 == 0 && ldu % 4 == 0 && ldy % 4 == 0, "bad leading dimension");
+  constexpr int NB = gadm::gemm::kPotrfNb;
+  const int64_t nblk = (k + NB - 1) / NB;
+  const float* linv = reinterpret_cast<const float*>(blocks);
+  const float* linv_t = linv + nblk * NB * NB;
+  // forward: y <- y L^-T
+  for (int64_t b = 0; b < nblk; ++b) {
+    const int64_t i0 = b * NB;
+    const int64_t nb = (k - i0) < NB ? (k - i0) : NB;
+    if (i0 > 0) GADM_TRY(gadm_gemm_tn(h, y, ldy, l + i0 * ldl, ldl, y + i0, ldy, m, nb, i0, -1.f, 1.f, 0.f, 0, stream));
+    GADM_TRY(gadm_gemm_tn(h, y + i0, ldy, linv + b * NB * NB, NB, y + i0, ldy, m, nb, nb, 1.f, 0.f, 0.f, 0, stream));
+  }
+  // backward: y <- y L^-1
+  for (int64_t b = nblk - 1; b >= 0; --b) {
+    const int64_t i0 = b * NB;
+    const int64_t nb = (k - i0) < NB ? (k - i0) : NB;
+    const int64_t i1 = i0 + nb;
+    if (i1 < k)
+      GADM_TRY(gadm_gemm_tn(h, y + i1, ldy, u + i0 * ldu + i1, ldu, y + i0, ldy, m, nb, k - i1, -1.f, 1.f, 0.f, 0, stream));
+    GADM_TRY(gadm_gemm_tn(h, y + i0, ldy, linv_t + b * NB * NB, NB, y + i0, ldy, m, nb, nb, 1.f, 0.f, 0.f, 0, stream));
+  }
+  return GADM_OK;
+}
+
+int gadm_row_norms(gadm_handle h, const float* x, int64_t rows, int64_t cols, int64_t ld, int reciprocal, float* out,
+                   void* stream) {
+  GADM_REQUIRE(h && x && out && rows > 0 && cols > 0 && ld >= cols, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::gemm::row_norms_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, rows, cols, ld, reciprocal,
+                                                                                        out);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_col_mean_scaled(gadm_handle h, const float* s, int64_t t, int64_t n, int64_t ld, const float* row_scale,
+                         const float* col_scale, float* out, void* stream) {
+  GADM_REQUIRE(h && s && out && t > 0 && n > 0 && ld >= n, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::gemm::col_mean_scaled_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(s, t, n, ld, row_scale,
+                                                                                               col_scale, out);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_scale_rows_cols(gadm_handle h, float* s, int64_t t, int64_t n, int64_t ld, const float* row_scale,
+                         const float* col_scale, void* stream) {
+  GADM_REQUIRE(h && s && t > 0 && n > 0 && ld >= n && t < 65536, "bad argument");
+  DeviceGuard guard(h->device);
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)t);
+  gadm::gemm::scale_rows_cols_kernel<<<grid, 256, 0, as_stream(stream)>>>(s, t, n, ld, row_scale, col_scale);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+// ------------------------------------------------------------------ aggregation
 
 int gadm_pack_masks(gadm_handle h, const uint8_t* x, int64_t n, int64_t d, uint32_t* rowbits, uint32_t* colbits,
                     void* stream) {

@@ -1,0 +1,403 @@
+"""TRAK / D-TRAK / influence scoring on sm_100a kernels, behind the reference's interfaces.
+
+Reference arithmetic (all restated in oracle/scorer.py and pinned on golden vectors):
+  text_to_image/traks.py:141-186         grad_sim, TRAK, relative / renormalised influence, journey-TRAK, D-TRAK
+  src/attributions/methods/compute_gradient_score.py:13-139    numpy / fp64 version with the kernel cache
+  unconditional_generation/attribute.py:15,150-152             imports a missing compute_dtrak_trak_scores
+
+What changes under the hood: K = Phi^T Phi + lam*I is factored once by a blocked Cholesky (tensor-core
+3xTF32 trailing updates) and applied to right-hand-side rows by blocked triangular solves; the explicit
+inverse of the reference (torch.inverse / np.linalg.inv) is only formed when a caller asks for it
+(kernel cache compatibility).  With ``torch.distributed`` initialised, training examples are sharded by
+row: one all-reduce of the Gram matrix, identical factorisation on every rank, local score slices
+[T, N/R], optional all-gather.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .aggregation import group_reduce, stable_rank
+
+_f32 = torch.float32
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (sm_100a); there is no CPU path")
+    if t.dtype != _f32:
+        t = t.float()
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D, got {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.data_ptr() % 16 != 0:
+        cols = t.shape[1]
+        ld = -(-cols // 4) * 4
+        buf = torch.zeros(t.shape[0], ld, dtype=_f32, device=t.device)
+        buf[:, :cols] = t
+        t = buf[:, :cols]
+    return t
+
+
+def _h(t: torch.Tensor):
+    return _lib.get_handle(t.device)
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, alpha: float = 1.0, beta: float = 0.0,
+            diag_add: float = 0.0, lower_only: bool = False) -> torch.Tensor:
+    """out = alpha * a @ b.T + beta * out  (fp32-grade accuracy, 3xTF32 tcgen05 kernel)."""
+    a = _check_cuda_f32(a, "a")
+    b = _check_cuda_f32(b, "b")
+    if a.shape[1] != b.shape[1]:
+        raise ValueError(f"contraction mismatch: {tuple(a.shape)} x {tuple(b.shape)}^T")
+    m, n, k = a.shape[0], b.shape[0], a.shape[1]
+    if out is None:
+        out = torch.zeros(m, n, dtype=_f32, device=a.device) if lower_only else torch.empty(m, n, dtype=_f32, device=a.device)
+    h = _h(a)
+    with torch.cuda.device(a.device):
+        _lib.check(h.lib.gadm_gemm_tn(h.ptr, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                                     out.stride(0), m, n, k, float(alpha), float(beta), float(diag_add),
+                                     int(lower_only), _lib.stream_ptr(a.device)))
+    return out
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """[R, C] -> [C, R] with a pitch that is a multiple of 4 floats (TMA-loadable)."""
+    x = _check_cuda_f32(x, "x")
+    r, c = x.shape
+    ld = -(-r // 4) * 4
+    out = torch.zeros(c, ld, dtype=_f32, device=x.device)
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        _lib.check(h.lib.gadm_transpose(h.ptr, x.data_ptr(), r, c, x.stride(0), out.data_ptr(), ld,
+                                       _lib.stream_ptr(x.device)))
+    return out[:, :r]
+
+
+def row_norms(x: torch.Tensor, reciprocal: bool = False) -> torch.Tensor:
+    x = _check_cuda_f32(x, "x")
+    out = torch.empty(x.shape[0], dtype=_f32, device=x.device)
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        _lib.check(h.lib.gadm_row_norms(h.ptr, x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), int(reciprocal),
+                                       out.data_ptr(), _lib.stream_ptr(x.device)))
+    return out
+
+
+def col_mean_scaled(s: torch.Tensor, row_scale: torch.Tensor | None = None,
+                    col_scale: torch.Tensor | None = None) -> torch.Tensor:
+    out = torch.empty(s.shape[1], dtype=_f32, device=s.device)
+    h = _h(s)
+    with torch.cuda.device(s.device):
+        _lib.check(h.lib.gadm_col_mean_scaled(h.ptr, s.data_ptr(), s.shape[0], s.shape[1], s.stride(0),
+                                             row_scale.data_ptr() if row_scale is not None else None,
+                                             col_scale.data_ptr() if col_scale is not None else None,
+                                             out.data_ptr(), _lib.stream_ptr(s.device)))
+    return out
+
+
+def scale_rows_cols_(s: torch.Tensor, row_scale: torch.Tensor | None = None, col_scale: torch.Tensor | None = None):
+    h = _h(s)
+    with torch.cuda.device(s.device):
+        _lib.check(h.lib.gadm_scale_rows_cols(h.ptr, s.data_ptr(), s.shape[0], s.shape[1], s.stride(0),
+                                             row_scale.data_ptr() if row_scale is not None else None,
+                                             col_scale.data_ptr() if col_scale is not None else None,
+                                             _lib.stream_ptr(s.device)))
+    return s
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class TrakScorer:
+    """K = Phi^T Phi + lam*I factored once; rows are then multiplied by K^-1 on demand."""
+
+    def __init__(self, lam: float = 5e-1, group=None):
+        self.lam = float(lam)
+        self.group = group
+        self.k = None
+        self.L = None
+        self.U = None
+        self.blocks = None
+        self.info = None
+
+    def fit(self, train_phi: torch.Tensor) -> "TrakScorer":
+        """train_phi: this rank's [N_local, k] features.  traks.py:149-151 / compute_gradient_score.py:108-110."""
+        phi = _check_cuda_f32(train_phi, "train_phi")
+        self.k = phi.shape[1]
+        dist = _dist()
+        world = dist.get_world_size(self.group) if dist else 1
+        phi_t = transpose(phi)  # [k, N]: contraction over examples becomes K-major
+        gram = gemm_tn(phi_t, phi_t, lower_only=True, diag_add=self.lam / world)
+        if dist and world > 1:
+            dist.all_reduce(gram, group=self.group)  # one NCCL all-reduce over NVLink (sum of per-rank Grams)
+        return self.factor_(gram)
+
+    def factor_(self, gram: torch.Tensor) -> "TrakScorer":
+        """In-place Cholesky of an already regularised symmetric matrix (lower triangle is read)."""
+        self.k = gram.shape[0]
+        h = _h(gram)
+        nbytes = int(h.lib.gadm_cholesky_workspace_bytes(self.k))
+        self.blocks = torch.empty(nbytes, dtype=torch.uint8, device=gram.device)
+        self.info = torch.zeros(1, dtype=torch.int32, device=gram.device)
+        with torch.cuda.device(gram.device):
+            _lib.check(h.lib.gadm_cholesky(h.ptr, gram.data_ptr(), gram.stride(0), self.k, self.blocks.data_ptr(), nbytes,
+                                          C.cast(self.info.data_ptr(), C.POINTER(C.c_int)), _lib.stream_ptr(gram.device)))
+        self.L = gram
+        self.U = transpose(gram)
+        return self
+
+    def check(self) -> None:
+        """Host sync: raise if the factorisation met a non-positive pivot."""
+        bad = int(self.info.item())
+        if bad:
+            raise _lib.GadmError(f"Gram matrix is not positive definite (pivot {bad - 1})")
+
+    def solve_rows(self, rows: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+        """rows [m, k] -> rows @ K^-1."""
+        y = _check_cuda_f32(rows, "rows")
+        if not inplace or y.data_ptr() != rows.data_ptr():
+            y = y.clone()
+        if y.stride(0) % 4 != 0:
+            raise ValueError("row pitch must be a multiple of 4")
+        h = _h(y)
+        with torch.cuda.device(y.device):
+            _lib.check(h.lib.gadm_solve_rows(h.ptr, self.L.data_ptr(), self.L.stride(0), self.U.data_ptr(), self.U.stride(0),
+                                            self.blocks.data_ptr(), self.k, y.data_ptr(), y.stride(0), y.shape[0],
+                                            _lib.stream_ptr(y.device)))
+        return y
+
+    def kernel_inverse(self) -> torch.Tensor:
+        """Explicit K^-1 (what the reference caches as kernel_*.npy, compute_gradient_score.py:104-111)."""
+        eye = torch.eye(self.k, dtype=_f32, device=self.L.device)
+        return self.solve_rows(eye, inplace=True)
+
+    def score_matrix(self, gen_phi: torch.Tensor, train_phi: torch.Tensor) -> torch.Tensor:
+        """S = gen_phi K^-1 train_phi^T  [T, N_local]  (traks.py:152-156; compute_gradient_score.py:126)."""
+        z = self.solve_rows(gen_phi)
+        return gemm_tn(z, _check_cuda_f32(train_phi, "train_phi"))
+
+
+TRAK_VARIANTS = ("grad_sim", "trak", "relative_influence", "renorm_influence")
+
+
+def trak_scores(train_phi: torch.Tensor, gen_phi: torch.Tensor, lam: float = 5e-1,
+                variants: Sequence[str] = TRAK_VARIANTS, journey_phi: torch.Tensor | None = None,
+                group=None, gather: bool = True, return_scorer: bool = False):
+    """Per-training-example attribution vectors of text_to_image/traks.py:139-173 (mean over generated images).
+
+    Returns dict name -> fp32 tensor [N] (all ranks' examples when ``gather`` and torch.distributed is up).
+    ``journey_trak`` is added when ``journey_phi`` is given.  D-TRAK (traks.py:176-186) is the same call on the
+    mean-squared-l2-norm features."""
+    train = _check_cuda_f32(train_phi, "train_phi")
+    gen = _check_cuda_f32(gen_phi, "gen_phi")
+    out = {}
+    inv_train_norm = None
+    if "grad_sim" in variants or "renorm_influence" in variants:
+        inv_train_norm = row_norms(train, reciprocal=True)
+    if "grad_sim" in variants:  # traks.py:141-146
+        cos = gemm_tn(gen, train)
+        out["grad_sim"] = col_mean_scaled(cos, row_norms(gen, reciprocal=True), inv_train_norm)
+        del cos
+    scorer = None
+    if any(v in variants for v in ("trak", "relative_influence", "renorm_influence")) or journey_phi is not None:
+        scorer = TrakScorer(lam, group).fit(train)
+        s = scorer.score_matrix(gen, train)  # [T, N]
+        if "trak" in variants:
+            out["trak"] = col_mean_scaled(s)  # traks.py:156-157
+        if "relative_influence" in variants:  # traks.py:161-164: / ||K^-1 phi_n||
+            w = scorer.solve_rows(train)
+            out["relative_influence"] = col_mean_scaled(s, None, row_norms(w, reciprocal=True))
+            del w
+        if "renorm_influence" in variants:  # traks.py:166-168: / ||phi_n||
+            out["renorm_influence"] = col_mean_scaled(s, None, inv_train_norm)
+        del s
+        if journey_phi is not None:  # traks.py:171-173
+            out["journey_trak"] = col_mean_scaled(scorer.score_matrix(_check_cuda_f32(journey_phi, "journey_phi"), train))
+    dist = _dist()
+    if gather and dist and dist.get_world_size(group) > 1:
+        for name, v in list(out.items()):
+            parts = [torch.empty_like(v) for _ in range(dist.get_world_size(group))]
+            dist.all_gather(parts, v, group=group)  # equal shard sizes assumed; pad on the caller side otherwise
+            out[name] = torch.cat(parts)
+    return (out, scorer) if return_scorer else out
+
+
+def group_and_rank(sample_output_dict: dict, group_ids, num_groups: int):
+    """traks.py:188-225: per-group aggregation (sum; grad_sim -> avg / max) and stable descending ranks.
+
+    Returns (output_dict name -> float64 [G, 1], rank_dict name -> int64 [G])."""
+    output_dict = {}
+    for method, attrs in sample_output_dict.items():
+        if method in ["grad_sim"]:
+            output_dict[f"avg_{method}"] = group_reduce(attrs, group_ids, num_groups, "mean").reshape(num_groups, 1)
+            output_dict[f"max_{method}"] = group_reduce(attrs, group_ids, num_groups, "max").reshape(num_groups, 1)
+        else:
+            output_dict[method] = group_reduce(attrs, group_ids, num_groups, "sum").reshape(num_groups, 1)
+    rank_dict = {name: stable_rank(output) for name, output in output_dict.items()}
+    return output_dict, rank_dict
+
+
+def aggregate_by_class(scores, labels, by: str = "mean", compat_max_over_all_rows: bool = True):
+    """src/attributions/methods/attribution_utils.py:15-48 with the dataset replaced by its label vector.
+
+    ``by="max"`` in the reference takes the max over *all* rows (attribution_utils.py:46); that behaviour is
+    kept by default (``compat_max_over_all_rows``)."""
+    scores = scores if isinstance(scores, torch.Tensor) else torch.as_tensor(np.asarray(scores))
+    if scores.dim() == 1:
+        scores = scores[None, :]
+    labels = np.asarray(labels)
+    uniq = sorted(set(labels.tolist()))
+    lut = {v: i for i, v in enumerate(uniq)}
+    gid = np.array([lut[v] for v in labels.tolist()], dtype=np.int32)
+    rows = []
+    for r in range(scores.shape[0]):
+        rows.append(group_reduce(scores[r].contiguous(), gid, len(uniq), "mean" if by == "mean" else "max"))
+    result = np.stack(rows)
+    if by == "max" and compat_max_over_all_rows:
+        result[:] = result.max(axis=0, keepdims=True)
+    return result
+
+
+def gradient_scores(train_phi: torch.Tensor, val_phi: torch.Tensor, gradient_type: str = "trak", lam: float = 5e-1,
+                    kernel_inverse: torch.Tensor | None = None):
+    """Score matrix [T, N] of compute_gradient_score.py:108-126 for one gradient_type; returns (scores, scorer)."""
+    train = _check_cuda_f32(train_phi, "train_phi")
+    val = _check_cuda_f32(val_phi, "val_phi")
+    if gradient_type == "vanilla_gradient":  # :114-117
+        s = gemm_tn(val, train)
+        return scale_rows_cols_(s, row_norms(val, True), row_norms(train, True)), None
+    scorer = None
+    if kernel_inverse is not None:  # cached kernel (:102-105): scores = val @ (train @ kernel).T
+        kinv = _check_cuda_f32(kernel_inverse, "kernel_inverse")
+        w = gemm_tn(train, kinv)  # kernel is symmetric
+    else:
+        scorer = TrakScorer(lam).fit(train)
+        w = None
+    if gradient_type == "relative_if":  # :119-120
+        if w is None:
+            w = scorer.solve_rows(train)
+        col = row_norms(w, True)
+    elif gradient_type == "renormalized_if":  # :121-122
+        col = row_norms(train, True)
+    else:
+        col = None
+    s = gemm_tn(val, w) if w is not None else scorer.score_matrix(val, train)
+    if col is not None:
+        scale_rows_cols_(s, None, col)
+    return s, scorer
+
+
+def _constants_outdir(outdir):
+    if outdir is not None:
+        return outdir
+    if os.environ.get("GADM_OUTDIR"):
+        return os.environ["GADM_OUTDIR"]
+    try:
+        import src.constants as constants  # the reference's user-created module (README.md:19-28)
+
+        return constants.OUTDIR
+    except Exception as e:  # pragma: no cover
+        raise RuntimeError("pass outdir=..., set GADM_OUTDIR or provide src/constants.py (OUTDIR)") from e
+
+
+def compute_gradient_scores(args, retraining: bool = False, training_seeds: Iterable[int] | None = None, *,
+                            outdir: str | None = None, n_train: int | None = None, n_val: int | None = None,
+                            labels=None, device=None, compat: bool = True):
+    """Reference signature: src/attributions/methods/compute_gradient_score.py:13 (called at baseline_lds.py:380-383).
+
+    Reads the reference's raw fp32 memmaps (``train_f=..._t=..._k=..._d=...`` / ``reference_f=...``), reuses or writes
+    the fp64 ``kernel_train_*.npy`` cache, and returns what the reference returns: with ``compat=True`` the
+    [T, N] score matrix unless ``args.by_class`` (the ``else: coeff = scores`` of :134-137), with ``compat=False``
+    the mean over T when the behaviour is global.  ``n_train`` / ``n_val`` replace ``len(dataset)`` /
+    ``len(ImageDataset(sample_dir))`` (dataset I/O is out of scope); ``labels`` feeds aggregate_by_class."""
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    outdir = _constants_outdir(outdir)
+    if args.gradient_type == "d_trak":
+        model_behavior, t_strategy = "mean-squared-l2-norm", "uniform"
+    else:
+        model_behavior, t_strategy = "loss", "uniform"
+    if args.gradient_type == "journey_trak":
+        val_grad_path = os.path.join(outdir, args.dataset, "d_trak", "full",
+                                     f"gen_f=loss_t=uniform_k={args.k_partition}_d={args.projector_dim}")
+    else:
+        val_grad_path = os.path.join(args.sample_dir, "d_trak",
+                                     f"reference_f={model_behavior}_t={t_strategy}_k={args.k_partition}_d={args.projector_dim}")
+    kdim = args.projector_dim
+    if n_val is None:
+        n_val = args.sample_size if args.gradient_type == "journey_trak" else os.path.getsize(val_grad_path) // (4 * kdim)
+    val_phi = np.memmap(val_grad_path, dtype=np.float32, mode="r", shape=(n_val, kdim))[: args.sample_size]
+    val = torch.from_numpy(np.ascontiguousarray(val_phi)).to(device)
+
+    def _load_train(path):
+        n = n_train if n_train is not None else os.path.getsize(path) // (4 * kdim)
+        return torch.from_numpy(np.ascontiguousarray(np.memmap(path, dtype=np.float32, mode="r", shape=(n, kdim)))).to(device)
+
+    if retraining:  # :54-79
+        scores = None
+        seeds = list(training_seeds)
+        for seed in seeds:
+            removal_dir = f"{args.removal_dist}/{args.removal_dist}_seed={seed}"
+            # the reference spells this directory "d_track" (:63); accept both
+            for sub in ("d_track", "d_trak"):
+                path = os.path.join(outdir, args.dataset, sub, removal_dir,
+                                    f"train_f={args.trak_behavior}_t={args.t_strategy}_k={args.k_partition}_d={kdim}")
+                if os.path.exists(path):
+                    break
+            train = _load_train(path)
+            s, _ = gradient_scores(train, val, "trak")
+            scores = s / len(seeds) if scores is None else scores + s / len(seeds)
+    else:
+        train_grad_dir = os.path.join(outdir, args.dataset, "d_trak", "full")
+        train_grad_path = os.path.join(train_grad_dir, f"train_f={model_behavior}_t={t_strategy}_k={args.k_partition}_d={kdim}")
+        kernel_path = os.path.join(train_grad_dir,
+                                   f"kernel_train_f={model_behavior}_t={t_strategy}_k={args.k_partition}_d={kdim}.npy")
+        train = _load_train(train_grad_path)
+        kinv = None
+        if os.path.isfile(kernel_path):
+            kinv = torch.from_numpy(np.load(kernel_path)).to(device=device, dtype=_f32)
+        scores, scorer = gradient_scores(train, val, args.gradient_type, kernel_inverse=kinv)
+        if kinv is None and scorer is not None:
+            np.save(kernel_path, scorer.kernel_inverse().double().cpu().numpy())
+    is_local = args.model_behavior_key in ["ssim", "nrmse", "diffusion_loss"]
+    if getattr(args, "by_class", False):
+        coeff = scores if is_local else col_mean_scaled(scores)
+        if labels is None:
+            from src.datasets import create_dataset  # reference module; only needed for the label vector
+
+            labels = [d[1] for d in create_dataset(dataset_name=args.dataset, train=True)]
+        return aggregate_by_class(coeff, labels, getattr(args, "by", "mean"))
+    if compat or is_local:
+        return scores.cpu().numpy()
+    return col_mean_scaled(scores).cpu().numpy()
+
+
+def compute_dtrak_trak_scores(args, train_idx=None, val_idx=None, **kw):
+    """The callee unconditional_generation/attribute.py:15,150-152 imports but the reference never ships.
+
+    ``args.attribution_method`` in {d-trak, trak, relative_if, randomized_if} selects the gradient type;
+    ``train_idx`` restricts the returned columns (remaining training examples)."""
+    method = getattr(args, "attribution_method", "trak")
+    gtype = {"d-trak": "d_trak", "d_trak": "d_trak", "trak": "trak", "relative_if": "relative_if",
+             "randomized_if": "renormalized_if", "renormalized_if": "renormalized_if"}[method]
+    ns = type("Args", (), dict(vars(args)))()
+    ns.gradient_type = gtype
+    for name, default in (("by_class", False), ("k_partition", 10), ("model_behavior_key", "global")):
+        if not hasattr(ns, name):
+            setattr(ns, name, default)
+    scores = compute_gradient_scores(ns, **kw)
+    scores = np.asarray(scores)
+    if scores.ndim == 2 and scores.shape[0] > 1 and not ns.by_class:
+        scores = scores.mean(axis=0)
+    if train_idx is not None and not ns.by_class:
+        scores = scores.reshape(-1)[np.asarray(train_idx)]
+    return scores

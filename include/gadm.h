@@ -83,6 +83,42 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
 int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_dim, uint64_t seed64, int proj_type,
                        float* out, void* stream);
 
+/* ---------------------------------------------------------------- TRAK scorer (fp32 data, 3xTF32 tensor-core GEMM) */
+
+/* C[M, N] = alpha * A[M, K] * B[N, K]^T + beta * C, then C[i, i] += diag_add.
+ *   A, B, C fp32 row-major (contraction index contiguous in A and B); lda, ldb multiples of 4; A, B 16-byte
+ *   aligned.  lower_only != 0 skips 128x128 tiles strictly above the diagonal (symmetric results).
+ *   Replaces torch.matmul at text_to_image/traks.py:141,149,152,156,171,176,181,184 and the numpy products at
+ *   src/attributions/methods/compute_gradient_score.py:75,79,108,126 (fp32-grade accuracy via 3xTF32). */
+int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
+                 int64_t m, int64_t n, int64_t k, float alpha, float beta, float diag_add, int lower_only,
+                 void* stream);
+/* out[c, r] = in[r, c]  (in: [rows, cols] pitch ld_in; out: [cols, rows] pitch ld_out) */
+int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                   int64_t ld_out, void* stream);
+/* In-place lower Cholesky factor of the symmetric positive definite a [k, k] (pitch ld, ld % 4 == 0, lower
+ * triangle read, strict upper of each diagonal block zeroed).  blocks: workspace of gadm_cholesky_workspace_bytes(k)
+ * that receives the inverses of the 128x128 diagonal factor blocks (used by gadm_solve_rows).
+ * info: device int, 0 on success else 1 + index of the first non-positive pivot.
+ * Replaces torch.inverse / np.linalg.inv at traks.py:151,180 and compute_gradient_score.py:77,110 (the
+ * inverse is never formed unless asked for: gadm_solve_rows applies it). */
+int64_t gadm_cholesky_workspace_bytes(int64_t k);
+int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, int64_t blocks_bytes, int* info,
+                  void* stream);
+/* y[m, k] <- y * (L L^T)^-1 in place (every row of y is a right-hand side).  l: Cholesky factor from
+ * gadm_cholesky, u: its transpose (gadm_transpose), blocks: the same workspace. */
+int gadm_solve_rows(gadm_handle h, const float* l, int64_t ldl, const float* u, int64_t ldu, const void* blocks,
+                    int64_t k, float* y, int64_t ldy, int64_t m, void* stream);
+/* out[r] = ||x[r, :]||_2, or 1 / that when reciprocal != 0 (traks.py:143,162,166) */
+int gadm_row_norms(gadm_handle h, const float* x, int64_t rows, int64_t cols, int64_t ld, int reciprocal, float* out,
+                   void* stream);
+/* out[n] = mean_t s[t, n] * row_scale[t] * col_scale[n]; either scale may be NULL (traks.py:146,157,162-168) */
+int gadm_col_mean_scaled(gadm_handle h, const float* s, int64_t t, int64_t n, int64_t ld, const float* row_scale,
+                         const float* col_scale, float* out, void* stream);
+/* s[t, n] *= row_scale[t] * col_scale[n] in place (compute_gradient_score.py:114-126) */
+int gadm_scale_rows_cols(gadm_handle h, float* s, int64_t t, int64_t n, int64_t ld, const float* row_scale,
+                         const float* col_scale, void* stream);
+
 /* ---------------------------------------------------------------- subset-mask aggregation (fp64) */
 
 enum { GADM_GRAM_SHAPLEY = 0, GADM_GRAM_BANZHAF = 1 };
