@@ -1,0 +1,389 @@
+"""Benchmark of the attribution hot path (driver contract: one JSON line on rank 0).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU projector (trak BasicProjector restatement)
+
+Workload (BASELINE.json configs[1], "CIFAR-10 DDPM TRAK ... proj_dim 4096"): one *step* = one pass of the JL
+projection over one staged batch of 512 per-example gradients of the 35 746 307-parameter DDPM-CIFAR U-Net
+(synthetic bf16 rows resident in HBM) -> 512 x 4096 features.  Metric = projected gradients per second,
+whole job (sum over ranks, weak scaling: every rank projects its own 512 examples per step, no collective on
+the projection path).  `roofline` = 2*M*D*k flops per launch / CUDA-event time against the measured dense
+bf16 peak; `e2e` = the same metric through the public `CudaProjector.deferred()` API with fp32 gradients
+coming from pinned host memory and the features read back to the host inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GRAD_DIM = 35_746_307  # DDPM-CIFAR U-Net (src/ddpm_config.py:48-82), SURVEY.md section 8
+PROJ_DIM = 4096
+STAGE_ROWS = 512
+N_TRAIN, N_GEN = 50_000, 1_000
+METRIC = "projected_grads_per_sec"
+UNIT = "grads/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p.get("bf16_tflops", 1590.0), "bf16_sustained": p.get("bf16_tflops_sustained", 1400.0),
+                "hbm_gbs": p.get("hbm_gbs", 6650.0), "source": "MEASURED_PEAKS.json"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _cpu_projector_rate(seconds_target: float = 8.0, proj_type: str = "normal"):
+    """grads/s of trak BasicProjector (oracle restatement) on the host cores, on a bounded sample."""
+    import torch
+
+    from oracle.projector import BasicProjectorOracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 8  # the reference's batch (d_trak_grad.py:327)
+    # calibrate on 1/64 of D, then pick the slice of D that costs ~seconds_target for ONE 100-column block
+    d_small = GRAD_DIM // 64
+    g = torch.randn(batch, d_small)
+    p = BasicProjectorOracle(d_small, PROJ_DIM, 42, proj_type)
+    t0 = time.perf_counter(); p.project(g, 0, blocks=1); t_small = time.perf_counter() - t0
+    frac = min(1.0, max(1.0 / 64, seconds_target / (t_small * 64)))
+    d_s = int(GRAD_DIM * frac)
+    g = torch.randn(batch, d_s)
+    p = BasicProjectorOracle(d_s, PROJ_DIM, 42, proj_type)
+    t0 = time.perf_counter(); p.project(g, 0, blocks=1); t_blk = time.perf_counter() - t0
+    blocks = -(-PROJ_DIM // 100)
+    t_full_batch = t_blk * (GRAD_DIM / d_s) * blocks  # linear in D and in the number of 100-column blocks
+    sample = (f"BasicProjector({proj_type}) 1 of {blocks} column blocks x [8, {d_s}] fp32 (D/{GRAD_DIM / d_s:.1f}) "
+              f"= {t_blk:.2f} s, extrapolated linearly to D={GRAD_DIM}, k={PROJ_DIM}")
+    return batch / t_full_batch, cores, sample, t_blk
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU projection path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    sample = ""
+    cores = os.cpu_count() or 1
+    t_begin = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, cores, sample, t_blk = _cpu_projector_rate(seconds_target=3.0)
+        if i >= args.warmup:
+            vals.append(v)
+        if time.perf_counter() - t_begin > 150 and vals:
+            break
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": 1e3 * STAGE_ROWS / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CIFAR-10 DDPM TRAK featurisation: JL projection of per-example U-Net gradients",
+                   "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": "normal", "batch": 8},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gadm", choices=["gadm", "reference"])
+    ap.add_argument("--proj-type", default="normal", choices=["normal", "rademacher"],
+                    help="normal is what the reference instantiates (d_trak_grad.py:508)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the scoring / aggregation side measurements")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import gadm_b200
+    from gadm_b200 import CudaProjector, ProjectionType
+
+    gadm_b200.load_library()  # fails loudly if the CUDA extension is missing
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = _peaks()
+    ptype = ProjectionType(args.proj_type)
+    proj = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ptype, dev, 32, stage_rows=STAGE_ROWS)
+    handle = proj._handle
+    stage = proj._stage_buffer(STAGE_ROWS)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    for r in range(0, STAGE_ROWS, 32):  # synthetic per-example gradients, randn * 1e-3, bf16, resident in HBM
+        stage[r:r + 32, :GRAD_DIM] = (torch.randn(32, GRAD_DIM, device=dev, generator=gen) * 1e-3).to(torch.bfloat16)
+    out = torch.empty(STAGE_ROWS, PROJ_DIM, device=dev)
+
+    # ---------------- device-resident throughput (value) + roofline
+    for _ in range(args.warmup):
+        proj._project_rows(stage, STAGE_ROWS, 0, out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = handle.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        proj._project_rows(stage, STAGE_ROWS, 0, out)
+        ev[i + 1].record()
+    barrier()
+    launches = handle.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    ms_per_step = total_ms / args.steps
+    value = STAGE_ROWS * world / (ms_per_step * 1e-3)
+    flops_per_launch = 2.0 * STAGE_ROWS * GRAD_DIM * PROJ_DIM
+    kernel_ms = sum(step_ms) / len(step_ms)  # project kernel + its (<0.1 %) split-K reduce, this rank
+    achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    wd = handle.watchdog_code()
+    assert wd == 0, f"kernel watchdog fired: {wd:#x}"
+
+    # ---------------- end to end: pinned host fp32 gradients -> public API -> features back on the host
+    e2e = None
+    if not args.no_e2e:
+        chunk = 32
+        host = torch.empty(chunk, GRAD_DIM, dtype=torch.float32).pin_memory()
+        host.normal_(0, 1e-3)
+        host_out = torch.empty(STAGE_ROWS, PROJ_DIM, dtype=torch.float32).pin_memory()
+        bufs = [torch.empty(chunk, GRAD_DIM, dtype=torch.float32, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        free_ev = [torch.cuda.Event() for _ in range(2)]
+        full_ev = [torch.cuda.Event() for _ in range(2)]
+        main_stream = torch.cuda.current_stream(dev)
+
+        def e2e_step():
+            with proj.deferred(model_id=0) as sink:
+                for c in range(STAGE_ROWS // chunk):
+                    b = c % 2
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(free_ev[b])
+                        bufs[b].copy_(host, non_blocking=True)  # H2D of this chunk's gradients
+                        full_ev[b].record(copy_stream)
+                    main_stream.wait_event(full_ev[b])
+                    sink.add(bufs[b])  # pack -> bf16 staging (projects when 512 rows are staged)
+                    free_ev[b].record(main_stream)
+            host_out.copy_(sink.result(), non_blocking=True)  # D2H of the step's result
+            main_stream.synchronize()
+
+        for e in free_ev:
+            e.record(main_stream)
+        n_e2e_warm = 1
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e_warm):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        e2e = {"value": STAGE_ROWS * world / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": STAGE_ROWS * GRAD_DIM * 4, "d2h_bytes_per_step": STAGE_ROWS * PROJ_DIM * 4,
+               "ms_per_step": e2e_ms, "steps": n_e2e,
+               "api": "CudaProjector.deferred().add(fp32 grads from pinned host) -> result() -> host"}
+        del bufs, host
+    proj.free_memory()
+    del stage
+    torch.cuda.empty_cache()
+
+    # ---------------- side measurements: full TRAK scoring at C2 dims, aggregation at config 5
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra = side_measurements(dev, rank, world)
+        except Exception as e:  # never lose the headline line
+            extra = {"error": f"{type(e).__name__}: {e}"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = _cpu_projector_rate(seconds_target=8.0, proj_type=args.proj_type)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        traffic = None
+        summ = os.path.join(ROOT, "profiles", "projection_traffic.json")
+        if os.path.exists(summ):
+            with open(summ) as f:
+                traffic = json.load(f).get(args.proj_type, {}).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "CIFAR-10 DDPM TRAK featurisation: JL projection of per-example U-Net gradients "
+                                   "(BASELINE configs[1]), 512 staged examples per step per GPU",
+                       "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": args.proj_type,
+                       "rows_per_step_per_gpu": STAGE_ROWS, "sharding": f"examples x{world}",
+                       "l2": "staged input (36.6 GB) and split-K partials (0.3 GB) exceed the 126 MB L2"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                         "peak_kind": f"bf16_tflops_sustained of measured ({peaks['source']}); timed inside a multi-step loop",
+                         "frac_of_burst_peak": achieved / peaks["bf16_burst"], "flops_per_launch": flops_per_launch,
+                         "kernel": "gadm::proj::project_kernel<2>"},
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "tflops": achieved * world, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def side_measurements(dev, rank, world):
+    """Full TRAK score time (C2 dims, sharded by example) and Shapley/Banzhaf/LDS aggregation (config 5)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import gadm_b200 as G
+
+    out = {}
+    n_local = N_TRAIN // world
+    g = torch.Generator(device=dev).manual_seed(rank)
+    train = torch.randn(n_local, PROJ_DIM, device=dev, generator=g)
+    g2 = torch.Generator(device=dev).manual_seed(10_000)
+    gen = torch.randn(N_GEN, PROJ_DIM, device=dev, generator=g2)
+    handle = G._lib.get_handle(dev) if hasattr(G, "_lib") else None
+    for it in range(2):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = G.trak_scores(train, gen, lam=0.5, variants=("trak",), gather=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out["trak_score"] = {"ms": ms, "n_train": N_TRAIN, "n_gen": N_GEN, "proj_dim": PROJ_DIM, "lam": 0.5,
+                         "what": "Gram (+NCCL all-reduce) -> Cholesky -> solve -> score GEMM -> mean (+all-gather)",
+                         "finite": bool(torch.isfinite(res["trak"]).all())}
+    del train, gen, res
+    torch.cuda.empty_cache()
+    if rank == 0:
+        from oracle import aggregation as oagg
+
+        n, d, K, m = 1000, 100, 1000, 100
+        rng = np.random.RandomState(0)
+        Xs = oagg.shapley_masks(d, list(range(n)))
+        w = rng.normal(size=(d, K))
+        Ys = Xs @ w + 0.1 * rng.normal(size=(n, K))
+        tests = []
+        for t in range(3):
+            Xt = oagg.datamodel_masks(d, list(range(5000 + 100 * t, 5000 + 100 * t + m)))
+            tests.append((Xt, Xt @ w + 0.5 * rng.normal(size=(m, K))))
+        for it in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            phi = G.data_shapley_batched(Xs, Ys, w.sum(axis=0), np.zeros(K))
+            phb = G.data_banzhaf_batched(Xs, Ys)
+            lds = G.evaluate_lds(phi, tests, K)
+            torch.cuda.synchronize()
+            agg_ms = (time.perf_counter() - t0) * 1e3
+        bytes_alg = n * d + 8 * n * K + 8 * d * K + 3 * (m * d + 8 * m * K) + 8 * d * K + 8 * 3 * K
+        out["aggregation"] = {"ms_host_to_host": agg_ms, "n_masks": n, "contributors": d, "behaviors": K,
+                              "algorithmic_bytes": bytes_alg, "lds": list(map(float, lds)),
+                              "what": "data_shapley x K + data_banzhaf x K + evaluate_lds (3 x 100 subsets), numpy in / numpy out"}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@ _SIGNATURES = {
     "gadm_destroy": (C.c_int, [c_vp]),
     "gadm_launch_count": (c_i64, [c_vp]),
     "gadm_watchdog_code": (C.c_int, [c_vp, C.POINTER(C.c_uint)]),
+    "gadm_set_watchdog_ns": (C.c_int, [c_vp, c_u64]),
     "gadm_project_workspace_bytes": (c_i64, [c_vp, c_i64, c_i64, c_i64, C.c_int]),
     "gadm_pack_block": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, C.c_float, c_vp]),
     "gadm_project_staged": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_i64,
@@ -109,6 +110,8 @@ class Handle:
         self.lib = lib
         self.ptr = h
         self.device_index = device_index
+        if os.environ.get("GADM_WATCHDOG_SEC") is not None:  # 0 disables (e.g. under ncu --set full)
+            check(lib.gadm_set_watchdog_ns(h, int(float(os.environ["GADM_WATCHDOG_SEC"]) * 1e9)))
 
     def launch_count(self) -> int:
         return int(self.lib.gadm_launch_count(self.ptr))

@@ -197,6 +197,14 @@ int gadm_watchdog_code(gadm_handle h, unsigned int* code) {
   return GADM_OK;
 }
 
+int gadm_set_watchdog_ns(gadm_handle h, uint64_t ns) {
+  GADM_REQUIRE(h, "null handle");
+  DeviceGuard guard(h->device);
+  unsigned long long v = ns;
+  GADM_CUDA(cudaMemcpyToSymbol(gadm::g_watchdog_ns, &v, sizeof(v)));
+  return GADM_OK;
+}
+
 int64_t gadm_project_workspace_bytes(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_dim, int cta_group) {
   if (!h) return fail(GADM_ERR_INVALID, "null handle");
   ProjPlan p;

@@ -8,10 +8,13 @@
 namespace gadm {
 
 // ------------------------------------------------------------------ watchdog
-// Every mbarrier wait is bounded: if a barrier is not satisfied within kWatchdogNs of wall time the
+// Every mbarrier wait is bounded: if a barrier is not satisfied within g_watchdog_ns of wall time the
 // kernel records a code in this device word and traps, so a protocol bug becomes a CUDA error
 // instead of a hung GPU box.
 __device__ unsigned int g_watchdog_code = 0;
+// 0 disables the watchdog (set through gadm_set_watchdog_ns; profilers that serialise or instrument
+// the kernel can stretch a legitimate wait far beyond the default).
+__device__ unsigned long long g_watchdog_ns = 4000000000ull;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -87,12 +90,12 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-constexpr uint64_t kWatchdogNs = 4000000000ull;  // 4 s
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t code) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
+  const uint64_t limit = *reinterpret_cast<volatile unsigned long long*>(&g_watchdog_ns);
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > kWatchdogNs) watchdog_fire(code);
+    if (limit != 0 && globaltimer_ns() - t0 > limit) watchdog_fire(code);
   }
 }
 

@@ -366,7 +366,10 @@ def compute_gradient_scores(args, retraining: bool = False, training_seeds: Iter
         if os.path.isfile(kernel_path):
             kinv = torch.from_numpy(np.load(kernel_path)).to(device=device, dtype=_f32)
         scores, scorer = gradient_scores(train, val, args.gradient_type, kernel_inverse=kinv)
-        if kinv is None and scorer is not None:
+        if kinv is None:
+            # the reference builds and caches the kernel before it looks at gradient_type (:102-111)
+            if scorer is None:
+                scorer = TrakScorer(5e-1).fit(train)
             np.save(kernel_path, scorer.kernel_inverse().double().cpu().numpy())
     is_local = args.model_behavior_key in ["ssim", "nrmse", "diffusion_loss"]
     if getattr(args, "by_class", False):

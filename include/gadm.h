@@ -55,6 +55,8 @@ int gadm_destroy(gadm_handle h);
 int64_t gadm_launch_count(gadm_handle h);
 /* reads and clears the in-kernel watchdog word (0 = no barrier timeout fired) */
 int gadm_watchdog_code(gadm_handle h, unsigned int* code);
+/* bound (ns of wall time) on any in-kernel barrier wait before the kernel traps; 0 disables (profilers) */
+int gadm_set_watchdog_ns(gadm_handle h, uint64_t ns);
 
 /* ---------------------------------------------------------------- JL projection */
 
