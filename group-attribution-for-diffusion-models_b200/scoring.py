@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from .aggregation import group_reduce, stable_rank
+from .distributed import allgather_cat, allreduce_sum_
 
 _f32 = torch.float32
 
@@ -138,8 +139,7 @@ class TrakScorer:
         world = dist.get_world_size(self.group) if dist else 1
         phi_t = transpose(phi)  # [k, N]: contraction over examples becomes K-major
         gram = gemm_tn(phi_t, phi_t, lower_only=True, diag_add=self.lam / world)
-        if dist and world > 1:
-            dist.all_reduce(gram, group=self.group)  # one NCCL all-reduce over NVLink (sum of per-rank Grams)
+        allreduce_sum_(gram, self.group)  # one NCCL all-reduce over NVLink (sum of per-rank Grams)
         return self.factor_(gram)
 
     def factor_(self, gram: torch.Tensor) -> "TrakScorer":
@@ -223,12 +223,9 @@ def trak_scores(train_phi: torch.Tensor, gen_phi: torch.Tensor, lam: float = 5e-
         del s
         if journey_phi is not None:  # traks.py:171-173
             out["journey_trak"] = col_mean_scaled(scorer.score_matrix(_check_cuda_f32(journey_phi, "journey_phi"), train))
-    dist = _dist()
-    if gather and dist and dist.get_world_size(group) > 1:
+    if gather:
         for name, v in list(out.items()):
-            parts = [torch.empty_like(v) for _ in range(dist.get_world_size(group))]
-            dist.all_gather(parts, v, group=group)  # equal shard sizes assumed; pad on the caller side otherwise
-            out[name] = torch.cat(parts)
+            out[name] = allgather_cat(v, dim=0, group=group)  # one all-gather of the per-example score slices
     return (out, scorer) if return_scorer else out
 
 
