@@ -61,9 +61,13 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on a barrier given by a shared::cluster address (own or peer CTA)
+// arrive on a barrier given by a shared::cluster address (own or peer CTA).  Default (.release.cta)
+// semantics on purpose: a .release.cluster arrive compiles to MEMBAR.ALL.GPU + CCTL.IVALL (an L1 flush
+// and a GPU-scope fence, ~microseconds) and sat on the critical path of every pipeline slot; the data
+// this arrival publishes lives in the arriving CTA's own shared memory and has already been ordered
+// for the async proxy by fence.proxy.async.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
@@ -73,7 +77,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, 0x20000;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x20000;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
