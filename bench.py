@@ -202,8 +202,14 @@ def main():
     handle = proj._handle
     stage = proj._stage_buffer(STAGE_ROWS)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    for r in range(0, STAGE_ROWS, 32):  # synthetic per-example gradients, randn * 1e-3, bf16, resident in HBM
-        stage[r:r + 32, :GRAD_DIM] = (torch.randn(32, GRAD_DIM, device=dev, generator=gen) * 1e-3).to(torch.bfloat16)
+    nkb = stage.shape[0]  # staging layout [D_pad/64][rows][64] (include/gadm.h)
+    for k0 in range(0, nkb, 8192):  # synthetic per-example gradients, randn * 1e-3, bf16, resident in HBM
+        k1 = min(nkb, k0 + 8192)
+        blk = (torch.randn(k1 - k0, STAGE_ROWS, 64, device=dev, generator=gen) * 1e-3).to(torch.bfloat16)
+        if k1 == nkb and GRAD_DIM % 64:
+            blk[-1, :, GRAD_DIM % 64:] = 0
+        stage[k0:k1] = blk
+    del blk
     out = torch.empty(STAGE_ROWS, PROJ_DIM, device=dev)
 
     # ---------------- device-resident throughput (value) + roofline

@@ -23,7 +23,8 @@ _SIGNATURES = {
     "gadm_watchdog_code": (C.c_int, [c_vp, C.POINTER(C.c_uint)]),
     "gadm_set_watchdog_ns": (C.c_int, [c_vp, c_u64]),
     "gadm_project_workspace_bytes": (c_i64, [c_vp, c_i64, c_i64, c_i64, C.c_int]),
-    "gadm_pack_block": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, C.c_float, c_vp]),
+    "gadm_pack_block": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_float,
+                                  c_vp]),
     "gadm_project_staged": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_i64,
                                       C.c_int, c_vp, c_i64, C.c_int, c_vp]),
     "gadm_materialize_p": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_vp]),

@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -84,6 +85,20 @@ int make_tmap_2d(gadm_handle h, CUtensorMap* map, CUtensorMapDataType dt, int el
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GADM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GADM_OK;
+}
+
+// staged gradients: bf16 [nkb][m_cap][64]; box = 64 x 128 x 1 (one contiguous 16 KiB tile)
+int make_tmap_staged(gadm_handle h, CUtensorMap* map, const void* base, uint64_t m_cap, uint64_t nkb) {
+  cuuint64_t gdim[3] = {64, m_cap, nkb};
+  cuuint64_t gstride[2] = {128, m_cap * 128};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  GADM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 127) == 0, "staging buffer %p is not 128-byte aligned", base);
+  CUresult r = h->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box,
+                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GADM_ERR_CUDA, "cuTensorMapEncodeTiled(staged) failed with CUresult %d", (int)r);
   return GADM_OK;
 }
 
@@ -214,11 +229,13 @@ int64_t gadm_project_workspace_bytes(gadm_handle h, int64_t m_rows, int64_t d_pa
 }
 
 int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, int64_t numel, int64_t src_stride,
-                    void* staged, int64_t ld, int64_t row0, int64_t col0, float scale, void* stream) {
+                    void* staged, int64_t d_pad, int64_t m_cap, int64_t row0, int64_t col0, float scale, void* stream) {
   GADM_REQUIRE(h && src && staged, "null argument");
-  GADM_REQUIRE(batch > 0 && numel > 0 && src_stride >= numel && ld >= col0 + numel && row0 >= 0 && col0 >= 0,
-               "bad block geometry (batch %lld numel %lld stride %lld ld %lld row0 %lld col0 %lld)", (long long)batch,
-               (long long)numel, (long long)src_stride, (long long)ld, (long long)row0, (long long)col0);
+  GADM_REQUIRE(batch > 0 && numel > 0 && src_stride >= numel && d_pad % 64 == 0 && d_pad >= col0 + numel && row0 >= 0 &&
+                   col0 >= 0 && row0 + batch <= m_cap,
+               "bad block geometry (batch %lld numel %lld stride %lld d_pad %lld m_cap %lld row0 %lld col0 %lld)",
+               (long long)batch, (long long)numel, (long long)src_stride, (long long)d_pad, (long long)m_cap,
+               (long long)row0, (long long)col0);
   DeviceGuard guard(h->device);
   const int threads = 256;
   int64_t bx = (numel + threads * 8 - 1) / (threads * 8);
@@ -228,13 +245,13 @@ int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, in
   auto* dst = reinterpret_cast<__nv_bfloat16*>(staged);
   if (dtype == GADM_DTYPE_F32)
     gadm::proj::pack_block_kernel<float><<<grid, threads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float*>(src), src_stride, numel, batch, dst, ld, row0, col0, scale);
+        reinterpret_cast<const float*>(src), src_stride, numel, batch, dst, m_cap, row0, col0, scale);
   else if (dtype == GADM_DTYPE_BF16)
     gadm::proj::pack_block_kernel<__nv_bfloat16><<<grid, threads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(src), src_stride, numel, batch, dst, ld, row0, col0, scale);
+        reinterpret_cast<const __nv_bfloat16*>(src), src_stride, numel, batch, dst, m_cap, row0, col0, scale);
   else if (dtype == GADM_DTYPE_F16)
     gadm::proj::pack_block_kernel<__half><<<grid, threads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __half*>(src), src_stride, numel, batch, dst, ld, row0, col0, scale);
+        reinterpret_cast<const __half*>(src), src_stride, numel, batch, dst, m_cap, row0, col0, scale);
   else
     return fail(GADM_ERR_INVALID, "unknown dtype %d", dtype);
   GADM_CUDA(cudaGetLastError());
@@ -242,13 +259,13 @@ int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, in
   return GADM_OK;
 }
 
-int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t ld, int64_t p_base,
+int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t m_cap, int64_t p_base,
                         int64_t proj_dim, uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate,
                         void* workspace, int64_t workspace_bytes, int cta_group, void* stream) {
   GADM_REQUIRE(h && staged && out && workspace, "null argument");
   GADM_REQUIRE(proj_type == GADM_PROJ_NORMAL || proj_type == GADM_PROJ_RADEMACHER, "unknown proj_type %d", proj_type);
   GADM_REQUIRE(p_base >= 0 && p_base % 64 == 0, "p_base %lld must be a non-negative multiple of 64", (long long)p_base);
-  GADM_REQUIRE(ld >= d_pad && ld % 8 == 0, "ld %lld must be >= d_pad and a multiple of 8", (long long)ld);
+  GADM_REQUIRE(m_cap >= m_rows, "m_cap %lld must be >= m_rows %lld", (long long)m_cap, (long long)m_rows);
   GADM_REQUIRE(ld_out >= proj_dim && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "out must be 16-byte aligned with pitch %% 4 == 0");
   GADM_REQUIRE((p_base + d_pad) / 8 < (1ll << 32), "parameter index exceeds the 2^35 counter range");
@@ -261,8 +278,7 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
   GADM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
   DeviceGuard guard(h->device);
   CUtensorMap tmap;
-  rc = make_tmap_2d(h, &tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, staged, (uint64_t)d_pad, (uint64_t)m_rows,
-                    (uint64_t)ld * 2, gadm::proj::kBlockK, gadm::proj::kAccRows);
+  rc = make_tmap_staged(h, &tmap, staged, (uint64_t)m_cap, (uint64_t)(d_pad / gadm::proj::kBlockK));
   if (rc != GADM_OK) return rc;
   gadm::proj::Args a;
   a.partial = reinterpret_cast<float*>(workspace);
@@ -276,6 +292,10 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
   a.key1 = (uint32_t)(seed64 >> 32);
   a.proj_type = (uint32_t)proj_type;
   a.p_base_div64 = (uint32_t)(p_base / 64);
+  {
+    const char* dbg = getenv("GADM_PROJ_DEBUG");  // perf ablation only; results are garbage when set
+    a.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
+  }
   cudaStream_t st = as_stream(stream);
   rc = (cta_group == 2) ? launch_project<2>(h, tmap, a, p.n_clusters, st) : launch_project<1>(h, tmap, a, p.n_clusters, st);
   if (rc != GADM_OK) return rc;

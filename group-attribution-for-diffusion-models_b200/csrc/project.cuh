@@ -8,7 +8,10 @@
 //   * one CTA pair (cluster of 2, tcgen05 cta_group::2) per "unit" = (256-column tile of Phi, D-split);
 //     UMMA 256x256x16 bf16 -> fp32, two accumulators (2 x 256 TMEM columns) so that a generated P
 //     tile feeds up to 512 staged gradient rows;
-//   * A operand (staged bf16 gradients, K-major) arrives by TMA into 128B-swizzled smem;
+//   * A operand (staged bf16 gradients, K-major) arrives by TMA into 128B-swizzled smem; the staging
+//     buffer is tile-major [D_pad/64][m_cap][64] so that a 128-row x 64-column tile is 16 KiB of
+//     contiguous HBM (with a plain [M, D] layout every 128-byte row of a tile opens its own DRAM page
+//     and the A feed, not the tensor pipe, capped the kernel at ~1.0 PFLOP/s);
 //   * B operand (P tile, K-major, 128B swizzle) is *written by generator warps* straight into the
 //     UMMA smem layout from Philox4x32-10 (see philox.cuh), then published to the async proxy;
 //   * warp roles: 0 = TMA, 1 = MMA issue (leader CTA, one thread), 2 = TMEM alloc, 4-7 = epilogue
@@ -68,6 +71,7 @@ struct Args {
   uint32_t key0, key1;  // Philox key = seed64
   uint32_t proj_type;   // ProjType
   uint32_t p_base_div64;  // canonical index of staged column 0, / 64
+  uint32_t debug;         // perf ablation only (GADM_PROJ_DEBUG): bit0 skip generation, bit1 skip TMA loads
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
@@ -174,13 +178,18 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u, 0x100 + s);
+          if (a.debug & 2u) {  // ablation: no loads, operands are whatever the slot holds
+            if (rank == 0) mbar_arrive(full_bar(s));
+            continue;
+          }
           if (rank == 0) mbar_arrive_expect_tx(full_bar(s), a.n_acc * C::kATileBytes * kCtaGroup);
           for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
             const int32_t row = acc * (kAccRows * kCtaGroup) + rank * kAccRows;
+            // staged layout [D_pad/64][m_cap][64]: one 128-row tile is 16 KiB of contiguous HBM
             if constexpr (kCtaGroup == 2)
-              tma_load_2d_cg2(smem_a(s, acc), &tmap_g, mapa(full_bar(s), 0), kb * kBlockK, row);
+              tma_load_3d_cg2(smem_a(s, acc), &tmap_g, mapa(full_bar(s), 0), 0, row, kb);
             else
-              tma_load_2d(smem_a(s, acc), &tmap_g, full_bar(s), kb * kBlockK, row);
+              tma_load_3d(smem_a(s, acc), &tmap_g, full_bar(s), 0, row, kb);
           }
         }
       }
@@ -258,7 +267,9 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
         const uint32_t ph = (it / C::kStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x500 + s);
         const uint32_t p_div64 = a.p_base_div64 + kb;
-        if (a.proj_type == kProjRademacher)
+        if (a.debug & 1u) {
+          // ablation: publish the slot without generating
+        } else if (a.proj_type == kProjRademacher)
           gen_rademacher_stage<C::kBRows>(smem_b(s), p_div64 * 2u, j0, a.key0, a.key1, tig, lane);
         else
           gen_normal_stage<C::kBRows>(smem_b(s), p_div64 * 8u, j0, a.key0, a.key1, tig);
@@ -325,18 +336,20 @@ __global__ void materialize_p_kernel(float* __restrict__ out, int64_t row0, int6
   out[idx] = v;
 }
 
-// fp32 / bf16 gradient block -> bf16 staging buffer.  src: [B, numel] with row pitch src_stride
-// (elements); dst: staged [rows, ld_dst] bf16, written at (row0 + b, col0 + i).
+// fp32 / bf16 / fp16 gradient block -> bf16 staging buffer in the tile-major layout
+// staged[kb][row][c] (kb = p / 64, c = p % 64, row pitch 64, slab pitch m_cap * 64), p = col0 + i.
+// src: [B, numel] with row pitch src_stride (elements); rows land at row0 + b.
 template <typename T>
 __global__ void pack_block_kernel(const T* __restrict__ src, int64_t src_stride, int64_t numel, int64_t B,
-                                  __nv_bfloat16* __restrict__ dst, int64_t ld_dst, int64_t row0, int64_t col0,
+                                  __nv_bfloat16* __restrict__ dst, int64_t m_cap, int64_t row0, int64_t col0,
                                   float scale) {
   const int64_t b = blockIdx.y;
   const T* s = src + b * src_stride;
-  __nv_bfloat16* d = dst + (row0 + b) * ld_dst + col0;
+  const int64_t row = row0 + b;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    d[i] = __float2bfloat16_rn(static_cast<float>(s[i]) * scale);
+    const int64_t p = col0 + i;
+    dst[((p >> 6) * m_cap + row) * 64 + (p & 63)] = __float2bfloat16_rn(static_cast<float>(s[i]) * scale);
   }
 }
 

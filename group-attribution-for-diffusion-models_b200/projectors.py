@@ -117,9 +117,10 @@ class CudaProjector:
 
     # ------------------------------------------------------------------ buffers
     def _stage_buffer(self, rows: int) -> torch.Tensor:
-        if self._stage is None or self._stage.shape[0] < rows:
+        """bf16 staging buffer in the kernel's tile-major layout [d_pad / 64][m_cap][64] (include/gadm.h)."""
+        if self._stage is None or self._stage.shape[1] < rows:
             self._stage = None
-            self._stage = torch.zeros(rows, self.d_pad, dtype=torch.bfloat16, device=self.device)
+            self._stage = torch.zeros(self.d_pad // TILE_K, rows, TILE_K, dtype=torch.bfloat16, device=self.device)
         return self._stage
 
     def _workspace(self, rows: int) -> torch.Tensor:
@@ -150,7 +151,7 @@ class CudaProjector:
             if numel == 0:
                 continue
             _lib.check(lib.gadm_pack_block(h, b.data_ptr(), _DTYPES[b.dtype], bsz, numel, b.stride(0) if bsz > 1 else numel,
-                                          stage.data_ptr(), stage.stride(0), row0, col, float(scale), st))
+                                          stage.data_ptr(), self.d_pad, stage.shape[1], row0, col, float(scale), st))
             col += numel
         return bsz
 
@@ -158,7 +159,7 @@ class CudaProjector:
         ws = self._workspace(rows)
         seed64 = (self.seed + SEED_MODEL_ID_STRIDE * int(model_id)) & 0xFFFFFFFFFFFFFFFF
         _lib.check(self._handle.lib.gadm_project_staged(
-            self._handle.ptr, stage.data_ptr(), rows, self.d_pad, stage.stride(0), 0, self.proj_dim, seed64,
+            self._handle.ptr, stage.data_ptr(), rows, self.d_pad, stage.shape[1], 0, self.proj_dim, seed64,
             _PROJ_CODE[self.proj_type], out.data_ptr(), out.stride(0), 0, ws.data_ptr(), ws.numel(), self.cta_group,
             _lib.stream_ptr(self.device)))
 

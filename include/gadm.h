@@ -63,21 +63,26 @@ int gadm_set_watchdog_ns(gadm_handle h, uint64_t ns);
 /* Bytes of scratch gadm_project_staged needs for split-K partial tiles. */
 int64_t gadm_project_workspace_bytes(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_dim, int cta_group);
 
-/* Convert one gradient block to bf16 inside the staging buffer.
+/* Staging buffer layout (bf16): staged[kb][row][c] with kb = p / 64, c = p % 64, i.e. a contiguous
+ * [d_pad / 64][m_cap][64] array, 128-byte aligned.  p is the position in the flattened gradient, row the example.
+ * Tile-major so that the 128-row x 64-column tiles the kernel streams are contiguous in HBM.
+ *
+ * Convert one gradient block to bf16 inside the staging buffer.
  *   src: [batch, numel] of `dtype`, consecutive examples `src_stride` elements apart
- *   staged: bf16 [rows, ld] row-major; block lands at rows row0..row0+batch, columns col0..col0+numel
+ *   block lands at rows row0..row0+batch, positions col0..col0+numel of the flattened gradient
  *   the value written is bf16(src * scale)  (scale = 1/K folds the timestep mean, d_trak_grad.py:770) */
 int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, int64_t numel, int64_t src_stride,
-                    void* staged, int64_t ld, int64_t row0, int64_t col0, float scale, void* stream);
+                    void* staged, int64_t d_pad, int64_t m_cap, int64_t row0, int64_t col0, float scale, void* stream);
 
-/* out[m, :] (+)= staged[m, :] * P[p_base : p_base + d_pad, 0:proj_dim]
- *   staged: bf16 [m_rows <= 512, d_pad] row-major with pitch ld (elements); d_pad % 64 == 0, ld % 8 == 0,
- *           16-byte aligned base; columns beyond the real gradient length must be zero
- *   p_base: canonical index (row of P) of staged column 0, multiple of 64
+/* out[m, :] (+)= G[m, :] * P[p_base : p_base + d_pad, 0:proj_dim]  for the first m_rows rows of the staging buffer
+ *   staged: layout above; d_pad % 64 == 0; positions beyond the real gradient length must be zero;
+ *           rows >= m_rows may hold anything (they only feed output rows that are never written)
+ *   m_rows <= 512 (256 for cta_group 1), m_cap >= m_rows
+ *   p_base: canonical index (row of P) of position 0, multiple of 64
  *   proj_dim % 256 == 0; seed64 = seed + 10^4 * model_id (CudaProjector semantics)
  *   out: fp32 [m_rows, proj_dim] with pitch ld_out; accumulate != 0 adds to out (D-chunked projection)
  *   cta_group: 2 (CTA-pair UMMA, default) or 1 */
-int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t ld, int64_t p_base,
+int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t m_cap, int64_t p_base,
                         int64_t proj_dim, uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate,
                         void* workspace, int64_t workspace_bytes, int cta_group, void* stream);
 
