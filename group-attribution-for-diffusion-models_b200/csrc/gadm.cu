@@ -139,16 +139,16 @@ int plan_projection(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_d
   return GADM_OK;
 }
 
-template <int kCtaGroup>
+template <int kCtaGroup, int kWarpsPerGroup>
 int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Args& args, uint32_t n_clusters,
                    cudaStream_t stream) {
   using C = gadm::proj::Cfg<kCtaGroup>;
-  auto kernel = gadm::proj::project_kernel<kCtaGroup>;
+  auto kernel = gadm::proj::project_kernel<kCtaGroup, kWarpsPerGroup>;
   GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   cudaLaunchConfig_t cfg{};
   const uint32_t clusters = args.n_units < n_clusters ? args.n_units : n_clusters;
   cfg.gridDim = dim3(clusters * kCtaGroup);
-  cfg.blockDim = dim3(gadm::proj::kThreads);
+  cfg.blockDim = dim3(gadm::proj::Roles<kWarpsPerGroup>::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -297,7 +297,13 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
     a.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
   }
   cudaStream_t st = as_stream(stream);
-  rc = (cta_group == 2) ? launch_project<2>(h, tmap, a, p.n_clusters, st) : launch_project<1>(h, tmap, a, p.n_clusters, st);
+  // generator warps per pipeline slot: 2 for Rademacher (cheap bits -> signs), 4 for the MUFU-heavy Box-Muller
+  int gw = (proj_type == GADM_PROJ_NORMAL) ? 4 : 2;
+  if (const char* e = getenv("GADM_PROJ_GEN_WARPS")) gw = (atoi(e) == 4) ? 4 : 2;  // tuning override
+  if (cta_group == 2)
+    rc = (gw == 4) ? launch_project<2, 4>(h, tmap, a, p.n_clusters, st) : launch_project<2, 2>(h, tmap, a, p.n_clusters, st);
+  else
+    rc = (gw == 4) ? launch_project<1, 4>(h, tmap, a, p.n_clusters, st) : launch_project<1, 2>(h, tmap, a, p.n_clusters, st);
   if (rc != GADM_OK) return rc;
   dim3 rgrid((unsigned)((proj_dim / 4 + 127) / 128), (unsigned)m_rows);
   gadm::proj::project_reduce_kernel<<<rgrid, 128, 0, st>>>(a.partial, out, ld_out, (uint32_t)m_rows, p.n_tiles,

@@ -60,10 +60,12 @@ __device__ __forceinline__ uint32_t box_muller_pair_bf16(uint32_t x) {
   const float u1 = __fmaf_rn(flo, 0.0000152587890625f, kBias);
   const float turn = __fmaf_rn(fhi, 0.0000152587890625f, kBias);
   const float theta = __fmul_rn(turn, 6.283185307179586f);
-  float r;  // sqrt(-2 ln u1) = sqrt(-2 ln2 * log2 u1), MUFU.LG2 + MUFU.SQRT
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(-1.3862943611198906f, __log2f(u1))));
-  float s, c;
-  __sincosf(theta, &s, &c);
+  // .ftz forms: one MUFU each (the non-ftz lg2/sin/cos add FSETP/FMUL/FADD subnormal fix-ups; u1 >= 2^-17)
+  float l2, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(-1.3862943611198906f, l2)));  // sqrt(-2 ln u1)
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(theta));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(theta));
   const __nv_bfloat162 v = __floats2bfloat162_rn(__fmul_rn(r, c), __fmul_rn(r, s));  // .x (low) = even p
   return *reinterpret_cast<const uint32_t*>(&v);
 }
