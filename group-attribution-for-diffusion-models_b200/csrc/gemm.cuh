@@ -12,10 +12,11 @@
 // relative, is dropped) -- "3xTF32", fp32 accumulation in TMEM.
 //
 // Pipeline per CTA (one 128 x 128 output tile, 3 stages of K = 32):
-//   warp 0   TMA: raw fp32 tiles of A and B (128B swizzle)            -> raw_full[s]
-//   warps 8-15 split raw -> hi (in place) + lo, fence.proxy.async     -> split_full[s]
-//   warp 1   MMA issue (one thread), tcgen05.commit                   -> empty[s], acc_full
-//   warps 4-7 epilogue: tcgen05.ld -> alpha/beta/diag-shift -> global
+//   warp 0     TMA: raw fp32 tiles of A and B (128B swizzle)              -> raw_full[s]
+//   warps 12-15 split raw -> hi (in place) + lo, fence.proxy.async        -> split_full[s]
+//   warp 1     MMA issue (one thread), tcgen05.commit                     -> empty[s], acc_full[buf]
+//   warps 4-11 promote each 128-element K chunk TMEM -> fp32 registers    -> acc_empty[buf];
+//              at the end alpha/beta/diag-shift -> global
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,13 +31,15 @@ constexpr int kBN = 128;
 constexpr int kBK = 32;     // fp32 elements per smem row = 128 B
 constexpr int kUmmaK = 8;   // tf32
 constexpr int kStages = 3;
+constexpr int kChunkKB = 4; // k-blocks (128 contraction elements) accumulated in TMEM before promotion
 constexpr int kTileBytes = kBM * kBK * 4;                 // 16 KiB (A and B tiles have the same shape)
 constexpr int kStageBytes = 4 * kTileBytes;               // rawA(hi) | rawB(hi) | loA | loB
-constexpr int kSplitWarps = 8;
+constexpr int kEpiWarps = 8;                              // 2 per TMEM lane quarter, 64 columns each
+constexpr int kSplitWarps = 4;
 constexpr int kFirstEpiWarp = 4;
-constexpr int kFirstSplitWarp = 8;
+constexpr int kFirstSplitWarp = kFirstEpiWarp + kEpiWarps;
 constexpr int kThreads = (kFirstSplitWarp + kSplitWarps) * 32;
-constexpr int kTmemCols = 128;
+constexpr int kTmemCols = 256;                            // two 128-column accumulator buffers
 constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
 
 struct Args {
@@ -62,6 +65,11 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
   lo = __float_as_uint(__fsub_rn(__uint_as_float(x), __uint_as_float(hi)));
 }
 
+// Why chunks: the tensor core adds into its fp32 accumulator with truncation, so a long same-sign sum
+// (the diagonal of a Gram matrix is one) drifts by ~(steps/2) * 2^-24 relative -- 5e-4 at 50 000
+// examples, far above fp32 GEMM accuracy.  The MMA warp therefore accumulates only kChunkKB k-blocks in
+// TMEM, ping-ponging between two accumulator buffers, and the epilogue warps promote every finished chunk
+// into fp32 registers with round-to-nearest adds while the next chunk is being multiplied.
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const Args a) {
@@ -74,8 +82,9 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   auto raw_full = [&](int s) { return bar_base + 8u * s; };
   auto split_full = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  const uint32_t acc_full = bar_base + 8u * (3 * kStages);
-  const uint32_t tmem_slot = acc_full + 8u;
+  auto acc_full = [&](int b) { return bar_base + 8u * (3 * kStages + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (3 * kStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * kStages + 4);
   auto hi_a = [&](int s) { return smem_base + s * kStageBytes; };
   auto hi_b = [&](int s) { return smem_base + s * kStageBytes + kTileBytes; };
   auto lo_a = [&](int s) { return smem_base + s * kStageBytes + 2 * kTileBytes; };
@@ -83,6 +92,7 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (a.K + kBK - 1) / kBK;
+  const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_b); }
   if (warp == 1 && lane == 0) {
@@ -91,7 +101,10 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(split_full(s), kSplitWarps);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, kTmemCols);
@@ -115,51 +128,72 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, kBM, kBN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1u;
-        mbar_wait(split_full(s), ph, 0x1200 + s);
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(acc_empty(buf), ((c >> 1) & 1u) ^ 1u, 0x1500 + buf);
         tcgen05_fence_after();
-        const uint64_t dha = umma_desc_kmajor_sw128(hi_a(s)), dhb = umma_desc_kmajor_sw128(hi_b(s));
-        const uint64_t dla = umma_desc_kmajor_sw128(lo_a(s)), dlb = umma_desc_kmajor_sw128(lo_b(s));
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        const int kb_end = (c + 1) * kChunkKB < nkb ? (c + 1) * kChunkKB : nkb;
+        for (int kb = c * kChunkKB; kb < kb_end; ++kb) {
+          const int s = kb % kStages;
+          const uint32_t ph = (kb / kStages) & 1u;
+          mbar_wait(split_full(s), ph, 0x1200 + s);
+          tcgen05_fence_after();
+          const uint64_t dha = umma_desc_kmajor_sw128(hi_a(s)), dhb = umma_desc_kmajor_sw128(hi_b(s));
+          const uint64_t dla = umma_desc_kmajor_sw128(lo_a(s)), dlb = umma_desc_kmajor_sw128(lo_b(s));
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-          umma_tf32(tmem_base, dla + 2u * k, dhb + 2u * k, idesc, first);  // small terms first
-          umma_tf32(tmem_base, dha + 2u * k, dlb + 2u * k, idesc, 1u);
-          umma_tf32(tmem_base, dha + 2u * k, dhb + 2u * k, idesc, 1u);
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint32_t first = (kb == c * kChunkKB && k == 0) ? 0u : 1u;
+            umma_tf32(d_tmem, dla + 2u * k, dhb + 2u * k, idesc, first);  // small terms first
+            umma_tf32(d_tmem, dha + 2u * k, dlb + 2u * k, idesc, 1u);
+            umma_tf32(d_tmem, dha + 2u * k, dhb + 2u * k, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        umma_commit(acc_full(buf));
       }
-      umma_commit(acc_full);
     }
   } else if (warp >= kFirstEpiWarp && warp < kFirstSplitWarp) {
-    const int q = warp & 3;
-    mbar_wait(acc_full, 0, 0x1300);
-    tcgen05_fence_after();
-    const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
-    const int64_t col0 = static_cast<int64_t>(tile_n) * kBN;
-#pragma unroll 1
-    for (int c = 0; c < kBN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
-      tmem_ld_wait();
-      if (row < a.M) {
-        float* crow = a.C + row * a.ldc;
+    const int e = warp - kFirstEpiWarp;
+    const int q = warp & 3;       // TMEM lane quarter this warp may read
+    const int half = e >> 2;      // which 64 of the 128 accumulator columns
+    float acc[64];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int64_t col = col0 + c + i;
-          if (col < a.N) {
-            float r = a.alpha * __uint_as_float(v[i]);
-            if (a.beta != 0.f) r += a.beta * crow[col];
-            if (col == row) r += a.diag_add;
-            crow[col] = r;
-          }
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(acc_full(buf), (c >> 1) & 1u, 0x1300 + buf);
+      tcgen05_fence_after();
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBN + half * 64;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t0 + j * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(v[i]));
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+    const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
+    const int64_t col0 = static_cast<int64_t>(tile_n) * kBN + half * 64;
+    if (row < a.M) {
+      float* crow = a.C + row * a.ldc;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const int64_t col = col0 + i;
+        if (col < a.N) {
+          float r = a.alpha * acc[i];
+          if (a.beta != 0.f) r += a.beta * crow[col];
+          if (col == row) r += a.diag_add;
+          crow[col] = r;
         }
       }
     }
   } else if (warp >= kFirstSplitWarp) {
-    const int t = threadIdx.x - kFirstSplitWarp * 32;  // 0..255
+    const int t = threadIdx.x - kFirstSplitWarp * 32;  // 0..127
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (kb / kStages) & 1u;
@@ -167,7 +201,7 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       // raw A|B are contiguous (2 * kTileBytes), lo A|B follow at +2*kTileBytes: purely elementwise, the
       // swizzle is a function of the address bits inside each 1024-B atom and is identical for hi and lo.
       const uint32_t raw = hi_a(s);
-#pragma unroll 4
+#pragma unroll 8
       for (int i = 0; i < (2 * kTileBytes) / 16 / (kSplitWarps * 32); ++i) {
         const uint32_t off = (static_cast<uint32_t>(i) * (kSplitWarps * 32) + t) * 16u;
         const uint4 x = ld_shared_v4(raw + off);
