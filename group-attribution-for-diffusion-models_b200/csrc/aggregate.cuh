@@ -65,32 +65,36 @@ __global__ void mask_gram_kernel(const uint32_t* __restrict__ colbits, int64_t d
 // out[i, k] = ( sum_r X[r,i] * (Y[r,k] - shift[k]) - half * sum_r (Y[r,k] - shift[k]) ) * scale
 //   Shapley: shift = v0, half = 0, scale = 1/n   (datashapley.py:30)
 //   Banzhaf: shift = 0 (null), half = 0.5, scale = 1   (databanzhaf.py:23)
-// Also serves X_test @ phi (evaluate_lds) through the transposed call mask_times_matrix_kernel below.
-constexpr int kXtyI = 8;  // players per thread
-__global__ void mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ Y,
-                                int64_t n, int64_t d, int64_t K, const double* __restrict__ shift, double half,
-                                double scale, double* __restrict__ out) {
-  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kXtyI;
-  if (k >= K) return;
+// Block = 64 behaviour columns x 4 mask words: thread (kx, s) owns the 32 players of word (4*blockIdx.y + s)
+// for column k, so a block covers 128 players and Y is streamed from HBM once when d <= 128 (coalesced 512-B
+// row segments; the mask word is a warp-wide broadcast).  Rows are visited in order: deterministic sums.
+constexpr int kXtyCols = 64;
+constexpr int kXtyWords = 4;
+__global__ void __launch_bounds__(kXtyCols * kXtyWords)
+mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ Y, int64_t n, int64_t d,
+                int64_t K, const double* __restrict__ shift, double half, double scale, double* __restrict__ out) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * kXtyCols + threadIdx.x;
+  const int64_t word = static_cast<int64_t>(blockIdx.y) * kXtyWords + threadIdx.y;
+  if (k >= K || word >= wd) return;
   const double sh = shift ? shift[k] : 0.0;
-  double acc[kXtyI];
+  double acc[32];
 #pragma unroll
-  for (int t = 0; t < kXtyI; ++t) acc[t] = 0.0;
+  for (int t = 0; t < 32; ++t) acc[t] = 0.0;
   double tot = 0.0;
-  const int64_t word = i0 >> 5;
-  const int bit0 = static_cast<int>(i0 & 31);
+#pragma unroll 2
   for (int64_t r = 0; r < n; ++r) {
     const double y = Y[r * K + k] - sh;
-    const uint32_t bits = rowbits[r * wd + word] >> bit0;  // kXtyI divides 32: the 8 players share a word
+    const uint32_t bits = rowbits[r * wd + word];
     tot += y;
 #pragma unroll
-    for (int t = 0; t < kXtyI; ++t)
+    for (int t = 0; t < 32; ++t)
       if ((bits >> t) & 1u) acc[t] += y;
   }
 #pragma unroll
-  for (int t = 0; t < kXtyI; ++t)
-    if (i0 + t < d) out[(i0 + t) * K + k] = (acc[t] - half * tot) * scale;
+  for (int t = 0; t < 32; ++t) {
+    const int64_t i = word * 32 + t;
+    if (i < d) out[i * K + k] = (acc[t] - half * tot) * scale;
+  }
 }
 
 // out[r, k] = sum_i X[r,i] * M[i,k]   (x_test @ attrs, shapley_lds.py:145)

@@ -502,9 +502,11 @@ int gadm_mask_xty(gadm_handle h, const uint32_t* rowbits, const double* y, int64
                   const double* shift, double half, double scale, double* out, void* stream) {
   GADM_REQUIRE(h && rowbits && y && out && n > 0 && d > 0 && k > 0, "bad argument");
   DeviceGuard guard(h->device);
-  dim3 grid((unsigned)((k + 127) / 128), (unsigned)((d + gadm::agg::kXtyI - 1) / gadm::agg::kXtyI));
-  gadm::agg::mask_xty_kernel<<<grid, 128, 0, as_stream(stream)>>>(rowbits, (d + 31) / 32, y, n, d, k, shift, half,
-                                                                  scale, out);
+  const int64_t wd = (d + 31) / 32;
+  dim3 grid((unsigned)((k + gadm::agg::kXtyCols - 1) / gadm::agg::kXtyCols),
+            (unsigned)((wd + gadm::agg::kXtyWords - 1) / gadm::agg::kXtyWords));
+  gadm::agg::mask_xty_kernel<<<grid, dim3(gadm::agg::kXtyCols, gadm::agg::kXtyWords), 0, as_stream(stream)>>>(
+      rowbits, wd, y, n, d, k, shift, half, scale, out);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

@@ -27,7 +27,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_sec
         "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 out = {}
 for h, u, v in zip(hdr, units, val):
-    if h in want or h.startswith("smsp__average_warp_latency_issue_stalled") or h.startswith("smsp__average_warps_issue_stalled"):
+    if (h in want or "pipe_tensor" in h or h.startswith("smsp__average_warps_issue_stalled")) and "pred_on" not in h:
         out[h] = f"{v} {u}".strip()
 for k in sorted(out):
     print(f"{k:100s} {out[k]}")
