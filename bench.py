@@ -238,6 +238,26 @@ def main():
     wd = handle.watchdog_code()
     assert wd == 0, f"kernel watchdog fired: {wd:#x}"
 
+    # the other projection type on the same staged rows (side number; the headline is --proj-type)
+    other = "rademacher" if args.proj_type == "normal" else "normal"
+    proj_o = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ProjectionType(other), dev, 32, stage_rows=STAGE_ROWS)
+    proj_o._stage, proj_o._ws = proj._stage, proj._ws
+    for _ in range(2):
+        proj_o._project_rows(stage, STAGE_ROWS, 0, out)
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for _ in range(3):
+        proj_o._project_rows(stage, STAGE_ROWS, 0, out)
+    o1.record()
+    barrier()
+    other_ms = max_over_ranks(o0.elapsed_time(o1)) / 3
+    other_line = {"proj_type": other, "ms_per_step": other_ms, "value": STAGE_ROWS * world / (other_ms * 1e-3),
+                  "unit": UNIT, "tflops_per_gpu": flops_per_launch / (other_ms * 1e-3) / 1e12,
+                  "frac_of_burst_peak": flops_per_launch / (other_ms * 1e-3) / 1e12 / peaks["bf16_burst"],
+                  "frac_of_sustained_peak": flops_per_launch / (other_ms * 1e-3) / 1e12 / peaks["bf16_sustained"]}
+    proj_o._stage = proj_o._ws = None
+
     # ---------------- end to end: pinned host fp32 gradients -> public API -> features back on the host
     e2e = None
     if not args.no_e2e:
@@ -296,6 +316,7 @@ def main():
             extra = side_measurements(dev, rank, world)
         except Exception as e:  # never lose the headline line
             extra = {"error": f"{type(e).__name__}: {e}"}
+    extra["projection_other_type"] = other_line
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

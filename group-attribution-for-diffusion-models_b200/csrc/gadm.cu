@@ -402,7 +402,7 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
   for (int64_t b = 0; b < nblk; ++b) {
     const int64_t j0 = b * NB;
     const int nb = (int)((k - j0) < NB ? (k - j0) : NB);
-    potrf<<<1, NB, gadm::gemm::kPotrfSmem, as_stream(stream)>>>(a + j0 * ld + j0, ld, nb, linv + b * NB * NB,
+    potrf<<<1, gadm::gemm::kPotrfThreads, gadm::gemm::kPotrfSmem, as_stream(stream)>>>(a + j0 * ld + j0, ld, nb, linv + b * NB * NB,
                                                                linv_t + b * NB * NB, info, (int)b);
     GADM_LAUNCHED(h);
     const int64_t rem = k - (j0 + nb);

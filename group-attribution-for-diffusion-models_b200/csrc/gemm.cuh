@@ -242,51 +242,68 @@ __global__ void transpose_kernel(const float* __restrict__ in, int64_t R, int64_
 }
 
 // Cholesky of one nb x nb diagonal block (nb <= 128), in place (lower; strict upper zeroed), plus the
-// inverse of the factor and its transpose (dense nb x nb, pitch 128) for the GEMM-based panel solves.
+// inverse of the factor and its transpose (dense nb x nb, pitch 128, identity-padded) for the GEMM-based
+// panel solves.  One CTA of 512 threads, block resident in shared memory; right-looking: per column one
+// scale phase and one rank-1 trailing update spread over all threads (16 x 32 thread grid), then a
+// column-parallel forward substitution for the inverse with 4 lanes sharing each column's dot product.
 constexpr int kPotrfNb = 128;
 constexpr int kPotrfLd = kPotrfNb + 1;
+constexpr int kPotrfThreads = 512;
 constexpr int kPotrfSmem = 2 * kPotrfNb * kPotrfLd * 4;
-__global__ void __launch_bounds__(kPotrfNb, 1)
+__global__ void __launch_bounds__(kPotrfThreads, 1)
 potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__ linv, float* __restrict__ linv_t,
                   int* __restrict__ info, int block_index) {
   extern __shared__ float potrf_smem[];
   float* L = potrf_smem;                       // [nb][kPotrfLd]
-  float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse
-  const int i = threadIdx.x;
-  for (int r = 0; r < nb; ++r)
-    if (i < nb) L[r * kPotrfLd + i] = A[static_cast<int64_t>(r) * ld + i];
+  float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse of the factor
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  for (int idx = tid; idx < nb * nb; idx += kPotrfThreads) {
+    const int r = idx / nb, c = idx % nb;
+    L[r * kPotrfLd + c] = A[static_cast<int64_t>(r) * ld + c];
+  }
   __syncthreads();
   for (int j = 0; j < nb; ++j) {
-    double s = 0.0;
-    if (i >= j && i < nb) {
-      s = static_cast<double>(L[i * kPotrfLd + j]);
-      for (int t = 0; t < j; ++t) s -= static_cast<double>(L[i * kPotrfLd + t]) * static_cast<double>(L[j * kPotrfLd + t]);
+    float d = L[j * kPotrfLd + j];
+    if (!(d > 0.f)) {
+      if (tid == 0 && info) atomicMax(info, block_index * kPotrfNb + j + 1);
+      d = 1.f;
     }
-    __shared__ double s_diag;
-    if (i == j) {
-      if (!(s > 0.0)) { if (info) atomicMax(info, block_index * kPotrfNb + j + 1); s = 1.0; }
-      s_diag = sqrt(s);
-    }
+    const float sd = sqrtf(d);
+    const float inv = 1.f / sd;
+    __syncthreads();  // everyone has read the pivot before it is overwritten
+    if (tid == j) L[j * kPotrfLd + j] = sd;
+    if (tid > j && tid < nb) L[tid * kPotrfLd + j] *= inv;
     __syncthreads();
-    if (i >= j && i < nb) L[i * kPotrfLd + j] = (i == j) ? static_cast<float>(s_diag) : static_cast<float>(s / s_diag);
+    for (int i = j + 1 + ty; i < nb; i += kPotrfThreads / 32) {
+      const float lij = L[i * kPotrfLd + j];
+      for (int c = j + 1 + tx; c <= i; c += 32) L[i * kPotrfLd + c] = fmaf(-lij, L[c * kPotrfLd + j], L[i * kPotrfLd + c]);
+    }
     __syncthreads();
   }
-  // inverse of the lower factor, column i per thread (forward substitution)
-  if (i < nb) {
-    for (int r = 0; r < nb; ++r) {
-      double s = (r == i) ? 1.0 : 0.0;
-      if (r < i) { X[r * kPotrfLd + i] = 0.f; continue; }
-      for (int t = i; t < r; ++t) s -= static_cast<double>(L[r * kPotrfLd + t]) * static_cast<double>(X[t * kPotrfLd + i]);
-      X[r * kPotrfLd + i] = static_cast<float>(s / static_cast<double>(L[r * kPotrfLd + r]));
+  // X = L^-1: column c by lanes 4c..4c+3 of the block (same warp), forward substitution down the rows
+  {
+    const int c = tid >> 2, part = tid & 3;
+    if (c < nb) {
+      for (int r = 0; r < c; ++r)
+        if (part == 0) X[r * kPotrfLd + c] = 0.f;
+      for (int r = c; r < nb; ++r) {
+        float s = 0.f;
+        for (int t = c + part; t < r; t += 4) s = fmaf(L[r * kPotrfLd + t], X[t * kPotrfLd + c], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) X[r * kPotrfLd + c] = (((r == c) ? 1.f : 0.f) - s) / L[r * kPotrfLd + r];
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
-  for (int r = 0; r < kPotrfNb; ++r) {
-    const bool in = (r < nb && i < nb);
-    if (in) A[static_cast<int64_t>(r) * ld + i] = (i <= r) ? L[r * kPotrfLd + i] : 0.f;
-    const float x = in ? X[r * kPotrfLd + i] : ((r == i) ? 1.f : 0.f);  // identity padding keeps the block invertible
-    linv[r * kPotrfNb + i] = x;
-    linv_t[i * kPotrfNb + r] = x;
+  for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) {
+    const int r = idx / kPotrfNb, c = idx % kPotrfNb;
+    const bool in = (r < nb && c < nb);
+    if (in) A[static_cast<int64_t>(r) * ld + c] = (c <= r) ? L[r * kPotrfLd + c] : 0.f;
+    const float x = in ? X[r * kPotrfLd + c] : ((r == c) ? 1.f : 0.f);  // identity padding keeps the block invertible
+    linv[r * kPotrfNb + c] = x;
+    linv_t[c * kPotrfNb + r] = x;
   }
 }
 
