@@ -280,20 +280,22 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
     }
     __syncthreads();
   }
-  // X = L^-1: column c by lanes 4c..4c+3 of the block (same warp), forward substitution down the rows
+  // X = L^-1: column c by lanes 4c..4c+3 of the block (same warp), forward substitution down the rows.
+  // Every lane runs the loops (warp-wide shuffles); lanes whose column is out of range only skip the memory ops.
   {
     const int c = tid >> 2, part = tid & 3;
-    if (c < nb) {
-      for (int r = 0; r < c; ++r)
-        if (part == 0) X[r * kPotrfLd + c] = 0.f;
-      for (int r = c; r < nb; ++r) {
-        float s = 0.f;
-        for (int t = c + part; t < r; t += 4) s = fmaf(L[r * kPotrfLd + t], X[t * kPotrfLd + c], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (part == 0) X[r * kPotrfLd + c] = (((r == c) ? 1.f : 0.f) - s) / L[r * kPotrfLd + r];
-        __syncwarp();
-      }
+    const bool active = c < nb;
+    const int cc = active ? c : 0;
+    if (active && part == 0)
+      for (int r = 0; r < cc; ++r) X[r * kPotrfLd + cc] = 0.f;
+    for (int r = 0; r < nb; ++r) {
+      float s = 0.f;
+      if (active && r >= cc)
+        for (int t = cc + part; t < r; t += 4) s = fmaf(L[r * kPotrfLd + t], X[t * kPotrfLd + cc], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (active && part == 0 && r >= cc) X[r * kPotrfLd + cc] = (((r == cc) ? 1.f : 0.f) - s) / L[r * kPotrfLd + r];
+      __syncwarp();
     }
   }
   __syncthreads();
