@@ -166,6 +166,32 @@ def data_banzhaf(x_train, y_train):
     return data_banzhaf_batched(x_train, np.asarray(y_train, dtype=np.float64).reshape(-1, 1))[:, 0]
 
 
+def loo_attr_batched(train_masks, train_targets, full_targets, device=None, as_numpy: bool = True):
+    """Leave-one-out attributions for all behaviours (lds.py:436-440):
+    coeff[i, k] = sum_r (1 - X[r, i]) * (full[k] - y[r, k])  -> [d, K]."""
+    masks = train_masks if isinstance(train_masks, PackedMasks) else PackedMasks(train_masks, device)
+    y = _dev_f64(train_targets, masks.device)
+    if y.dim() == 1:
+        y = y[:, None]
+    full = _dev_f64(np.broadcast_to(np.asarray(full_targets, dtype=np.float64).reshape(-1), (y.shape[1],)), masks.device)
+    # X^T (y - full) = -sum_r X (full - y); sum_r (1 - X)(full - y) = sum_r (full - y) - sum_r X (full - y)
+    xt = masks.xty(y, full, 0.0, 1.0)                       # sum_r X[r,i] (y - full)
+    tot = (y - full[None, :]).sum(dim=0)                    # sum_r (y - full)   [K]
+    coef = xt - tot[None, :]                                # = sum_r (1 - X)(full - y)
+    return coef.cpu().numpy() if as_numpy else coef
+
+
+def aoi_attr_batched(train_masks, train_targets, null_targets, device=None, as_numpy: bool = True):
+    """Add-one-in attributions (lds.py:442-445): coeff[i, k] = sum_r X[r, i] * (y[r, k] - null[k]) -> [d, K]."""
+    masks = train_masks if isinstance(train_masks, PackedMasks) else PackedMasks(train_masks, device)
+    y = _dev_f64(train_targets, masks.device)
+    if y.dim() == 1:
+        y = y[:, None]
+    null = _dev_f64(np.broadcast_to(np.asarray(null_targets, dtype=np.float64).reshape(-1), (y.shape[1],)), masks.device)
+    coef = masks.xty(y, null, 0.0, 1.0)
+    return coef.cpu().numpy() if as_numpy else coef
+
+
 def spearman_matrix(x_test, y_test, attrs, idx=None, device=None, as_numpy: bool = True):
     """rho[e, k] = spearmanr(x_test[idx[e]] @ attrs[:, k], y_test[idx[e], k]); idx None -> one identity row."""
     masks = x_test if isinstance(x_test, PackedMasks) else PackedMasks(x_test, device)

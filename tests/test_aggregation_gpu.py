@@ -163,3 +163,19 @@ def test_group_reduce_and_ranks_vs_traks_golden():
     # ties resolve to the lower index; NaNs last
     x = np.array([1.0, 3.0, 3.0, np.nan, -2.0, 3.0, 1.0])
     np.testing.assert_array_equal(G.stable_rank(x), np.argsort(-x, kind="stable"))
+
+
+def test_loo_and_aoi_attributions():
+    """lds.py:436-445 per-behaviour sums, batched over behaviours."""
+    import gadm_b200 as G
+
+    rng = np.random.RandomState(5)
+    n, d, K = 60, 37, 9
+    X = (rng.rand(n, d) > 0.3).astype(float)
+    Y = rng.normal(size=(n, K))
+    full, null = rng.normal(size=K), rng.normal(size=K)
+    loo = G.loo_attr_batched(X, Y, full)
+    aoi = G.aoi_attr_batched(X, Y, null)
+    for k in range(K):
+        _close(loo[:, k], oagg.loo_attr(X, Y[:, k], full[k]), 1e-11)
+        _close(aoi[:, k], oagg.aoi_attr(X, Y[:, k], null[k]), 1e-11)
