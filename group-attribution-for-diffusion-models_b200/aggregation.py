@@ -76,7 +76,7 @@ class PackedMasks:
     def times(self, mat: torch.Tensor) -> torch.Tensor:
         out = torch.empty(self.n, mat.shape[1], dtype=_f64, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.h.lib.gadm_mask_times_matrix(self.h.ptr, self.rowbits.data_ptr(), mat.data_ptr(), self.n,
+            _lib.check(self.h.lib.gadm_mask_times_matrix(self.h.ptr, self.colbits.data_ptr(), mat.data_ptr(), self.n,
                                                         self.d, mat.shape[1], out.data_ptr(),
                                                         _lib.stream_ptr(self.device)))
         return out

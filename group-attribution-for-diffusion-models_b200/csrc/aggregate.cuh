@@ -97,23 +97,9 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
   }
 }
 
-// out[r, k] = sum_i X[r,i] * M[i,k]   (x_test @ attrs, shapley_lds.py:145)
-__global__ void mask_times_matrix_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ M,
-                                         int64_t m, int64_t d, int64_t K, double* __restrict__ out) {
-  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t r = blockIdx.y;
-  if (k >= K || r >= m) return;
-  double acc = 0.0;
-  for (int64_t w = 0; w < wd; ++w) {
-    uint32_t bits = rowbits[r * wd + w];
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      acc += M[(w * 32 + b) * K + k];
-    }
-  }
-  out[r * K + k] = acc;
-}
+// X_test @ attrs (shapley_lds.py:145): out[r, k] = sum_i X[r,i] * M[i,k] is the same kernel with the roles of
+// rows and players swapped -- pass the *column* bit planes (bits over rows r for each player i) as `rowbits`,
+// n := d (the summed index), d := m (the outputs): every M[i, :] row is then streamed exactly once.
 
 // ------------------------------------------------------------------ symmetric pseudo-inverse
 // One-sided (Hestenes) Jacobi SVD of a symmetric matrix, fp64, one CTA.  Rows of G start as the rows

@@ -511,12 +511,15 @@ int gadm_mask_xty(gadm_handle h, const uint32_t* rowbits, const double* y, int64
   return GADM_OK;
 }
 
-int gadm_mask_times_matrix(gadm_handle h, const uint32_t* rowbits, const double* mat, int64_t m, int64_t d, int64_t k,
+int gadm_mask_times_matrix(gadm_handle h, const uint32_t* colbits, const double* mat, int64_t m, int64_t d, int64_t k,
                            double* out, void* stream) {
-  GADM_REQUIRE(h && rowbits && mat && out && m > 0 && d > 0 && k > 0 && m < 65536, "bad argument");
+  GADM_REQUIRE(h && colbits && mat && out && m > 0 && d > 0 && k > 0, "bad argument");
   DeviceGuard guard(h->device);
-  dim3 grid((unsigned)((k + 127) / 128), (unsigned)m);
-  gadm::agg::mask_times_matrix_kernel<<<grid, 128, 0, as_stream(stream)>>>(rowbits, (d + 31) / 32, mat, m, d, k, out);
+  const int64_t wm = (m + 31) / 32;  // words per player in the column bit planes
+  dim3 grid((unsigned)((k + gadm::agg::kXtyCols - 1) / gadm::agg::kXtyCols),
+            (unsigned)((wm + gadm::agg::kXtyWords - 1) / gadm::agg::kXtyWords));
+  gadm::agg::mask_xty_kernel<<<grid, dim3(gadm::agg::kXtyCols, gadm::agg::kXtyWords), 0, as_stream(stream)>>>(
+      colbits, wm, mat, /*summed=*/d, /*outputs=*/m, k, nullptr, 0.0, 1.0, out);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

@@ -143,8 +143,9 @@ int gadm_mask_gram(gadm_handle h, const uint32_t* colbits, int64_t n, int64_t d,
  * Shapley b_hat: shift = v0, half = 0, scale = 1/n ; Banzhaf rhs: shift = NULL, half = 0.5, scale = 1 */
 int gadm_mask_xty(gadm_handle h, const uint32_t* rowbits, const double* y, int64_t n, int64_t d, int64_t k,
                   const double* shift, double half, double scale, double* out, void* stream);
-/* out[r, k] = sum_i X[r,i] * M[i,k]  (x_test @ attrs_all, shapley_lds.py:145) ; M [d, K], out [m, K] */
-int gadm_mask_times_matrix(gadm_handle h, const uint32_t* rowbits, const double* mat, int64_t m, int64_t d, int64_t k,
+/* out[r, k] = sum_i X[r,i] * M[i,k]  (x_test @ attrs_all, shapley_lds.py:145) ; X given by its column bit planes
+ * colbits [d, ceil(m/32)], M [d, K], out [m, K]; each row of M is streamed once */
+int gadm_mask_times_matrix(gadm_handle h, const uint32_t* colbits, const double* mat, int64_t m, int64_t d, int64_t k,
                            double* out, void* stream);
 /* Moore-Penrose inverse of a symmetric matrix by one-sided Jacobi SVD; singular values <= rcond * max are
  * dropped (numpy.linalg.pinv / lstsq cut-off semantics).  info (device int[2], may be NULL) = {sweeps, rank}. */
