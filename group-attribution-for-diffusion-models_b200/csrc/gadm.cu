@@ -22,6 +22,7 @@ struct gadm_ctx {
   int device = 0;
   int num_sms = 0;
   int64_t launches = 0;
+  uint32_t* scratch = nullptr;  // small device scratch owned by the handle (lockstep counter)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
 
@@ -151,14 +152,42 @@ int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Arg
   cfg.blockDim = dim3(gadm::proj::Roles<kWarpsPerGroup>::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCtaGroup;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;  // co-residency guarantee for the inter-cluster lockstep
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
+  gadm::proj::Args a = args;
+  // lockstep only over the k-block count every launched cluster reaches (clusters own whole units round-robin)
+  uint64_t min_iters = ~0ull;
+  for (uint32_t c = 0; c < clusters; ++c) {
+    uint64_t iters = 0;
+    for (uint32_t u = c; u < a.n_units; u += clusters) {
+      const uint64_t split = u / a.n_tiles;
+      iters += (split + 1) * a.nkb_total / a.n_splits - split * a.nkb_total / a.n_splits;
+    }
+    if (iters < min_iters) min_iters = iters;
+  }
+  const char* nosync = getenv("GADM_PROJ_NO_LOCKSTEP");
+  a.sync_counter = h->scratch;
+  a.sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / gadm::proj::kSyncEvery) * gadm::proj::kSyncEvery);
+  const char* coop = getenv("GADM_PROJ_COOPERATIVE");  // "0": plain launch, lockstep kept (ncu cannot replay cooperative launches)
+  if (a.sync_iters) {
+    GADM_CUDA(cudaMemsetAsync(h->scratch, 0, sizeof(uint32_t), stream));
+    cfg.numAttrs = (coop && atoi(coop) == 0) ? 1 : 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, a);
+    if (e == cudaSuccess) {
+      h->launches++;
+      return GADM_OK;
+    }
+    (void)cudaGetLastError();  // cooperative launch refused (GPU shared / too large): run without the lockstep
+    a.sync_iters = 0;
+  }
   cfg.numAttrs = 1;
-  GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, args));
+  GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, a));
   h->launches++;
   return GADM_OK;
 }
@@ -192,11 +221,16 @@ int gadm_create(gadm_handle* out, int device) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  if (cudaMalloc(&h->scratch, 256) != cudaSuccess) {
+    delete h;
+    return fail(GADM_ERR_CUDA, "cudaMalloc of the handle scratch failed");
+  }
   *out = h;
   return GADM_OK;
 }
 
 int gadm_destroy(gadm_handle h) {
+  if (h && h->scratch) cudaFree(h->scratch);
   delete h;
   return GADM_OK;
 }

@@ -81,7 +81,29 @@ struct Args {
   uint32_t proj_type;   // ProjType
   uint32_t p_base_div64;  // canonical index of staged column 0, / 64
   uint32_t debug;         // perf ablation only (GADM_PROJ_DEBUG): bit0 skip generation, bit1 skip TMA loads
+  uint32_t* sync_counter; // zeroed device word for the inter-cluster lockstep (nullptr: disabled)
+  uint32_t sync_iters;    // lockstep only while the cluster-local k-block counter is below this (multiple of kSyncEvery)
 };
+
+// Inter-cluster lockstep.  The 16 clusters that work on the same D-split (one per 256-column tile) stream
+// the SAME gradient tiles; they only hit in L2 if they stay within the L2 retention window of each other
+// (~300 k-blocks).  Left alone they drift apart over a 15 000-k-block unit (two dies, arbitration jitter)
+// and the staged gradients were re-read 4.6-8.6x from HBM.  Every kSyncEvery k-blocks the leader CTA's TMA
+// thread therefore passes a monotonic global counter barrier; the 4-slot pipeline hides the wait.
+// All clusters are co-resident (grid <= SM count, cooperative launch), so the spin cannot deadlock.
+constexpr uint32_t kSyncEvery = 128;
+__device__ __forceinline__ void grid_lockstep(uint32_t* counter, uint32_t target) {
+  atomicAdd(counter, 1u);
+  const uint64_t t0 = globaltimer_ns();
+  const uint64_t limit = *reinterpret_cast<volatile unsigned long long*>(&g_watchdog_ns);
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= target) break;
+    __nanosleep(200);
+    if (limit != 0 && globaltimer_ns() - t0 > limit) watchdog_fire(0x600);
+  } while (true);
+}
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
@@ -188,6 +210,8 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u, 0x100 + s);
+          if (rank == 0 && it != 0 && it < a.sync_iters && (it % kSyncEvery) == 0)
+            grid_lockstep(a.sync_counter, (it / kSyncEvery) * n_clusters);
           if (a.debug & 2u) {  // ablation: no loads, operands are whatever the slot holds
             if (rank == 0) mbar_arrive(full_bar(s));
             continue;

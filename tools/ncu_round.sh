@@ -4,6 +4,7 @@
 set -u
 mkdir -p gpurun_out
 export GADM_WATCHDOG_SEC=0
+export GADM_PROJ_COOPERATIVE=0   # ncu kernel replay does not support cooperative launches
 for t in rademacher normal; do
   CMD="python tools/bench_projection.py --type $t --M 512 --k 4096 --D 4468288 --iters 1"
   timeout 200 $CMD > gpurun_out/plain_$t.log 2>&1 && \
