@@ -173,7 +173,9 @@ int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Arg
   }
   const char* nosync = getenv("GADM_PROJ_NO_LOCKSTEP");
   a.sync_counter = h->scratch;
-  a.sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / gadm::proj::kSyncEvery) * gadm::proj::kSyncEvery);
+  a.sync_every = gadm::proj::kSyncEvery;
+  if (const char* e = getenv("GADM_PROJ_SYNC_EVERY")) { const int v = atoi(e); if (v >= 4) a.sync_every = (uint32_t)v; }
+  a.sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / a.sync_every) * a.sync_every);
   const char* coop = getenv("GADM_PROJ_COOPERATIVE");  // "0": plain launch, lockstep kept (ncu cannot replay cooperative launches)
   if (a.sync_iters) {
     GADM_CUDA(cudaMemsetAsync(h->scratch, 0, sizeof(uint32_t), stream));

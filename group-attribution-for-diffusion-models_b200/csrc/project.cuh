@@ -82,7 +82,8 @@ struct Args {
   uint32_t p_base_div64;  // canonical index of staged column 0, / 64
   uint32_t debug;         // perf ablation only (GADM_PROJ_DEBUG): bit0 skip generation, bit1 skip TMA loads
   uint32_t* sync_counter; // zeroed device word for the inter-cluster lockstep (nullptr: disabled)
-  uint32_t sync_iters;    // lockstep only while the cluster-local k-block counter is below this (multiple of kSyncEvery)
+  uint32_t sync_iters;    // lockstep only while the cluster-local k-block counter is below this (multiple of sync_every)
+  uint32_t sync_every;    // k-blocks between lockstep points
 };
 
 // Inter-cluster lockstep.  The 16 clusters that work on the same D-split (one per 256-column tile) stream
@@ -91,7 +92,7 @@ struct Args {
 // and the staged gradients were re-read 4.6-8.6x from HBM.  Every kSyncEvery k-blocks the leader CTA's TMA
 // thread therefore passes a monotonic global counter barrier; the 4-slot pipeline hides the wait.
 // All clusters are co-resident (grid <= SM count, cooperative launch), so the spin cannot deadlock.
-constexpr uint32_t kSyncEvery = 128;
+constexpr uint32_t kSyncEvery = 128;  // default; GADM_PROJ_SYNC_EVERY overrides for tuning
 __device__ __forceinline__ void grid_lockstep(uint32_t* counter, uint32_t target) {
   atomicAdd(counter, 1u);
   const uint64_t t0 = globaltimer_ns();
@@ -210,8 +211,8 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u, 0x100 + s);
-          if (rank == 0 && it != 0 && it < a.sync_iters && (it % kSyncEvery) == 0)
-            grid_lockstep(a.sync_counter, (it / kSyncEvery) * n_clusters);
+          if (rank == 0 && it != 0 && it < a.sync_iters && (it % a.sync_every) == 0)
+            grid_lockstep(a.sync_counter, (it / a.sync_every) * n_clusters);
           if (a.debug & 2u) {  // ablation: no loads, operands are whatever the slot holds
             if (rank == 0) mbar_arrive(full_bar(s));
             continue;
