@@ -82,6 +82,15 @@ class PackedMasks:
         return out
 
 
+def masks_from_remaining_idx(remaining_idx_list, num_groups: int, device=None) -> PackedMasks:
+    """Bit-packed masks from the jsonl records' ``remaining_idx`` lists (shapley_lds.py:114-119, lds.py:232-233),
+    built as uint8 on the host (the jsonl / pandas parsing stays host Python) and packed on the device."""
+    x = np.zeros((len(remaining_idx_list), num_groups), dtype=np.uint8)
+    for r, idx in enumerate(remaining_idx_list):
+        x[r, np.asarray(idx, dtype=np.int64)] = 1
+    return PackedMasks(x, device)
+
+
 def _dev_f64(a, device) -> torch.Tensor:
     t = torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)) if not isinstance(a, torch.Tensor) else a)
     return t.to(device=device, dtype=_f64, non_blocking=True).contiguous()
