@@ -15,6 +15,7 @@
 #include "gadm_ptx.cuh"
 #include "philox.cuh"
 #include "project.cuh"
+#include "project_quad.cuh"
 #include "aggregate.cuh"
 #include "gemm.cuh"
 
@@ -23,6 +24,7 @@ struct gadm_ctx {
   int num_sms = 0;
   int64_t launches = 0;
   uint32_t* scratch = nullptr;  // small device scratch owned by the handle (lockstep counter)
+  int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
 
@@ -108,8 +110,10 @@ struct ProjPlan {
   int64_t ws_bytes;
 };
 
+int quad_cluster_count(gadm_handle h);
+
 int plan_projection(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_dim, int cta_group, ProjPlan* p) {
-  GADM_REQUIRE(cta_group == 1 || cta_group == 2, "cta_group must be 1 or 2, got %d", cta_group);
+  GADM_REQUIRE(cta_group == 1 || cta_group == 2 || cta_group == 4, "cta_group must be 1, 2 or 4, got %d", cta_group);
   GADM_REQUIRE(proj_dim > 0 && proj_dim % gadm::proj::kTileN == 0, "proj_dim %lld must be a positive multiple of 256",
                (long long)proj_dim);
   GADM_REQUIRE(d_pad > 0 && d_pad % gadm::proj::kBlockK == 0, "d_pad %lld must be a positive multiple of 64",
@@ -119,9 +123,15 @@ int plan_projection(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_d
                (long long)m_rows, (long long)max_rows, cta_group);
   p->n_tiles = (uint32_t)(proj_dim / gadm::proj::kTileN);
   p->nkb_total = (uint32_t)(d_pad / gadm::proj::kBlockK);
-  p->n_acc = (m_rows > (int64_t)gadm::proj::kAccRows * cta_group) ? 2u : 1u;
+  p->n_acc = (cta_group == 4 || m_rows > (int64_t)gadm::proj::kAccRows * cta_group) ? 2u : 1u;
   p->unit_rows = p->n_acc * gadm::proj::kAccRows * cta_group;
-  p->n_clusters = (uint32_t)(h->num_sms / cta_group);
+  if (cta_group == 4) {
+    const int qc = quad_cluster_count(h);
+    if (qc <= 0) return fail(GADM_ERR_CUDA, "no co-resident 4-CTA clusters available for the quad projection kernel");
+    p->n_clusters = (uint32_t)qc;
+  } else {
+    p->n_clusters = (uint32_t)(h->num_sms / cta_group);
+  }
   // smallest D-split count whose unit count fills whole waves of clusters to >= 97% (units of one
   // wave cover consecutive splits x all column tiles, so a gradient tile is re-read from L2, not HBM)
   uint32_t best = 1;
@@ -186,6 +196,75 @@ int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Arg
       return GADM_OK;
     }
     (void)cudaGetLastError();  // cooperative launch refused (GPU shared / too large): run without the lockstep
+    a.sync_iters = 0;
+  }
+  cfg.numAttrs = 1;
+  GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, a));
+  h->launches++;
+  return GADM_OK;
+}
+
+int quad_cluster_count(gadm_handle h) {
+  if (h->quad_clusters >= 0) return h->quad_clusters;
+  using C = gadm::proj::Cfg<2>;
+  auto kernel = gadm::proj::project_quad_kernel<4>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(h->num_sms / 4 * 4));
+    cfg.blockDim = dim3(gadm::proj::Roles<4>::kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+  } else {
+    (void)cudaGetLastError();
+  }
+  h->quad_clusters = n;
+  return n;
+}
+
+template <int kWarpsPerGroup>
+int launch_project_quad(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Args& args, uint32_t n_clusters,
+                        cudaStream_t stream) {
+  using C = gadm::proj::Cfg<2>;
+  auto kernel = gadm::proj::project_quad_kernel<kWarpsPerGroup>;
+  GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  cudaLaunchConfig_t cfg{};
+  const uint32_t clusters = args.n_units < n_clusters ? args.n_units : n_clusters;
+  cfg.gridDim = dim3(clusters * 4);
+  cfg.blockDim = dim3(gadm::proj::Roles<kWarpsPerGroup>::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
+  cfg.attrs = attr;
+  gadm::proj::Args a = args;
+  uint64_t min_iters = ~0ull;
+  for (uint32_t c = 0; c < clusters; ++c) {
+    uint64_t iters = 0;
+    for (uint32_t u = c; u < a.n_units; u += clusters) {
+      const uint64_t split = u / a.n_tiles;
+      iters += (split + 1) * a.nkb_total / a.n_splits - split * a.nkb_total / a.n_splits;
+    }
+    if (iters < min_iters) min_iters = iters;
+  }
+  const char* nosync = getenv("GADM_PROJ_NO_LOCKSTEP");
+  const char* coop = getenv("GADM_PROJ_COOPERATIVE");
+  a.sync_counter = h->scratch;
+  a.sync_every = gadm::proj::kSyncEvery;
+  a.sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / a.sync_every) * a.sync_every);
+  if (a.sync_iters) {
+    GADM_CUDA(cudaMemsetAsync(h->scratch, 0, sizeof(uint32_t), stream));
+    cfg.numAttrs = (coop && atoi(coop) == 0) ? 1 : 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, a);
+    if (e == cudaSuccess) { h->launches++; return GADM_OK; }
+    (void)cudaGetLastError();
     a.sync_iters = 0;
   }
   cfg.numAttrs = 1;
@@ -336,7 +415,9 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
   // generator warps per pipeline slot: 2 for Rademacher (cheap bits -> signs), 4 for the MUFU-heavy Box-Muller
   int gw = (proj_type == GADM_PROJ_NORMAL) ? 4 : 2;
   if (const char* e = getenv("GADM_PROJ_GEN_WARPS")) gw = (atoi(e) == 4) ? 4 : 2;  // tuning override
-  if (cta_group == 2)
+  if (cta_group == 4)
+    rc = (gw == 4) ? launch_project_quad<4>(h, tmap, a, p.n_clusters, st) : launch_project_quad<2>(h, tmap, a, p.n_clusters, st);
+  else if (cta_group == 2)
     rc = (gw == 4) ? launch_project<2, 4>(h, tmap, a, p.n_clusters, st) : launch_project<2, 2>(h, tmap, a, p.n_clusters, st);
   else
     rc = (gw == 4) ? launch_project<1, 4>(h, tmap, a, p.n_clusters, st) : launch_project<1, 2>(h, tmap, a, p.n_clusters, st);

@@ -152,6 +152,19 @@ __device__ __forceinline__ void tma_load_3d_cg2(uint32_t smem_dst, const void* t
       : "memory");
 }
 
+// shared::cta -> (peer) shared::cluster bulk copy through the async proxy; completion bytes are signalled on an
+// mbarrier that lives in the destination CTA
+__device__ __forceinline__ void bulk_copy_smem_to_cluster(uint32_t cluster_dst, uint32_t smem_src, uint32_t bytes,
+                                                          uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(cluster_dst), "r"(smem_src), "r"(bytes), "r"(cluster_bar)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM
 template <int kCtaGroup>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {

@@ -123,9 +123,13 @@ class CudaProjector:
             self._stage = torch.zeros(self.d_pad // TILE_K, rows, TILE_K, dtype=torch.bfloat16, device=self.device)
         return self._stage
 
+    def _group_for(self, rows: int) -> int:
+        """cta_group 4 (two CTA pairs sharing the generated P tiles) only pays when both pairs have rows."""
+        return 2 if (self.cta_group == 4 and rows <= 512) else self.cta_group
+
     def _workspace(self, rows: int) -> torch.Tensor:
         need = _lib.check(self._handle.lib.gadm_project_workspace_bytes(
-            self._handle.ptr, rows, self.d_pad, self.proj_dim, self.cta_group))
+            self._handle.ptr, rows, self.d_pad, self.proj_dim, self._group_for(rows)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -160,8 +164,8 @@ class CudaProjector:
         seed64 = (self.seed + SEED_MODEL_ID_STRIDE * int(model_id)) & 0xFFFFFFFFFFFFFFFF
         _lib.check(self._handle.lib.gadm_project_staged(
             self._handle.ptr, stage.data_ptr(), rows, self.d_pad, stage.shape[1], 0, self.proj_dim, seed64,
-            _PROJ_CODE[self.proj_type], out.data_ptr(), out.stride(0), 0, ws.data_ptr(), ws.numel(), self.cta_group,
-            _lib.stream_ptr(self.device)))
+            _PROJ_CODE[self.proj_type], out.data_ptr(), out.stride(0), 0, ws.data_ptr(), ws.numel(),
+            self._group_for(rows), _lib.stream_ptr(self.device)))
 
     # ------------------------------------------------------------------ reference API
     def project(self, grads: GradsLike, model_id: int) -> torch.Tensor:

@@ -77,11 +77,12 @@ int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, in
 /* out[m, :] (+)= G[m, :] * P[p_base : p_base + d_pad, 0:proj_dim]  for the first m_rows rows of the staging buffer
  *   staged: layout above; d_pad % 64 == 0; positions beyond the real gradient length must be zero;
  *           rows >= m_rows may hold anything (they only feed output rows that are never written)
- *   m_rows <= 512 (256 for cta_group 1), m_cap >= m_rows
+ *   m_rows <= 512 (256 for cta_group 1, 1024 for cta_group 4), m_cap >= m_rows
  *   p_base: canonical index (row of P) of position 0, multiple of 64
  *   proj_dim % 256 == 0; seed64 = seed + 10^4 * model_id (CudaProjector semantics)
  *   out: fp32 [m_rows, proj_dim] with pitch ld_out; accumulate != 0 adds to out (D-chunked projection)
- *   cta_group: 2 (CTA-pair UMMA, default) or 1 */
+ *   cta_group: 2 (CTA-pair UMMA, default), 1 (single CTA), or 4 = two CTA pairs per cluster that share the
+ *              generated P tiles through DSMEM bulk copies (halves the generator work; up to 1024 rows) */
 int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t m_cap, int64_t p_base,
                         int64_t proj_dim, uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate,
                         void* workspace, int64_t workspace_bytes, int cta_group, void* stream);

@@ -84,6 +84,34 @@ def test_project_matches_explicit_matrix(cta_group, ptype, B, D, k):
     assert np.all(np.abs(ratio - 1) < 6 / np.sqrt(k) + 5e-3), ratio
 
 
+@pytest.mark.parametrize("ptype", ["rademacher", "normal"])
+@pytest.mark.parametrize("B,D,k", [(700, 20000, 512), (1024, 9000, 1024), (513, 70001, 512)])
+def test_quad_cluster_variant_matches_explicit_matrix(ptype, B, D, k):
+    """cta_group=4: two CTA pairs per cluster share the generated P tiles (DSMEM bulk copies), 1024 rows per pass."""
+    g = torch.Generator(device="cpu").manual_seed(B + D)
+    grads = (torch.randn(B, D, generator=g) * 1e-2).to(DEV)
+    p = _proj(D, k, 77, ptype, cta_group=4)
+    assert p.stage_rows == 1024
+    got = p.project(grads, model_id=0)
+    torch.cuda.synchronize()
+    assert p._handle.watchdog_code() == 0
+    got = got.cpu().numpy().astype(np.float64)
+    G = grads.cpu().numpy()
+    if ptype == "rademacher":
+        want = project_explicit(G, seed=77, model_id=0, proj_type="rademacher", proj_dim=k)
+        pmax = 1.0
+    else:
+        P = p.materialize(0, D, model_id=0).cpu().numpy()
+        want = project_explicit(G, P)
+        pmax = float(np.abs(P).max())
+    gn = np.linalg.norm(philox.round_to_bf16(G).astype(np.float64), axis=1, keepdims=True)
+    tol = 2e-4 * gn * pmax + 1e-12
+    assert np.all(np.abs(got - want) <= tol), _report(got, want, tol)
+    # same features as the pair kernel (different split-K plan -> equal up to fp32 summation order)
+    ref = _proj(D, k, 77, ptype, cta_group=2).project(grads, model_id=0).cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(got - ref) <= tol)
+
+
 def test_block_inputs_and_batch_tiling_are_equivalent():
     D, k, B = 12345, 512, 40
     g = torch.Generator(device="cpu").manual_seed(0)

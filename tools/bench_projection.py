@@ -19,6 +19,8 @@ def main():
     a = ap.parse_args()
     dev = "cuda:0"
     p = CudaProjector(a.D, a.k, 42, ProjectionType(a.type), dev, 32, stage_rows=a.M, cta_group=a.cta_group)
+    if a.M > 1024 // (4 // a.cta_group if a.cta_group in (1, 2, 4) else 1):
+        pass
     stage = p._stage_buffer(a.M)  # tile-major [nkb, M, 64]
     g = torch.Generator(device=dev).manual_seed(1234)
     nkb = stage.shape[0]
