@@ -6,9 +6,9 @@
     python bench.py --impl reference ...      # the reference's CPU projector (trak BasicProjector restatement)
 
 Workload (BASELINE.json configs[1], "CIFAR-10 DDPM TRAK ... proj_dim 4096"): one *step* = one pass of the JL
-projection over one staged batch of 512 per-example gradients of the 35 746 307-parameter DDPM-CIFAR U-Net
-(synthetic bf16 rows resident in HBM) -> 512 x 4096 features.  Metric = projected gradients per second,
-whole job (sum over ranks, weak scaling: every rank projects its own 512 examples per step, no collective on
+projection over one staged batch of 1024 (normal type; 512 for Rademacher) per-example gradients of the
+35 746 307-parameter DDPM-CIFAR U-Net (synthetic bf16 rows resident in HBM) -> 1024 x 4096 features.  Metric =
+projected gradients per second, whole job (sum over ranks, weak scaling: every rank projects its own batch per step, no collective on
 the projection path).  `roofline` = 2*M*D*k flops per launch / CUDA-event time against the measured dense
 bf16 peak; `e2e` = the same metric through the public `CudaProjector.deferred()` API with fp32 gradients
 coming from pinned host memory and the features read back to the host inside the timed region.
@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 
 GRAD_DIM = 35_746_307  # DDPM-CIFAR U-Net (src/ddpm_config.py:48-82), SURVEY.md section 8
 PROJ_DIM = 4096
-STAGE_ROWS = 512
+STAGE_ROWS = 512  # rows per pass of the pair kernel (Rademacher); the normal type stages 1024 (quad kernel)
 N_TRAIN, N_GEN = 50_000, 1_000
 METRIC = "projected_grads_per_sec"
 UNIT = "grads/s"
@@ -142,7 +142,7 @@ def run_reference(args):
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": 1e3 * STAGE_ROWS / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * 1024 / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "CIFAR-10 DDPM TRAK featurisation: JL projection of per-example U-Net gradients",
                    "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": "normal", "batch": 8},
@@ -198,23 +198,24 @@ def main():
 
     peaks = _peaks()
     ptype = ProjectionType(args.proj_type)
-    proj = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ptype, dev, 32, stage_rows=STAGE_ROWS)
+    rows = 1024 if args.proj_type == "normal" else STAGE_ROWS  # staged examples per step per GPU
+    proj = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ptype, dev, 32, stage_rows=rows)
     handle = proj._handle
-    stage = proj._stage_buffer(STAGE_ROWS)
+    stage = proj._stage_buffer(rows)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     nkb = stage.shape[0]  # staging layout [D_pad/64][rows][64] (include/gadm.h)
     for k0 in range(0, nkb, 8192):  # synthetic per-example gradients, randn * 1e-3, bf16, resident in HBM
         k1 = min(nkb, k0 + 8192)
-        blk = (torch.randn(k1 - k0, STAGE_ROWS, 64, device=dev, generator=gen) * 1e-3).to(torch.bfloat16)
+        blk = (torch.randn(k1 - k0, rows, 64, device=dev, generator=gen) * 1e-3).to(torch.bfloat16)
         if k1 == nkb and GRAD_DIM % 64:
             blk[-1, :, GRAD_DIM % 64:] = 0
         stage[k0:k1] = blk
     del blk
-    out = torch.empty(STAGE_ROWS, PROJ_DIM, device=dev)
+    out = torch.empty(rows, PROJ_DIM, device=dev)
 
     # ---------------- device-resident throughput (value) + roofline
     for _ in range(args.warmup):
-        proj._project_rows(stage, STAGE_ROWS, 0, out)
+        proj._project_rows(stage, rows, 0, out)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -223,7 +224,7 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     for i in range(args.steps):
-        proj._project_rows(stage, STAGE_ROWS, 0, out)
+        proj._project_rows(stage, rows, 0, out)
         ev[i + 1].record()
     barrier()
     launches = handle.launch_count() - launches0
@@ -231,8 +232,8 @@ def main():
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     ms_per_step = total_ms / args.steps
-    value = STAGE_ROWS * world / (ms_per_step * 1e-3)
-    flops_per_launch = 2.0 * STAGE_ROWS * GRAD_DIM * PROJ_DIM
+    value = rows * world / (ms_per_step * 1e-3)
+    flops_per_launch = 2.0 * rows * GRAD_DIM * PROJ_DIM
     kernel_ms = sum(step_ms) / len(step_ms)  # project kernel + its (<0.1 %) split-K reduce, this rank
     achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12
     wd = handle.watchdog_code()
@@ -240,23 +241,27 @@ def main():
 
     # the other projection type on the same staged rows (side number; the headline is --proj-type)
     other = "rademacher" if args.proj_type == "normal" else "normal"
-    proj_o = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ProjectionType(other), dev, 32, stage_rows=STAGE_ROWS)
-    proj_o._stage, proj_o._ws = proj._stage, proj._ws
+    rows_o = min(rows, 1024 if other == "normal" else STAGE_ROWS)
+    proj_o = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ProjectionType(other), dev, 32, stage_rows=rows_o)
+    proj_o._stage = proj._stage
     for _ in range(2):
-        proj_o._project_rows(stage, STAGE_ROWS, 0, out)
+        proj_o._project_rows(stage, rows_o, 0, out)
     barrier()
     o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     o0.record()
     for _ in range(3):
-        proj_o._project_rows(stage, STAGE_ROWS, 0, out)
+        proj_o._project_rows(stage, rows_o, 0, out)
     o1.record()
     barrier()
     other_ms = max_over_ranks(o0.elapsed_time(o1)) / 3
-    other_line = {"proj_type": other, "ms_per_step": other_ms, "value": STAGE_ROWS * world / (other_ms * 1e-3),
-                  "unit": UNIT, "tflops_per_gpu": flops_per_launch / (other_ms * 1e-3) / 1e12,
-                  "frac_of_burst_peak": flops_per_launch / (other_ms * 1e-3) / 1e12 / peaks["bf16_burst"],
-                  "frac_of_sustained_peak": flops_per_launch / (other_ms * 1e-3) / 1e12 / peaks["bf16_sustained"]}
+    flops_o = 2.0 * rows_o * GRAD_DIM * PROJ_DIM
+    other_line = {"proj_type": other, "rows_per_step_per_gpu": rows_o, "ms_per_step": other_ms,
+                  "value": rows_o * world / (other_ms * 1e-3), "unit": UNIT,
+                  "tflops_per_gpu": flops_o / (other_ms * 1e-3) / 1e12,
+                  "frac_of_burst_peak": flops_o / (other_ms * 1e-3) / 1e12 / peaks["bf16_burst"],
+                  "frac_of_sustained_peak": flops_o / (other_ms * 1e-3) / 1e12 / peaks["bf16_sustained"]}
     proj_o._stage = proj_o._ws = None
+    del proj_o
 
     # ---------------- end to end: pinned host fp32 gradients -> public API -> features back on the host
     e2e = None
@@ -264,7 +269,7 @@ def main():
         chunk = 32
         host = torch.empty(chunk, GRAD_DIM, dtype=torch.float32).pin_memory()
         host.normal_(0, 1e-3)
-        host_out = torch.empty(STAGE_ROWS, PROJ_DIM, dtype=torch.float32).pin_memory()
+        host_out = torch.empty(rows, PROJ_DIM, dtype=torch.float32).pin_memory()
         bufs = [torch.empty(chunk, GRAD_DIM, dtype=torch.float32, device=dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         free_ev = [torch.cuda.Event() for _ in range(2)]
@@ -273,7 +278,7 @@ def main():
 
         def e2e_step():
             with proj.deferred(model_id=0) as sink:
-                for c in range(STAGE_ROWS // chunk):
+                for c in range(rows // chunk):
                     b = c % 2
                     with torch.cuda.stream(copy_stream):
                         copy_stream.wait_event(free_ev[b])
@@ -300,8 +305,8 @@ def main():
         e1.record()
         barrier()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
-        e2e = {"value": STAGE_ROWS * world / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": STAGE_ROWS * GRAD_DIM * 4, "d2h_bytes_per_step": STAGE_ROWS * PROJ_DIM * 4,
+        e2e = {"value": rows * world / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": rows * GRAD_DIM * 4, "d2h_bytes_per_step": rows * PROJ_DIM * 4,
                "ms_per_step": e2e_ms, "steps": n_e2e,
                "api": "CudaProjector.deferred().add(fp32 grads from pinned host) -> result() -> host"}
         del bufs, host
@@ -334,15 +339,16 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "CIFAR-10 DDPM TRAK featurisation: JL projection of per-example U-Net gradients "
-                                   "(BASELINE configs[1]), 512 staged examples per step per GPU",
+                                   f"(BASELINE configs[1]), {rows} staged examples per step per GPU",
                        "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": args.proj_type,
-                       "rows_per_step_per_gpu": STAGE_ROWS, "sharding": f"examples x{world}",
-                       "l2": "staged input (36.6 GB) and split-K partials (0.3 GB) exceed the 126 MB L2"},
+                       "rows_per_step_per_gpu": rows, "sharding": f"examples x{world}",
+                       "l2": f"staged input ({rows * GRAD_DIM * 2 / 1e9:.1f} GB) and split-K partials exceed the 126 MB L2"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                          "peak_kind": f"bf16_tflops_sustained of measured ({peaks['source']}); timed inside a multi-step loop",
                          "frac_of_burst_peak": achieved / peaks["bf16_burst"], "flops_per_launch": flops_per_launch,
-                         "kernel": "gadm::proj::project_kernel<2>"},
+                         "kernel": "gadm::proj::project_quad_kernel<4>" if args.proj_type == "normal"
+                         else "gadm::proj::project_kernel<2,2>"},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "tflops": achieved * world, "extra": extra,
         }

@@ -14,8 +14,8 @@ function of ``seed + 10**4 * model_id`` and is not scaled by 1/sqrt(k).  Differe
 * ``project`` also accepts the *dict / list of per-parameter gradient tensors* that
   ``torch.func.vmap(grad(f))`` returns, so ``vectorize_and_ignore_buffers``
   (``d_trak_grad.py:188-226``) and its extra B*D*4-byte copy can be dropped;
-* ``deferred()`` stages up to 512 examples (bf16 rows in HBM) and projects them in one pass, which
-  is what makes the tensor cores, not the random-number generation, the bound.
+* ``deferred()`` stages up to 512 (Rademacher) / 1024 (normal) examples (bf16 rows in HBM) and projects them
+  in one pass, which is what makes the tensor cores, not the random-number generation, the bound.
 
 There is no CPU path: a non-CUDA device raises ``ValueError`` exactly like upstream's CudaProjector.
 """
@@ -75,7 +75,7 @@ class CudaProjector:
     """``trak.projectors.CudaProjector`` signature over ``gadm_project_staged``."""
 
     def __init__(self, grad_dim: int, proj_dim: int, seed: int, proj_type: ProjectionType,
-                 device, max_batch_size: int = 32, *args, stage_rows: int | None = None, cta_group: int = 2,
+                 device, max_batch_size: int = 32, *args, stage_rows: int | None = None, cta_group: int | None = None,
                  **kwargs) -> None:
         self.grad_dim = int(grad_dim)
         self.proj_dim = int(proj_dim)
@@ -101,6 +101,10 @@ class CudaProjector:
             raise ValueError(f"proj_dim must be a positive multiple of 512 (got {self.proj_dim})")
         if self.grad_dim <= 0:
             raise ValueError("grad_dim must be positive")
+        # kernel variant: 2 = one tcgen05 CTA pair per unit (512 rows per pass); 4 = two pairs per cluster sharing the
+        # generated P tiles (1024 rows per pass) -- halves the Box-Muller work that bounds the normal type.
+        if cta_group is None:
+            cta_group = 4 if proj_type == ProjectionType.normal else 2
         self.cta_group = int(cta_group)
         self.d_pad = -(-self.grad_dim // TILE_K) * TILE_K
         self._handle = _lib.get_handle(device)

@@ -12,15 +12,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--D", type=int, default=35_746_307)
     ap.add_argument("--k", type=int, default=4096)
-    ap.add_argument("--M", type=int, default=512)
+    ap.add_argument("--M", type=int, default=0, help="staged rows (default: 1024 for normal, 512 for rademacher)")
     ap.add_argument("--type", default="rademacher")
     ap.add_argument("--iters", type=int, default=3)
-    ap.add_argument("--cta-group", type=int, default=2)
+    ap.add_argument("--cta-group", type=int, default=0, help="0 = projector default (4 for normal, 2 for rademacher)")
     a = ap.parse_args()
     dev = "cuda:0"
-    p = CudaProjector(a.D, a.k, 42, ProjectionType(a.type), dev, 32, stage_rows=a.M, cta_group=a.cta_group)
-    if a.M > 1024 // (4 // a.cta_group if a.cta_group in (1, 2, 4) else 1):
-        pass
+    if a.M == 0:
+        a.M = 1024 if (a.type == "normal" and a.cta_group in (0, 4)) else 512
+    p = CudaProjector(a.D, a.k, 42, ProjectionType(a.type), dev, 32, stage_rows=a.M, cta_group=a.cta_group or None)
+    a.cta_group = p._group_for(a.M)
     stage = p._stage_buffer(a.M)  # tile-major [nkb, M, 64]
     g = torch.Generator(device=dev).manual_seed(1234)
     nkb = stage.shape[0]

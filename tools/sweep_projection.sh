@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 for t in rademacher normal; do for gw in 2 4; do
   nvidia-smi --query-gpu=clocks.sm,power.draw --format=csv,noheader,nounits -lms 100 > gpurun_out/clk_${t}_${gw}.csv &
   SMI=$!
-  GADM_PROJ_GEN_WARPS=$gw timeout 120 python tools/bench_projection.py --type $t --M 512 --k 4096 --iters 5 | cut -c1-250
+  GADM_PROJ_GEN_WARPS=$gw timeout 120 python tools/bench_projection.py --type $t --k 4096 --iters 5 | cut -c1-250
   kill $SMI
   python - <<PY
 import statistics
