@@ -8,7 +8,7 @@ M="dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_te
 for t in normal rademacher; do
   CMD="python tools/bench_projection.py --type $t --k 4096 --iters 1"
   timeout 200 $CMD > gpurun_out/plain_full_$t.log 2>&1 && \
-  timeout 600 ncu --metrics $M --clock-control none -k regex:project_ -s 1 -c 1 --csv \
+  timeout 600 ncu --metrics $M --clock-control none -k "regex:^project_(quad_)?kernel" -s 1 -c 1 --csv \
       --log-file gpurun_out/traffic_full_$t.csv $CMD > gpurun_out/ncu_full_$t.log 2>&1
   tail -n 8 gpurun_out/traffic_full_$t.csv | cut -d, -f5,13- | cut -c1-200
 done
