@@ -392,16 +392,14 @@ def side_measurements(dev, rank, world):
     del train, gen, res
     torch.cuda.empty_cache()
     if rank == 0:
-        from oracle import aggregation as oagg
-
         n, d, K, m = 1000, 100, 1000, 100
         rng = np.random.RandomState(0)
-        Xs = oagg.shapley_masks(d, list(range(n)))
+        Xs = G.masks_from_seeds(d, list(range(n)), "shapley").astype(np.float64)
         w = rng.normal(size=(d, K))
         Ys = Xs @ w + 0.1 * rng.normal(size=(n, K))
         tests = []
         for t in range(3):
-            Xt = oagg.datamodel_masks(d, list(range(5000 + 100 * t, 5000 + 100 * t + m)))
+            Xt = G.masks_from_seeds(d, list(range(5000 + 100 * t, 5000 + 100 * t + m)), "datamodel").astype(np.float64)
             tests.append((Xt, Xt @ w + 0.5 * rng.normal(size=(m, K))))
         for it in range(2):
             torch.cuda.synchronize()

@@ -7,6 +7,8 @@ from .aggregation import (PackedMasks, aoi_attr_batched, bootstrap_statistic, lo
 from .scoring import (TrakScorer, aggregate_by_class, col_mean_scaled, compute_dtrak_trak_scores,  # noqa: F401
                       compute_gradient_scores, gemm_tn, gradient_scores, group_and_rank, row_norms, trak_scores,
                       transpose)
+from .masks import (counterfactual_split, masks_from_seeds, remove_data_by_datamodel, remove_data_by_shapley,  # noqa: F401
+                    remove_data_by_uniform)
 from ._lib import GadmError, load_library  # noqa: F401
 
 __all__ = [
@@ -16,5 +18,7 @@ __all__ = [
     "sym_pinv",
     "TrakScorer", "aggregate_by_class", "col_mean_scaled", "compute_dtrak_trak_scores", "compute_gradient_scores",
     "gemm_tn", "gradient_scores", "group_and_rank", "row_norms", "trak_scores", "transpose",
+    "counterfactual_split", "masks_from_seeds", "remove_data_by_datamodel", "remove_data_by_shapley",
+    "remove_data_by_uniform",
     "GadmError", "load_library",
 ]
