@@ -136,6 +136,77 @@ sym_pinv_kernel(const double* __restrict__ A, int d, double rcond, double* __res
   }
   __syncthreads();
 
+  // ---- fast path: A symmetric positive definite and well conditioned (the usual n >= d case) -> A^-1 by Cholesky.
+  // A pivot below 1e-8 * max diag means sigma_min / sigma_max could approach numpy's cut-off, so only then is the
+  // Jacobi SVD (exact pinv semantics, rank-deficient input) run.  For a full-rank matrix inv == pinv up to kappa*eps.
+  __shared__ int s_chol_ok;
+  __shared__ double s_maxdiag;
+  if (tid == 0) {
+    double mx = 0.0;
+    for (int i = 0; i < d; ++i) mx = fmax(mx, G[static_cast<size_t>(i) * dp + i]);
+    s_maxdiag = mx;
+    s_chol_ok = (mx > 0.0) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int j = 0; j < d && s_chol_ok; ++j) {
+    const double piv = G[static_cast<size_t>(j) * dp + j];
+    __syncthreads();
+    if (!(piv > 1e-8 * s_maxdiag)) {
+      if (tid == 0) s_chol_ok = 0;
+      __syncthreads();
+      break;
+    }
+    const double sd = sqrt(piv);
+    if (tid == 0) G[static_cast<size_t>(j) * dp + j] = sd;
+    for (int i = j + 1 + tid; i < d; i += kPinvThreads) G[static_cast<size_t>(i) * dp + j] /= sd;
+    __syncthreads();
+    const int m = d - 1 - j;  // trailing rows j+1..d-1, lower triangle incl. diagonal
+    for (int e = tid; e < m * m; e += kPinvThreads) {
+      const int i = j + 1 + e / m, c = j + 1 + e % m;
+      if (c <= i) G[static_cast<size_t>(i) * dp + c] -= G[static_cast<size_t>(i) * dp + j] * G[static_cast<size_t>(c) * dp + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_chol_ok) {
+    // Vt <- L^-1 (lower triangular), column c handled by 4 lanes of one warp
+    const int c = tid >> 2, part = tid & 3;
+    for (int c0 = 0; c0 < d; c0 += kPinvThreads / 4) {
+      const int col = c0 + c;
+      const bool active = col < d;
+      const int cc = active ? col : 0;
+      if (active && part == 0)
+        for (int r = 0; r < cc; ++r) Vt[static_cast<size_t>(r) * dp + cc] = 0.0;
+      for (int r = 0; r < d; ++r) {
+        double sum = 0.0;
+        if (active && r >= cc)
+          for (int t = cc + part; t < r; t += 4) sum += G[static_cast<size_t>(r) * dp + t] * Vt[static_cast<size_t>(t) * dp + cc];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (active && part == 0 && r >= cc)
+          Vt[static_cast<size_t>(r) * dp + cc] = (((r == cc) ? 1.0 : 0.0) - sum) / G[static_cast<size_t>(r) * dp + r];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // A^-1 = L^-T L^-1
+    for (int idx = tid; idx < d * d; idx += kPinvThreads) {
+      const int a = idx / d, b = idx % d;
+      double acc = 0.0;
+      for (int i = (a > b ? a : b); i < d; ++i) acc += Vt[static_cast<size_t>(i) * dp + a] * Vt[static_cast<size_t>(i) * dp + b];
+      out[idx] = acc;
+    }
+    if (tid == 0 && info) { info[0] = 0; info[1] = d; }
+    return;
+  }
+  // ---- general path: restore the working copies and run the one-sided Jacobi SVD
+  for (int idx = tid; idx < dp * dp; idx += kPinvThreads) {
+    const int i = idx / dp, j = idx % dp;
+    G[idx] = (i < d && j < d) ? A[i * d + j] : 0.0;
+    Vt[idx] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
   const int npairs = dp / 2;
   int sweep = 0;
   for (; sweep < kPinvMaxSweeps; ++sweep) {
