@@ -92,7 +92,11 @@ def masks_from_remaining_idx(remaining_idx_list, num_groups: int, device=None) -
 
 
 def _dev_f64(a, device) -> torch.Tensor:
-    t = torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)) if not isinstance(a, torch.Tensor) else a)
+    if not isinstance(a, torch.Tensor):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        if not a.flags.writeable:
+            a = a.copy()
+    t = torch.as_tensor(a)
     return t.to(device=device, dtype=_f64, non_blocking=True).contiguous()
 
 

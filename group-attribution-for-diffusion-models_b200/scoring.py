@@ -333,11 +333,11 @@ def compute_gradient_scores(args, retraining: bool = False, training_seeds: Iter
     if n_val is None:
         n_val = args.sample_size if args.gradient_type == "journey_trak" else os.path.getsize(val_grad_path) // (4 * kdim)
     val_phi = np.memmap(val_grad_path, dtype=np.float32, mode="r", shape=(n_val, kdim))[: args.sample_size]
-    val = torch.from_numpy(np.ascontiguousarray(val_phi)).to(device)
+    val = torch.from_numpy(np.array(val_phi, dtype=np.float32, copy=True)).to(device)
 
     def _load_train(path):
         n = n_train if n_train is not None else os.path.getsize(path) // (4 * kdim)
-        return torch.from_numpy(np.ascontiguousarray(np.memmap(path, dtype=np.float32, mode="r", shape=(n, kdim)))).to(device)
+        return torch.from_numpy(np.array(np.memmap(path, dtype=np.float32, mode="r", shape=(n, kdim)), copy=True)).to(device)
 
     if retraining:  # :54-79
         scores = None
