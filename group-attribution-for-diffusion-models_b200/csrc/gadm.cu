@@ -407,6 +407,11 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
   a.key1 = (uint32_t)(seed64 >> 32);
   a.proj_type = (uint32_t)proj_type;
   a.p_base_div64 = (uint32_t)(p_base / 64);
+  // k-blocks per TMEM accumulation segment (see project.cuh).  Measured at the C2 shape (fp64 reference, full D):
+  // normal 256 -> 1.9e-5 relative error (unsegmented 1.3e-3), Rademacher 512 -> 1.3e-6; each costs ~2 % throughput.
+  // GADM_PROJ_SEG_KB overrides for tuning.
+  a.seg_kb = (proj_type == gadm::kProjRademacher) ? 512u : 256u;
+  if (const char* e = getenv("GADM_PROJ_SEG_KB")) { const long v = atol(e); if (v >= 1) a.seg_kb = (uint32_t)v; }
   {
     const char* dbg = getenv("GADM_PROJ_DEBUG");  // perf ablation only; results are garbage when set
     a.debug = dbg ? (uint32_t)atoi(dbg) : 0u;

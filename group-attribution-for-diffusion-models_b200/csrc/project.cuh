@@ -65,7 +65,8 @@ struct Cfg {
   // slot's barriers (mbarrier parity waits must never run more than one phase ahead).
   static constexpr int kGenGroups = kStages;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kEpiBytes = 4 * 32 * 144;                       // per-warp transpose buffers of the epilogue
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // + alignment slack
   static constexpr int kUnitRows = kNumAcc * kAccRows * kCtaGroup;     // rows of a full partial tile (512 / 256)
 };
 
@@ -84,7 +85,71 @@ struct Args {
   uint32_t* sync_counter; // zeroed device word for the inter-cluster lockstep (nullptr: disabled)
   uint32_t sync_iters;    // lockstep only while the cluster-local k-block counter is below this (multiple of sync_every)
   uint32_t sync_every;    // k-blocks between lockstep points
+  uint32_t seg_kb;        // k-blocks accumulated in TMEM before the accumulators are promoted into the partial tile
 };
+
+// Why segments: tcgen05 adds each MMA result into the fp32 TMEM accumulator with truncation.  Over a
+// 15 000-k-block unit (60 000 accumulations) that shrinks every feature systematically -- measured -1.1e-3
+// relative at the C2 shape (both projection types), -3 % at C3 -- far outside fp32-accumulate accuracy.  A unit
+// is therefore cut into segments of seg_kb k-blocks: after each segment the epilogue warps add the accumulators
+// into the unit's partial tile in HBM with round-to-nearest fp32 adds and the MMA restarts from zero.
+// The add is a fire-and-forget vector reduction (REDG.E.ADD.F32x4.RN), a plain store for the first segment: no
+// load, so the accumulators are released after ~16 TMEM loads instead of an HBM round trip per 64 B.  One thread
+// owns an address for the whole launch and its st / red operations on it are ordered (same-thread, same
+// location), so the sum order is fixed and the result deterministic.
+__device__ __forceinline__ uint32_t num_segments(uint32_t kb0, uint32_t kb1, uint32_t seg_kb) {
+  return (kb1 - kb0 + seg_kb - 1) / seg_kb;
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(x)),
+               "f"(__uint_as_float(y)), "f"(__uint_as_float(z)), "f"(__uint_as_float(w))
+               : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
+
+// Epilogue of one segment for one accumulator: the 32 TMEM lanes of this warp -> 32 partial-tile rows
+// (store for the first segment, add afterwards).  tcgen05.ld hands lane r the 32 columns of row r; written
+// out like that every instruction would touch 32 different 128-byte lines with 16 bytes each, and those LSU
+// transactions, not the data, were the cost of a drain.  The 32x32 block is therefore transposed through a
+// 4.5 KiB per-warp smem buffer (row pitch 144 B: conflict-free 16-byte accesses both ways) so that one
+// instruction covers 4 rows x 128 contiguous bytes.
+constexpr int kEpiPitch = 144;
+constexpr int kEpiWarpBytes = 32 * kEpiPitch;
+__device__ __forceinline__ void drain_accumulator(uint32_t tmem_addr, float* __restrict__ dst_warp, bool first,
+                                                  uint32_t buf, int lane) {
+  const uint32_t my_row = buf + lane * kEpiPitch;
+  const int rr = lane >> 3, cc = lane & 7;
+#pragma unroll 1
+  for (int c = 0; c < kTileN; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_addr + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_shared_v4(my_row + i * 16, make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + rr;
+      const uint4 w = ld_shared_v4(buf + row * kEpiPitch + cc * 16);
+      float* g = dst_warp + static_cast<size_t>(row) * kTileN + c + cc * 4;
+      if (first) *reinterpret_cast<uint4*>(g) = w;
+      else red_add_v4(g, w.x, w.y, w.z, w.w);
+    }
+    __syncwarp();
+  }
+}
 
 // Inter-cluster lockstep.  The 16 clusters that work on the same D-split (one per 256-column tile) stream
 // the SAME gradient tiles; they only hit in L2 if they stay within the L2 retention window of each other
@@ -104,11 +169,6 @@ __device__ __forceinline__ void grid_lockstep(uint32_t* counter, uint32_t target
     __nanosleep(200);
     if (limit != 0 && globaltimer_ns() - t0 > limit) watchdog_fire(0x600);
   } while (true);
-}
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
 }
 
 // Fill one B stage (kBRows x 64 bf16, K-major, 128B swizzle) with Rademacher signs.
@@ -233,56 +293,56 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
     // ===================== MMA issuer (leader CTA, one thread)
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = umma_idesc(UMMA_FMT_BF16, kAccRows * kCtaGroup, kTileN);
-      uint32_t it = 0, unit_iter = 0;
-      for (uint32_t u = cid; u < a.n_units; u += n_clusters, ++unit_iter) {
+      uint32_t it = 0, seg_iter = 0;
+      for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
         const uint32_t split = u / a.n_tiles;
         const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
-        if (unit_iter > 0) mbar_wait(tmem_empty_bar, (unit_iter - 1) & 1u, 0x200);
-        tcgen05_fence_after();
-        for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % C::kStages;
-          const uint32_t ph = (it / C::kStages) & 1u;
-          mbar_wait(full_bar(s), ph, 0x300 + s);
+        for (uint32_t seg0 = kb0; seg0 < kb1; seg0 += a.seg_kb, ++seg_iter) {
+          const uint32_t seg1 = (seg0 + a.seg_kb < kb1) ? seg0 + a.seg_kb : kb1;
+          if (seg_iter > 0) mbar_wait(tmem_empty_bar, (seg_iter - 1) & 1u, 0x200);
           tcgen05_fence_after();
-          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b(s));
-          for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
-            const uint64_t adesc = umma_desc_kmajor_sw128(smem_a(s, acc));
+          for (uint32_t kb = seg0; kb < seg1; ++kb, ++it) {
+            const int s = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1u;
+            mbar_wait(full_bar(s), ph, 0x300 + s);
+            tcgen05_fence_after();
+            const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b(s));
+            for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
+              const uint64_t adesc = umma_desc_kmajor_sw128(smem_a(s, acc));
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advancing K by 16 bf16 = 32 B inside the 128B swizzle row: +2 in the (addr >> 4) field
-              umma_f16<kCtaGroup>(tmem_base + acc * kTileN, adesc + 2u * k, bdesc + 2u * k, idesc,
-                                  (kb > kb0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // advancing K by 16 bf16 = 32 B inside the 128B swizzle row: +2 in the (addr >> 4) field
+                umma_f16<kCtaGroup>(tmem_base + acc * kTileN, adesc + 2u * k, bdesc + 2u * k, idesc,
+                                    (kb > seg0 || k > 0) ? 1u : 0u);
+              }
             }
+            if constexpr (kCtaGroup == 2) umma_commit_cg2_mcast(empty_bar(s), 0x3); else umma_commit(empty_bar(s));
           }
-          if constexpr (kCtaGroup == 2) umma_commit_cg2_mcast(empty_bar(s), 0x3); else umma_commit(empty_bar(s));
+          if constexpr (kCtaGroup == 2) umma_commit_cg2_mcast(tmem_full_bar, 0x3); else umma_commit(tmem_full_bar);
         }
-        if constexpr (kCtaGroup == 2) umma_commit_cg2_mcast(tmem_full_bar, 0x3); else umma_commit(tmem_full_bar);
       }
     }
   } else if (warp >= R::kFirstEpiWarp && warp < R::kFirstEpiWarp + 4) {
     // ===================== epilogue: TMEM -> registers -> split-K partial tile
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    uint32_t unit_iter = 0;
-    for (uint32_t u = cid; u < a.n_units; u += n_clusters, ++unit_iter) {
-      mbar_wait(tmem_full_bar, unit_iter & 1u, 0x400);
-      tcgen05_fence_after();
-      for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
-        const uint32_t row = acc * (kAccRows * kCtaGroup) + rank * kAccRows + q * 32 + lane;
-        float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
-#pragma unroll 1
-        for (int c = 0; c < kTileN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<uint4*>(dst + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    uint32_t seg_iter = 0;
+    for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
+      const uint32_t split = u / a.n_tiles;
+      const uint32_t nseg = num_segments(kb_begin(split), kb_begin(split + 1), a.seg_kb);
+      for (uint32_t seg = 0; seg < nseg; ++seg, ++seg_iter) {
+        mbar_wait(tmem_full_bar, seg_iter & 1u, 0x400);
+        tcgen05_fence_after();
+        for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
+          const uint32_t row = acc * (kAccRows * kCtaGroup) + rank * kAccRows + q * 32;
+          float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
+          drain_accumulator(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN, dst, seg == 0,
+                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane);
         }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCtaGroup == 2) mbar_arrive_cluster(mapa(tmem_empty_bar, 0)); else mbar_arrive(tmem_empty_bar);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtaGroup == 2) mbar_arrive_cluster(mapa(tmem_empty_bar, 0)); else mbar_arrive(tmem_empty_bar);
+        }
       }
     }
   } else if (warp < R::kGenWarps) {

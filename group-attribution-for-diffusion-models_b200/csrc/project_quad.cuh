@@ -140,27 +140,30 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
         // ===================== MMA issuer of this pair
         const uint32_t idesc = umma_idesc(UMMA_FMT_BF16, kAccRows * 2, kTileN);
         const uint16_t pair_mask = static_cast<uint16_t>(0x3u << leader4);
-        uint32_t it = 0, unit_iter = 0;
-        for (uint32_t u = cid; u < a.n_units; u += n_clusters, ++unit_iter) {
+        uint32_t it = 0, seg_iter = 0;
+        for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
           const uint32_t split = u / a.n_tiles;
           const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
-          if (unit_iter > 0) mbar_wait(tmem_empty_bar, (unit_iter - 1) & 1u, 0x2200);
-          tcgen05_fence_after();
-          for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-            const int s = it % C::kStages;
-            const uint32_t ph = (it / C::kStages) & 1u;
-            mbar_wait(full_bar(s), ph, 0x2300 + s);
+          for (uint32_t seg0 = kb0; seg0 < kb1; seg0 += a.seg_kb, ++seg_iter) {
+            const uint32_t seg1 = (seg0 + a.seg_kb < kb1) ? seg0 + a.seg_kb : kb1;
+            if (seg_iter > 0) mbar_wait(tmem_empty_bar, (seg_iter - 1) & 1u, 0x2200);
             tcgen05_fence_after();
-            const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b(s));
-            for (uint32_t acc = 0; acc < kNumAcc; ++acc) {
-              const uint64_t adesc = umma_desc_kmajor_sw128(smem_a(s, acc));
+            for (uint32_t kb = seg0; kb < seg1; ++kb, ++it) {
+              const int s = it % C::kStages;
+              const uint32_t ph = (it / C::kStages) & 1u;
+              mbar_wait(full_bar(s), ph, 0x2300 + s);
+              tcgen05_fence_after();
+              const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b(s));
+              for (uint32_t acc = 0; acc < kNumAcc; ++acc) {
+                const uint64_t adesc = umma_desc_kmajor_sw128(smem_a(s, acc));
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                umma_f16<2>(tmem_base + acc * kTileN, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_f16<2>(tmem_base + acc * kTileN, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > seg0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit_cg2_mcast(empty_bar(s), 0xF);  // both pairs must release a slot before anyone refills it
             }
-            umma_commit_cg2_mcast(empty_bar(s), 0xF);  // both pairs must release a slot before anyone refills it
+            umma_commit_cg2_mcast(tmem_full_bar, pair_mask);
           }
-          umma_commit_cg2_mcast(tmem_full_bar, pair_mask);
         }
       } else {
         // ===================== relay (odd rank): the 8 KiB shipped into this CTA landed -> tell the pair leader
@@ -181,26 +184,23 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp >= R::kFirstEpiWarp && warp < R::kFirstEpiWarp + 4) {
     // ===================== epilogue: TMEM -> registers -> split-K partial tile (rows of this pair)
     const int q = warp & 3;
-    uint32_t unit_iter = 0;
-    for (uint32_t u = cid; u < a.n_units; u += n_clusters, ++unit_iter) {
-      mbar_wait(tmem_full_bar, unit_iter & 1u, 0x2400);
-      tcgen05_fence_after();
-      for (uint32_t acc = 0; acc < kNumAcc; ++acc) {
-        const uint32_t row = pair * pair_rows + acc * (kAccRows * 2) + rank * kAccRows + q * 32 + lane;
-        float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
-#pragma unroll 1
-        for (int c = 0; c < kTileN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<uint4*>(dst + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    uint32_t seg_iter = 0;
+    for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
+      const uint32_t split = u / a.n_tiles;
+      const uint32_t nseg = num_segments(kb_begin(split), kb_begin(split + 1), a.seg_kb);
+      for (uint32_t seg = 0; seg < nseg; ++seg, ++seg_iter) {
+        mbar_wait(tmem_full_bar, seg_iter & 1u, 0x2400);
+        tcgen05_fence_after();
+        for (uint32_t acc = 0; acc < kNumAcc; ++acc) {
+          const uint32_t row = pair * pair_rows + acc * (kAccRows * 2) + rank * kAccRows + q * 32;
+          float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
+          drain_accumulator(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN, dst, seg == 0,
+                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane);
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(tmem_empty_bar, leader4));
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(tmem_empty_bar, leader4));
     }
   } else if (warp < R::kGenWarps) {
     // ===================== generators: own 64 rows of the P tile -> local smem -> shipped to the partner CTA

@@ -16,6 +16,8 @@ def main():
     ap.add_argument("--type", default="rademacher")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--cta-group", type=int, default=0, help="0 = projector default (4 for normal, 2 for rademacher)")
+    ap.add_argument("--check", type=int, default=0,
+                    help="rows to compare with an fp64 product against the kernel's own materialised P (full D)")
     a = ap.parse_args()
     dev = "cuda:0"
     if a.M == 0:
@@ -46,11 +48,31 @@ def main():
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = min(ts)
+    chk = None
+    if a.check:
+        # exact accuracy at full size: fp64 (staged bf16 rows) @ P, P materialised by the kernel's own generator
+        R = a.check
+        rows_sel = torch.linspace(0, a.M - 1, R).long().to(dev)
+        want = torch.zeros(R, a.k, dtype=torch.float64, device=dev)
+        step_kb = 1024  # 65 536 rows of P per chunk
+        for k0 in range(0, nkb, step_kb):
+            k1 = min(nkb, k0 + step_kb)
+            n = min(a.D, k1 * 64) - k0 * 64
+            P = p.materialize(k0 * 64, n).double()
+            g = stage[k0:k1].index_select(1, rows_sel).permute(1, 0, 2).reshape(R, -1)[:, :n].double()
+            want += g @ P
+            del P, g
+        got = out.index_select(0, rows_sel).double()
+        rel = (got - want).norm(dim=1) / want.norm(dim=1)
+        shrink = ((got * want).sum(dim=1) / (want * want).sum(dim=1)) - 1  # systematic scale error
+        chk = {"rel_err_rows": [float(x) for x in rel], "scale_err_rows": [float(x) for x in shrink],
+               "max_abs_over_rownorm": float(((got - want).abs().max(dim=1).values / want.norm(dim=1) * a.k ** 0.5).max())}
     flops = 2.0 * a.M * a.D * a.k
     print(json.dumps({"D": a.D, "k": a.k, "M": a.M, "type": a.type, "cta_group": a.cta_group, "ms": ts,
                       "tflops": flops / ms / 1e9, "frac_of_1590": flops / ms / 1e9 / 1590.4,
                       "gen_elems_per_s": a.D * a.k / ms * 1e3, "watchdog": p._handle.watchdog_code(),
-                      "norm_ratio": float(out.double().norm(dim=1).mean() / (gnorm * a.k ** 0.5))}))
+                      "norm_ratio": float(out.double().norm(dim=1).mean() / (gnorm * a.k ** 0.5)),
+                      "seg_kb": os.environ.get("GADM_PROJ_SEG_KB"), "check": chk}))
 
 
 if __name__ == "__main__":
