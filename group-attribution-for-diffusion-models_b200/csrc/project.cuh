@@ -101,9 +101,22 @@ __device__ __forceinline__ uint32_t num_segments(uint32_t kb0, uint32_t kb1, uin
   return (kb1 - kb0 + seg_kb - 1) / seg_kb;
 }
 
-__device__ __forceinline__ void red_add_v4(float* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(x)),
-               "f"(__uint_as_float(y)), "f"(__uint_as_float(z)), "f"(__uint_as_float(w))
+// The partial tiles in flight (one per cluster, 33-37 MB in total) are re-touched once per segment; without a hint
+// the gradient stream pushes them out of L2 in between and every segment costs a DRAM read + write of the tile
+// (ncu, full size: +72 GB per launch).  evict_last keeps them resident.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_add_v4(float* p, uint4 v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v4_hint(float* p, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w), "l"(pol)
                : "memory");
 }
 
@@ -111,7 +124,6 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
@@ -128,7 +140,7 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 constexpr int kEpiPitch = 144;
 constexpr int kEpiWarpBytes = 32 * kEpiPitch;
 __device__ __forceinline__ void drain_accumulator(uint32_t tmem_addr, float* __restrict__ dst_warp, bool first,
-                                                  uint32_t buf, int lane) {
+                                                  uint32_t buf, int lane, uint64_t pol) {
   const uint32_t my_row = buf + lane * kEpiPitch;
   const int rr = lane >> 3, cc = lane & 7;
 #pragma unroll 1
@@ -144,8 +156,8 @@ __device__ __forceinline__ void drain_accumulator(uint32_t tmem_addr, float* __r
       const int row = i * 4 + rr;
       const uint4 w = ld_shared_v4(buf + row * kEpiPitch + cc * 16);
       float* g = dst_warp + static_cast<size_t>(row) * kTileN + c + cc * 4;
-      if (first) *reinterpret_cast<uint4*>(g) = w;
-      else red_add_v4(g, w.x, w.y, w.z, w.w);
+      if (first) st_global_v4_hint(g, w, pol);
+      else red_add_v4(g, w, pol);
     }
     __syncwarp();
   }
@@ -325,6 +337,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp >= R::kFirstEpiWarp && warp < R::kFirstEpiWarp + 4) {
     // ===================== epilogue: TMEM -> registers -> split-K partial tile
     const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const uint64_t pol = l2_policy_evict_last();
     uint32_t seg_iter = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
       const uint32_t split = u / a.n_tiles;
@@ -336,7 +349,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
           const uint32_t row = acc * (kAccRows * kCtaGroup) + rank * kAccRows + q * 32;
           float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
           drain_accumulator(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN, dst, seg == 0,
-                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane);
+                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane, pol);
         }
         tcgen05_fence_before();
         __syncwarp();

@@ -184,6 +184,7 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp >= R::kFirstEpiWarp && warp < R::kFirstEpiWarp + 4) {
     // ===================== epilogue: TMEM -> registers -> split-K partial tile (rows of this pair)
     const int q = warp & 3;
+    const uint64_t pol = l2_policy_evict_last();
     uint32_t seg_iter = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
       const uint32_t split = u / a.n_tiles;
@@ -195,7 +196,7 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
           const uint32_t row = pair * pair_rows + acc * (kAccRows * 2) + rank * kAccRows + q * 32;
           float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
           drain_accumulator(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN, dst, seg == 0,
-                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane);
+                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane, pol);
         }
         tcgen05_fence_before();
         __syncwarp();
