@@ -9,6 +9,7 @@ from .scoring import (TrakScorer, aggregate_by_class, col_mean_scaled, compute_d
                       transpose)
 from .masks import (counterfactual_split, masks_from_seeds, remove_data_by_datamodel, remove_data_by_shapley,  # noqa: F401
                     remove_data_by_uniform)
+from .datamodel import RidgeCV, datamodel_ridge_batched, ridge_cv_batched  # noqa: F401
 from ._lib import GadmError, load_library  # noqa: F401
 
 __all__ = [
@@ -20,5 +21,6 @@ __all__ = [
     "gemm_tn", "gradient_scores", "group_and_rank", "row_norms", "trak_scores", "transpose",
     "counterfactual_split", "masks_from_seeds", "remove_data_by_datamodel", "remove_data_by_shapley",
     "remove_data_by_uniform",
+    "RidgeCV", "datamodel_ridge_batched", "ridge_cv_batched",
     "GadmError", "load_library",
 ]

@@ -44,6 +44,13 @@ _SIGNATURES = {
     "gadm_sym_pinv_workspace_bytes": (c_i64, [c_i64]),
     "gadm_sym_pinv": (C.c_int, [c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),
     "gadm_dgemm_dk": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_double, c_vp, c_vp]),
+    "gadm_center_columns": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "gadm_dgemm": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "gadm_sym_eig_workspace_bytes": (c_i64, [c_i64]),
+    "gadm_sym_eig": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),
+    "gadm_ridge_gcv": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "gadm_ridge_select": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "gadm_ridge_intercept": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gadm_shapley_rhs": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gadm_lds_spearman": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gadm_lds_mean": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),

@@ -117,6 +117,57 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// One-sided (Hestenes) Jacobi: rotate the rows of G (dp x dp, dp even) until mutually orthogonal, accumulating the
+// rotations in Vt.  Whole CTA (kPinvThreads); returns the number of sweeps.  For symmetric A = V L V^T the rows end
+// as g_i = lambda_i v_i^T with v_i^T = row i of Vt.
+__device__ __forceinline__ int jacobi_orthogonalise_rows(double* G, double* Vt, int dp, int* s_rot_p) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kPinvThreads / 32;
+  int& s_rot = *s_rot_p;
+  const int npairs = dp / 2;
+  int sweep = 0;
+  for (; sweep < kPinvMaxSweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int round = 0; round < dp - 1; ++round) {
+      // round-robin tournament: dp/2 disjoint pairs per round, every pair once per sweep
+      for (int pr = warp; pr < npairs; pr += nwarps) {
+        // circle method: (dp-1, round) and every {a, b} with a + b == 2*round (mod dp-1)
+        const int a = (pr == 0) ? dp - 1 : (round + pr) % (dp - 1);
+        const int b = (pr == 0) ? round : (round - pr + (dp - 1)) % (dp - 1);
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        double* gp = G + static_cast<size_t>(p) * dp;
+        double* gq = G + static_cast<size_t>(q) * dp;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int j = lane; j < dp; j += 32) {
+          const double x = gp[j], y = gq[j];
+          alpha += x * x; beta += y * y; gamma += x * y;
+        }
+        alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+        if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && gamma != 0.0) {
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          double* vp = Vt + static_cast<size_t>(p) * dp;
+          double* vq = Vt + static_cast<size_t>(q) * dp;
+          for (int j = lane; j < dp; j += 32) {
+            const double x = gp[j], y = gq[j];
+            gp[j] = c * x - s * y; gq[j] = s * x + c * y;
+            const double vx = vp[j], vy = vq[j];
+            vp[j] = c * vx - s * vy; vq[j] = s * vx + c * vy;
+          }
+          if (lane == 0) atomicAdd(&s_rot, 1);
+        }
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (rot == 0) break;
+  }
+
+  return sweep;
+}
+
 __global__ void __launch_bounds__(kPinvThreads, 1)
 sym_pinv_kernel(const double* __restrict__ A, int d, double rcond, double* __restrict__ out, double* gwork,
                 int use_smem, int* __restrict__ info) {
@@ -207,47 +258,7 @@ sym_pinv_kernel(const double* __restrict__ A, int d, double rcond, double* __res
   }
   __syncthreads();
 
-  const int npairs = dp / 2;
-  int sweep = 0;
-  for (; sweep < kPinvMaxSweeps; ++sweep) {
-    if (tid == 0) s_rot = 0;
-    __syncthreads();
-    for (int round = 0; round < dp - 1; ++round) {
-      // round-robin tournament: dp/2 disjoint pairs per round, every pair once per sweep
-      for (int pr = warp; pr < npairs; pr += nwarps) {
-        // circle method: (dp-1, round) and every {a, b} with a + b == 2*round (mod dp-1)
-        const int a = (pr == 0) ? dp - 1 : (round + pr) % (dp - 1);
-        const int b = (pr == 0) ? round : (round - pr + (dp - 1)) % (dp - 1);
-        const int p = a < b ? a : b, q = a < b ? b : a;
-        double* gp = G + static_cast<size_t>(p) * dp;
-        double* gq = G + static_cast<size_t>(q) * dp;
-        double alpha = 0.0, beta = 0.0, gamma = 0.0;
-        for (int j = lane; j < dp; j += 32) {
-          const double x = gp[j], y = gq[j];
-          alpha += x * x; beta += y * y; gamma += x * y;
-        }
-        alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
-        if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && gamma != 0.0) {
-          const double zeta = (beta - alpha) / (2.0 * gamma);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-          double* vp = Vt + static_cast<size_t>(p) * dp;
-          double* vq = Vt + static_cast<size_t>(q) * dp;
-          for (int j = lane; j < dp; j += 32) {
-            const double x = gp[j], y = gq[j];
-            gp[j] = c * x - s * y; gq[j] = s * x + c * y;
-            const double vx = vp[j], vy = vq[j];
-            vp[j] = c * vx - s * vy; vq[j] = s * vx + c * vy;
-          }
-          if (lane == 0) atomicAdd(&s_rot, 1);
-        }
-      }
-      __syncthreads();
-    }
-    const int rot = s_rot;
-    __syncthreads();
-    if (rot == 0) break;
-  }
+  const int sweep = jacobi_orthogonalise_rows(G, Vt, dp, &s_rot);
 
   // singular values
   if (tid == 0) s_max = 0.0;

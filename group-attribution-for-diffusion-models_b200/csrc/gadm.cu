@@ -17,6 +17,7 @@
 #include "project.cuh"
 #include "project_quad.cuh"
 #include "aggregate.cuh"
+#include "ridge.cuh"
 #include "gemm.cuh"
 
 struct gadm_ctx {
@@ -673,6 +674,102 @@ int gadm_dgemm_dk(gadm_handle h, const double* a, const double* b, int64_t d, in
   DeviceGuard guard(h->device);
   dim3 grid((unsigned)((k + 31) / 32), (unsigned)((d + gadm::agg::kDgemmTile - 1) / gadm::agg::kDgemmTile));
   gadm::agg::dgemm_dk_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(a, b, d, k, zero_below, c);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+// ------------------------------------------------------------------ RidgeCV datamodel estimator (lds.py:411-421)
+int gadm_center_columns(gadm_handle h, const double* x, int64_t n, int64_t d, double* xc, double* mean, void* stream) {
+  GADM_REQUIRE(h && x && xc && mean && n > 0 && d > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::ridge::center_columns_kernel<<<(unsigned)((d + 63) / 64), 64, 0, as_stream(stream)>>>(x, n, d, xc, mean);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_dgemm(gadm_handle h, int trans_a, const double* a, int64_t lda, const double* b, int64_t ldb, int64_t m,
+               int64_t j, int64_t n, double* c, int64_t ldc, void* stream) {
+  GADM_REQUIRE(h && a && b && c && m > 0 && j > 0 && n > 0 && lda > 0 && ldb >= n && ldc >= n, "bad argument");
+  DeviceGuard guard(h->device);
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32));
+  if (trans_a) gadm::ridge::dgemm_kernel<true><<<grid, dim3(32, 8), 0, as_stream(stream)>>>(a, lda, b, ldb, m, j, n, c, ldc);
+  else gadm::ridge::dgemm_kernel<false><<<grid, dim3(32, 8), 0, as_stream(stream)>>>(a, lda, b, ldb, m, j, n, c, ldc);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int64_t gadm_sym_eig_workspace_bytes(int64_t d) {
+  const int64_t dp = (d + 1) & ~1ll;
+  return 2 * dp * dp * (int64_t)sizeof(double);
+}
+
+int gadm_sym_eig(gadm_handle h, const double* a, int64_t d, double* evals, double* v, void* workspace,
+                 int64_t workspace_bytes, int* info, void* stream) {
+  GADM_REQUIRE(h && a && evals && v && workspace && d > 0 && d <= 8192, "bad argument");
+  const int64_t need = gadm_sym_eig_workspace_bytes(d);
+  if (workspace_bytes < need)
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)need);
+  DeviceGuard guard(h->device);
+  const int use_smem = need <= 200 * 1024;
+  auto kernel = gadm::ridge::sym_eig_kernel;
+  if (use_smem) GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  kernel<<<1, gadm::agg::kPinvThreads, use_smem ? (size_t)need : 0, as_stream(stream)>>>(
+      a, (int)d, evals, v, reinterpret_cast<double*>(workspace), use_smem, info);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_ridge_gcv(gadm_handle h, const double* z, const double* t, const double* yc, const double* evals,
+                   const double* alphas, int64_t n, int64_t d, int64_t k, int64_t n_alphas, double* q_work,
+                   double* den_work, double* score, void* stream) {
+  GADM_REQUIRE(h && z && t && yc && evals && alphas && q_work && den_work && score, "null argument");
+  GADM_REQUIRE(n > 0 && d > 0 && k > 0 && n_alphas > 0 && n_alphas <= 65535, "bad size");
+  GADM_REQUIRE(d <= 1600, "d = %lld: the GCV kernel stages a [d, 16] slab in shared memory (d <= 1600)", (long long)d);
+  DeviceGuard guard(h->device);
+  cudaStream_t st = as_stream(stream);
+  gadm::ridge::column_sums_kernel<<<(unsigned)((d + 63) / 64), 64, 0, st>>>(z, n, d, q_work);
+  GADM_LAUNCHED(h);
+  const int64_t jobs = n_alphas * n;
+  gadm::ridge::ridge_denominator_kernel<<<(unsigned)((jobs + 7) / 8), 256, 0, st>>>(z, evals, q_work, alphas, n, d,
+                                                                                    n_alphas, den_work);
+  GADM_LAUNCHED(h);
+  if (d <= 400) {
+    constexpr int kTX = 32;
+    const size_t smem = ((size_t)d * 2 * kTX + (256 / kTX) * 2 * kTX) * sizeof(double);
+    auto kernel = gadm::ridge::ridge_gcv_score_kernel<kTX>;
+    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((k + 2 * kTX - 1) / (2 * kTX)), (unsigned)n_alphas);
+    kernel<<<grid, dim3(kTX, 256 / kTX), smem, st>>>(z, t, yc, evals, den_work, alphas, n, d, k, score);
+  } else {
+    constexpr int kTX = 8;
+    const size_t smem = ((size_t)d * 2 * kTX + (256 / kTX) * 2 * kTX) * sizeof(double);
+    auto kernel = gadm::ridge::ridge_gcv_score_kernel<kTX>;
+    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((k + 2 * kTX - 1) / (2 * kTX)), (unsigned)n_alphas);
+    kernel<<<grid, dim3(kTX, 256 / kTX), smem, st>>>(z, t, yc, evals, den_work, alphas, n, d, k, score);
+  }
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_ridge_select(gadm_handle h, const double* score, int64_t n_alphas, int64_t k, int per_target,
+                      const double* alphas, const double* evals, const double* t, int64_t d, int32_t* best,
+                      double* best_score, double* t_scaled, void* stream) {
+  GADM_REQUIRE(h && score && alphas && evals && t && best && best_score && t_scaled && n_alphas > 0 && k > 0 && d > 0,
+               "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::ridge::ridge_select_kernel<<<(unsigned)((k + 127) / 128), 128, 0, as_stream(stream)>>>(
+      score, n_alphas, k, per_target, alphas, evals, t, d, best, best_score, t_scaled);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_ridge_intercept(gadm_handle h, const double* coef, const double* xmean, const double* ymean, int64_t d,
+                         int64_t k, double* intercept, void* stream) {
+  GADM_REQUIRE(h && coef && xmean && ymean && intercept && d > 0 && k > 0, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::ridge::ridge_intercept_kernel<<<(unsigned)((k + 127) / 128), 128, 0, as_stream(stream)>>>(coef, xmean, ymean, d,
+                                                                                                  k, intercept);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

@@ -101,12 +101,15 @@ __device__ __forceinline__ uint32_t num_segments(uint32_t kb0, uint32_t kb1, uin
   return (kb1 - kb0 + seg_kb - 1) / seg_kb;
 }
 
-// The partial tiles in flight (one per cluster, 33-37 MB in total) are re-touched once per segment; without a hint
-// the gradient stream pushes them out of L2 in between and every segment costs a DRAM read + write of the tile
-// (ncu, full size: +72 GB per launch).  evict_last keeps them resident.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+// The partial tiles in flight (one per cluster, 33-37 MB in total) are re-touched once per segment; in between the
+// gradient stream pushes them out of L2, so every segment costs a DRAM read + write of the tile.  An evict_last
+// hint cuts the re-reads to a third in the quad kernel (ncu, full size: DRAM 178 -> 150 GB per launch; the
+// write-backs remain, L2 cleans dirty lines regardless).  In the faster pair kernel the pinned tiles crowd the
+// window in which the 16 clusters of a D-split share gradient tiles (71 -> 82 GB), so it keeps the default policy.
+__device__ __forceinline__ uint64_t l2_policy(bool evict_last) {
   uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  if (evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
 __device__ __forceinline__ void red_add_v4(float* p, uint4 v, uint64_t pol) {
@@ -337,7 +340,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp >= R::kFirstEpiWarp && warp < R::kFirstEpiWarp + 4) {
     // ===================== epilogue: TMEM -> registers -> split-K partial tile
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const uint64_t pol = l2_policy_evict_last();
+    const uint64_t pol = l2_policy(false);
     uint32_t seg_iter = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
       const uint32_t split = u / a.n_tiles;

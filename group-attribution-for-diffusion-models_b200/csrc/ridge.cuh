@@ -1,0 +1,250 @@
+// Datamodel estimator of lds.py:411-421:  RidgeCV(alphas=np.linspace(0.01, 10, 100)).fit(masks, targets[:, i])
+// for every model behaviour i -- sklearn's efficient leave-one-out (GCV) ridge with an intercept -- batched over
+// all K behaviours and all alphas.  (The reference refits, and re-decomposes the same mask matrix, once per
+// behaviour.)
+//
+// sklearn 1.9 arithmetic restated (sklearn/linear_model/_ridge.py, _RidgeGCV, dense X, fit_intercept=True,
+// gcv_mode "cov" for n > d / "gram" for n <= d; both are the same function of the centred data):
+//   Xc = X - mean_rows(X), yc = y - mean(y);  C = Xc^T Xc = V L V^T
+//   H^-1(a) = V diag(1 / (L + a)) V^T
+//   alpha*c = yc - Xc H^-1 Xc^T yc
+//   alpha*d = 1 - diag(Xc H^-1 Xc^T) - (1 - Xc H^-1 Xc^T 1) / n
+//   looe = (alpha*c) / (alpha*d);  score(a) = -mean(looe^2);  alpha_ = first a with the largest score
+//   coef = H^-1(alpha_) Xc^T yc;  intercept = mean(y) - mean_rows(X) . coef
+// With Z = Xc V (n x d), T = Z^T Yc (d x K), q = Z^T 1 and w_j(a) = 1 / (L_j + a):
+//   (Xc H^-1 Xc^T yc)_i = sum_j Z_ij w_j T_jk      diag_i = sum_j Z_ij^2 w_j      (Xc H^-1 Xc^T 1)_i = sum_j Z_ij w_j q_j
+// so one decomposition serves every alpha and every behaviour; the work is the A x (n x d) x (d x K) contraction
+// in ridge_gcv_score_kernel (fp64 FMA pipe), everything else is O(n d^2 + n d K).
+// All fp64 SIMT with fixed summation orders (deterministic).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "aggregate.cuh"
+
+namespace gadm {
+namespace ridge {
+
+// mean[j] = mean_i X[i, j] (sequential over i: deterministic); Xc = X - mean.  One thread per column.
+__global__ void center_columns_kernel(const double* __restrict__ X, int64_t n, int64_t d, double* __restrict__ Xc,
+                                      double* __restrict__ mean) {
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += X[i * d + j];
+  const double m = s / static_cast<double>(n);
+  mean[j] = m;
+  for (int64_t i = 0; i < n; ++i) Xc[i * d + j] = X[i * d + j] - m;
+}
+
+// C[i, k] = sum_j op(A)(i, j) * B[j, k];  op(A)(i, j) = A[i * lda + j] (kTransA = false) or A[j * lda + i] (true).
+// B: [J, N] row pitch ldb, C: [M, N] row pitch ldc.  32 x 32 output tile, blockDim (32, 8), 4 rows per thread.
+template <bool kTransA>
+__global__ void dgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                             int64_t M, int64_t J, int64_t N, double* __restrict__ Cout, int64_t ldc) {
+  __shared__ double sA[32][33];
+  __shared__ double sB[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * 32, k0 = static_cast<int64_t>(blockIdx.x) * 32;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t j0 = 0; j0 < J; j0 += 32) {
+    for (int t = ty; t < 32; t += 8) {
+      // sA[row i][col j]
+      if (kTransA) {
+        const int64_t j = j0 + t, i = i0 + tx;  // coalesced along i
+        sA[tx][t] = (i < M && j < J) ? A[j * lda + i] : 0.0;
+      } else {
+        const int64_t i = i0 + t, j = j0 + tx;  // coalesced along j
+        sA[t][tx] = (i < M && j < J) ? A[i * lda + j] : 0.0;
+      }
+      const int64_t jb = j0 + t, kb = k0 + tx;
+      sB[t][tx] = (jb < J && kb < N) ? B[jb * ldb + kb] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const double b = sB[jj][tx];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[t] += sA[ty + 8 * t][jj] * b;
+    }
+    __syncthreads();
+  }
+  const int64_t k = k0 + tx;
+  if (k < N) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int64_t i = i0 + ty + 8 * t;
+      if (i < M) Cout[i * ldc + k] = acc[t];
+    }
+  }
+}
+
+// Symmetric eigendecomposition A = V diag(evals) V^T by the one-sided Jacobi of aggregate.cuh (one CTA, fp64).
+// V: [d, d] row-major, COLUMN i = eigenvector i; evals unsorted.  work: 2 dp^2 doubles (smem when it fits).
+__global__ void __launch_bounds__(agg::kPinvThreads, 1)
+sym_eig_kernel(const double* __restrict__ A, int d, double* __restrict__ evals, double* __restrict__ V, double* gwork,
+               int use_smem, int* __restrict__ info) {
+  extern __shared__ double eig_smem[];
+  const int dp = (d + 1) & ~1;
+  double* G = use_smem ? eig_smem : gwork;
+  double* Vt = G + static_cast<size_t>(dp) * dp;
+  __shared__ int s_rot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = agg::kPinvThreads / 32;
+  for (int idx = tid; idx < dp * dp; idx += agg::kPinvThreads) {
+    const int i = idx / dp, j = idx % dp;
+    G[idx] = (i < d && j < d) ? A[i * d + j] : 0.0;
+    Vt[idx] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int sweeps = agg::jacobi_orthogonalise_rows(G, Vt, dp, &s_rot);
+  __syncthreads();
+  // lambda_i = g_i . v_i (signed); the padding row (d odd) carries lambda = 0 and the unit vector e_{dp-1}: dropped
+  // by writing only the d x d block -- its coupling to the others is exactly zero because row/column dp-1 of A is zero.
+  for (int i = warp; i < d; i += nwarps) {
+    double a = 0.0;
+    for (int j = lane; j < dp; j += 32) a += G[static_cast<size_t>(i) * dp + j] * Vt[static_cast<size_t>(i) * dp + j];
+    a = agg::warp_sum(a);
+    if (lane == 0) evals[i] = a;
+  }
+  for (int idx = tid; idx < d * d; idx += agg::kPinvThreads) {
+    const int r = idx / d, c = idx % d;
+    V[idx] = Vt[static_cast<size_t>(c) * dp + r];
+  }
+  if (tid == 0 && info) info[0] = sweeps;
+}
+
+// q[j] = sum_i Z[i, j]  (column sums, sequential: deterministic)
+__global__ void column_sums_kernel(const double* __restrict__ Z, int64_t n, int64_t d, double* __restrict__ q) {
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += Z[i * d + j];
+  q[j] = s;
+}
+
+// den[a, i] = alpha*d of the header comment.  One warp per (a, i).
+__global__ void ridge_denominator_kernel(const double* __restrict__ Z, const double* __restrict__ evals,
+                                         const double* __restrict__ q, const double* __restrict__ alphas, int64_t n,
+                                         int64_t d, int64_t A, double* __restrict__ den) {
+  const int lane = threadIdx.x & 31;
+  const int64_t job = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (job >= A * n) return;
+  const int64_t a = job / n, i = job % n;
+  const double alpha = alphas[a];
+  double s2 = 0.0, s1 = 0.0;
+  for (int64_t j = lane; j < d; j += 32) {
+    const double z = Z[i * d + j], w = 1.0 / (evals[j] + alpha);
+    s2 += z * z * w;
+    s1 += z * w * q[j];
+  }
+  s2 = agg::warp_sum(s2);
+  s1 = agg::warp_sum(s1);
+  if (lane == 0) den[job] = 1.0 - s2 - (1.0 - s1) / static_cast<double>(n);
+}
+
+// score[a, k] = -(1/n) sum_i ( (Yc[i,k] - sum_j Z[i,j] w_j(a) T[j,k]) / den[a,i] )^2
+// Block = (alpha a, 2*kTX behaviours); Wt[j][kk] = w_j T[j, k0+kk] staged in smem (d x 2kTX doubles); each thread owns
+// 2 adjacent behaviours x 4 rows per pass (8 accumulators, Z read as warp broadcasts).  blockDim = (kTX, 256 / kTX).
+template <int kTX>
+__global__ void __launch_bounds__(256)
+ridge_gcv_score_kernel(const double* __restrict__ Z, const double* __restrict__ T, const double* __restrict__ Yc,
+                       const double* __restrict__ evals, const double* __restrict__ den,
+                       const double* __restrict__ alphas, int64_t n, int64_t d, int64_t K, double* __restrict__ score) {
+  constexpr int kTK = 2 * kTX;
+  constexpr int kTY = 256 / kTX;
+  extern __shared__ double ridge_smem[];  // Wt [d][kTK], then red [kTY][kTK]
+  double* Wt = ridge_smem;
+  double* red = ridge_smem + static_cast<size_t>(d) * kTK;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t a = blockIdx.y;
+  const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kTK;
+  const double alpha = alphas[a];
+  for (int idx = ty * kTX + tx; idx < d * kTK; idx += 256) {
+    const int j = idx / kTK, kk = idx % kTK;
+    const int64_t k = k0 + kk;
+    Wt[idx] = (k < K) ? T[static_cast<int64_t>(j) * K + k] / (evals[j] + alpha) : 0.0;
+  }
+  __syncthreads();
+  const int64_t ka = k0 + 2 * tx, kb = ka + 1;
+  double sum_a = 0.0, sum_b = 0.0;
+  const double* dn = den + a * n;
+  for (int64_t i0 = static_cast<int64_t>(ty) * 4; i0 < n; i0 += kTY * 4) {
+    double acc[4][2];
+    const double* zr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      acc[r][0] = acc[r][1] = 0.0;
+      const int64_t i = (i0 + r < n) ? i0 + r : n - 1;  // clamped rows are discarded below
+      zr[r] = Z + i * d;
+    }
+#pragma unroll 4
+    for (int64_t j = 0; j < d; ++j) {
+      const double2 w = *reinterpret_cast<const double2*>(Wt + j * kTK + 2 * tx);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double z = zr[r][j];
+        acc[r][0] += z * w.x;
+        acc[r][1] += z * w.y;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = i0 + r;
+      if (i < n) {
+        const double dd = dn[i];
+        if (ka < K) { const double e = (Yc[i * K + ka] - acc[r][0]) / dd; sum_a += e * e; }
+        if (kb < K) { const double e = (Yc[i * K + kb] - acc[r][1]) / dd; sum_b += e * e; }
+      }
+    }
+  }
+  red[ty * kTK + 2 * tx] = sum_a;
+  red[ty * kTK + 2 * tx + 1] = sum_b;
+  __syncthreads();
+  if (ty == 0) {
+    double sa = 0.0, sb = 0.0;
+    for (int t = 0; t < kTY; ++t) { sa += red[t * kTK + 2 * tx]; sb += red[t * kTK + 2 * tx + 1]; }
+    if (ka < K) score[a * K + ka] = -sa / static_cast<double>(n);
+    if (kb < K) score[a * K + kb] = -sb / static_cast<double>(n);
+  }
+}
+
+// Model selection (_RidgeGCV.fit loop): best[k] = first alpha index with the strictly largest score
+// (per behaviour, or -- per_target == 0 -- of the mean over behaviours, shared by all k), then
+// Ts[j, k] = T[j, k] / (evals[j] + alphas[best[k]]) so that coef = V Ts.
+__global__ void ridge_select_kernel(const double* __restrict__ score, int64_t A, int64_t K, int per_target,
+                                    const double* __restrict__ alphas, const double* __restrict__ evals,
+                                    const double* __restrict__ T, int64_t d, int32_t* __restrict__ best,
+                                    double* __restrict__ best_score, double* __restrict__ Ts) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int32_t bi = 0;
+  double bs = 0.0;
+  for (int64_t a = 0; a < A; ++a) {
+    double sc;
+    if (per_target) sc = score[a * K + k];
+    else {  // np.mean(-squared_errors) over all n*K entries = mean_k score[a, k] (fixed order; every thread the same)
+      double s = 0.0;
+      for (int64_t kk = 0; kk < K; ++kk) s += score[a * K + kk];
+      sc = s / static_cast<double>(K);
+    }
+    if (a == 0 || sc > bs) { bs = sc; bi = static_cast<int32_t>(a); }
+  }
+  best[k] = bi;
+  best_score[k] = bs;
+  const double alpha = alphas[bi];
+  for (int64_t j = 0; j < d; ++j) Ts[j * K + k] = T[j * K + k] / (evals[j] + alpha);
+}
+
+// intercept[k] = ymean[k] - sum_j xmean[j] * coef[j, k]   (LinearModel._set_intercept)
+__global__ void ridge_intercept_kernel(const double* __restrict__ coef, const double* __restrict__ xmean,
+                                       const double* __restrict__ ymean, int64_t d, int64_t K,
+                                       double* __restrict__ intercept) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double s = 0.0;
+  for (int64_t j = 0; j < d; ++j) s += xmean[j] * coef[j * K + k];
+  intercept[k] = ymean[k] - s;
+}
+
+}  // namespace ridge
+}  // namespace gadm

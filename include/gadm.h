@@ -156,6 +156,34 @@ int gadm_sym_pinv(gadm_handle h, const double* a, int64_t d, double rcond, doubl
 /* C[i, k] = sum_j A[i, j] * B[j, k]; |C| < zero_below -> 0 (datashapley.py:45).  A [d, d], B and C [d, K]. */
 int gadm_dgemm_dk(gadm_handle h, const double* a, const double* b, int64_t d, int64_t k, double zero_below, double* c,
                   void* stream);
+/* ---- RidgeCV datamodel estimator: replaces `RidgeCV(alphas=np.linspace(0.01, 10, 100)).fit(masks, targets[:, i])`
+ * per behaviour (lds.py:411-421; sklearn _RidgeGCV: efficient leave-one-out ridge with intercept), batched over all
+ * behaviours and alphas.  Sequence: center_columns(X), center_columns(Y) -> dgemm C = Xc^T Xc -> sym_eig ->
+ * dgemm Z = Xc V -> dgemm T = Z^T Yc -> ridge_gcv (scores[a, k]) -> ridge_select -> dgemm coef = V Ts ->
+ * ridge_intercept.  All fp64, deterministic summation orders. */
+/* xc[i, j] = x[i, j] - mean[j], mean[j] = mean_i x[i, j]; x, xc: [n, d] */
+int gadm_center_columns(gadm_handle h, const double* x, int64_t n, int64_t d, double* xc, double* mean, void* stream);
+/* c[m, n] = op(a) b; op(a)(i, j) = a[i * lda + j] (trans_a = 0) or a[j * lda + i] (trans_a = 1); b: [j, n] */
+int gadm_dgemm(gadm_handle h, int trans_a, const double* a, int64_t lda, const double* b, int64_t ldb, int64_t m,
+               int64_t j, int64_t n, double* c, int64_t ldc, void* stream);
+/* a = v diag(evals) v^T for symmetric a [d, d] (one-sided Jacobi, fp64); column i of v = eigenvector i, unsorted.
+ * info (device int[1], may be NULL) = sweeps. */
+int64_t gadm_sym_eig_workspace_bytes(int64_t d);
+int gadm_sym_eig(gadm_handle h, const double* a, int64_t d, double* evals, double* v, void* workspace,
+                 int64_t workspace_bytes, int* info, void* stream);
+/* score[a, k] = -mean_i looe(a)[i, k]^2 (sklearn _RidgeGCV with intercept).  z = Xc V [n, d], t = z^T yc [d, k],
+ * yc [n, k] centred targets; q_work: d doubles, den_work: n_alphas * n doubles. */
+int gadm_ridge_gcv(gadm_handle h, const double* z, const double* t, const double* yc, const double* evals,
+                   const double* alphas, int64_t n, int64_t d, int64_t k, int64_t n_alphas, double* q_work,
+                   double* den_work, double* score, void* stream);
+/* best[k] = first alpha index with the largest score (per behaviour, or of the mean over behaviours when
+ * per_target = 0); t_scaled[j, k] = t[j, k] / (evals[j] + alphas[best[k]]) (coef = v t_scaled). */
+int gadm_ridge_select(gadm_handle h, const double* score, int64_t n_alphas, int64_t k, int per_target,
+                      const double* alphas, const double* evals, const double* t, int64_t d, int32_t* best,
+                      double* best_score, double* t_scaled, void* stream);
+/* intercept[k] = ymean[k] - xmean . coef[:, k] */
+int gadm_ridge_intercept(gadm_handle h, const double* coef, const double* xmean, const double* ymean, int64_t d,
+                         int64_t k, double* intercept, void* stream);
 /* Efficiency-constraint step of closed-form KernelSHAP (datashapley.py:38-43):
  * rhs[:, k] = b[:, k] - (1^T Ainv b[:, k] - v1[k] + v0[k]) / (1^T Ainv 1) ; colsum_work: d + 1 doubles */
 int gadm_shapley_rhs(gadm_handle h, const double* ainv, const double* b, int64_t d, int64_t k, const double* v1,

@@ -261,10 +261,44 @@ def make_lds_py(tmp):
     print("lds_py_golden.npz", mean, ci)
 
 
+def make_ridge():
+    """lds.py:411-421: the datamodel branch is a plain sklearn call per behaviour; executed here as written there
+    (`RidgeCV(alphas=np.linspace(0.01, 10, 100)).fit(train_masks_fold, train_targets_fold[:, i])`), on masks drawn
+    by the reference's own datamodel sampler (src/datasets.py:619-626 logic via oracle.aggregation.datamodel_masks,
+    itself pinned to the reference in aggregation_golden.npz)."""
+    import sklearn
+    from sklearn.linear_model import RidgeCV
+
+    from oracle.aggregation import datamodel_masks
+
+    res = {"sklearn_version": np.array(sklearn.__version__)}
+    rng = np.random.RandomState(7)
+    for tag, n, d, K, noise in (("long", 300, 40, 6, 0.3), ("wide", 24, 40, 4, 0.05), ("square", 40, 40, 3, 1.0)):
+        X = datamodel_masks(d, list(range(1000, 1000 + n)), alpha=0.5)
+        w = rng.normal(size=(d, K))
+        Y = X @ w + noise * rng.normal(size=(n, K)) + 3.0
+        coefs, alphas, ics = [], [], []
+        for i in range(K):
+            m = RidgeCV(alphas=np.linspace(0.01, 10, 100)).fit(X, Y[:, i])
+            coefs.append(m.coef_); alphas.append(m.alpha_); ics.append(m.intercept_)
+        res[f"{tag}_X"] = X.astype(np.uint8)
+        res[f"{tag}_Y"] = Y
+        res[f"{tag}_coef"] = np.stack(coefs, axis=1)
+        res[f"{tag}_alpha"] = np.asarray(alphas)
+        res[f"{tag}_intercept"] = np.asarray(ics)
+    np.savez_compressed(os.path.join(HERE, "ridge_golden.npz"), **res)
+    print("ridge_golden.npz", {k: v.shape for k, v in res.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ridge":  # regenerate only the sklearn-based fixture
+        sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+        make_ridge()
+        sys.exit(0)
     with tempfile.TemporaryDirectory() as tmp:
         consts = _inject_env(tmp)
         make_aggregation(tmp)
         make_traks(tmp, consts)
         make_gradient_scores(tmp, consts)
         make_lds_py(tmp)
+    make_ridge()
