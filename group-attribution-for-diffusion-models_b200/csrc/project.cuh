@@ -105,22 +105,29 @@ __device__ __forceinline__ uint32_t num_segments(uint32_t kb0, uint32_t kb1, uin
 // gradient stream pushes them out of L2, so every segment costs a DRAM read + write of the tile.  An evict_last
 // hint cuts the re-reads to a third in the quad kernel (ncu, full size: DRAM 178 -> 150 GB per launch; the
 // write-backs remain, L2 cleans dirty lines regardless).  In the faster pair kernel the pinned tiles crowd the
-// window in which the 16 clusters of a D-split share gradient tiles (71 -> 82 GB), so it keeps the default policy.
-__device__ __forceinline__ uint64_t l2_policy(bool evict_last) {
+// window in which the 16 clusters of a D-split share gradient tiles (71 -> 82 GB), so it issues the same instructions without a hint (pol == 0).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
-  if (evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
 __device__ __forceinline__ void red_add_v4(float* p, uint4 v, uint64_t pol) {
-  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(__uint_as_float(v.x)),
-               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)), "l"(pol)
-               : "memory");
+  if (pol != 0)
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)), "l"(pol)
+                 : "memory");
+  else
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
 }
 __device__ __forceinline__ void st_global_v4_hint(float* p, uint4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w), "l"(pol)
-               : "memory");
+  if (pol != 0)
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
+                 : "memory");
+  else
+    *reinterpret_cast<uint4*>(p) = v;
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
@@ -340,7 +347,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp >= R::kFirstEpiWarp && warp < R::kFirstEpiWarp + 4) {
     // ===================== epilogue: TMEM -> registers -> split-K partial tile
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const uint64_t pol = l2_policy(false);
+    const uint64_t pol = 0;  // no L2 hint in the pair kernel (see red_add_v4)
     uint32_t seg_iter = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
       const uint32_t split = u / a.n_tiles;

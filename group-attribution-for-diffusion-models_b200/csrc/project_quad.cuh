@@ -184,7 +184,7 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp >= R::kFirstEpiWarp && warp < R::kFirstEpiWarp + 4) {
     // ===================== epilogue: TMEM -> registers -> split-K partial tile (rows of this pair)
     const int q = warp & 3;
-    const uint64_t pol = l2_policy(true);
+    const uint64_t pol = l2_policy_evict_last();
     uint32_t seg_iter = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
       const uint32_t split = u / a.n_tiles;

@@ -159,3 +159,33 @@ def test_compute_gradient_scores_reads_reference_files(tmp_path):
                               projector_dim=k, sample_size=T, k_partition=10, model_behavior_key="fid")
     s = G.compute_dtrak_trak_scores(args, train_idx=np.arange(10), outdir=str(tmp_path / "out"))
     assert np.allclose(s, g["out_relative_if_byclass=0"].mean(axis=0)[:10], rtol=2e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,k,T", [(300, 1024, 20), (1000, 2048, 64), (129, 512, 5)])
+def test_dual_path_when_fewer_examples_than_dimensions(N, k, T):
+    """BASELINE configs 3 / 4 have N = 5000 < k = 8192 / 32768: the scorer factors Phi Phi^T + lam I (N x N)
+    instead of Phi^T Phi + lam I (k x k).  Same scores as the fp64 oracle of the reference's primal formulas and as
+    the forced primal path."""
+    import gadm_b200 as G
+
+    train, gen = _rand((N, k), 21), _rand((T, k), 22)
+    got, scorer = G.trak_scores(train, gen, lam=0.5, return_scorer=True)
+    assert scorer.dual and scorer.k == N
+    scorer.check()
+    want = oscore.score_fp64(train.cpu().numpy(), gen.cpu().numpy(), 0.5)
+    for name in ("grad_sim", "trak", "relative_influence", "renorm_influence"):
+        g = got[name].cpu().numpy().astype(np.float64)
+        assert np.abs(g - want[name]).max() < 2e-4 * np.abs(want[name]).max(), name
+    primal = G.TrakScorer(0.5).fit(train, dual=False)
+    s_primal = primal.score_matrix(gen, train)
+    s_dual = scorer.score_matrix(gen, train)
+    assert float((s_primal - s_dual).abs().max()) < 2e-4 * float(s_primal.abs().max())
+    # rows @ K^-1 through Woodbury agrees with the primal solve (normwise)
+    rows = _rand((7, k), 23)
+    a, b = primal.solve_rows(rows), scorer.solve_rows(rows)
+    assert float((a - b).abs().max()) < 1e-4 * float(a.abs().max())
+    for gtype in ("trak", "relative_if", "renormalized_if"):
+        s, sc = G.gradient_scores(train, gen, gtype)
+        assert sc.dual
+        w, _ = oscore.score_numpy(train.cpu().numpy(), gen.cpu().numpy(), gtype, average=False)
+        assert np.abs(s.cpu().numpy() - w).max() < 2e-4 * np.abs(w).max(), gtype

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--d", type=int, default=100)
     ap.add_argument("--K", type=int, default=1000)
     ap.add_argument("--m", type=int, default=100)
+    ap.add_argument("--cpu-targets", type=int, default=0, help="time sklearn RidgeCV on this many behaviours (host)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     rng = np.random.RandomState(0)
@@ -48,6 +49,20 @@ def main():
     ms, _ = ev(lambda: agg.data_shapley_batched(masks, Y, v0 + 1.0, v0, as_numpy=False)); res["shapley_total_ms"] = ms
     alg = a.n * a.d / 8 + 8.0 * a.n * a.K + 8.0 * a.d * a.K
     res["shapley_algorithmic_GBps"] = alg / ms / 1e6
+    # datamodel estimator (lds.py:411-421): RidgeCV over 100 alphas for every behaviour
+    from gadm_b200.datamodel import ridge_cv_batched
+    Xf = torch.as_tensor(X.astype(np.float64)).to(dev)
+    ms, rc = ev(lambda: ridge_cv_batched(Xf, Y, as_numpy=False)); res["ridgecv_total_ms"] = ms
+    res["ridgecv_gcv_fp64_gflops"] = 2.0 * 100 * a.n * a.d * a.K / ms / 1e6
+    if a.cpu_targets:
+        import time
+        from sklearn.linear_model import RidgeCV
+        Yh = Y[:, :a.cpu_targets].cpu().numpy(); Xh = X.astype(np.float64)
+        t0 = time.perf_counter()
+        for i in range(a.cpu_targets):
+            RidgeCV(alphas=np.linspace(0.01, 10, 100)).fit(Xh, Yh[:, i])
+        res["ridgecv_sklearn_ms_per_target"] = (time.perf_counter() - t0) * 1e3 / a.cpu_targets
+        res["ridgecv_sklearn_ms_extrapolated_K"] = res["ridgecv_sklearn_ms_per_target"] * a.K
     print(json.dumps(res))
 
 
