@@ -46,6 +46,16 @@ def _check_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+def _clone_padded(t: torch.Tensor) -> torch.Tensor:
+    """Copy of a 2-D fp32 tensor whose row pitch is a multiple of 4 floats (16 B: TMA / float4 requirement)."""
+    ld = -(-t.shape[1] // 4) * 4
+    buf = torch.zeros(t.shape[0], ld, dtype=_f32, device=t.device) if ld != t.shape[1] else \
+        torch.empty(t.shape[0], ld, dtype=_f32, device=t.device)
+    out = buf[:, :t.shape[1]]
+    out.copy_(t)
+    return out
+
+
 def _h(t: torch.Tensor):
     return _lib.get_handle(t.device)
 
@@ -58,8 +68,10 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, a
     if a.shape[1] != b.shape[1]:
         raise ValueError(f"contraction mismatch: {tuple(a.shape)} x {tuple(b.shape)}^T")
     m, n, k = a.shape[0], b.shape[0], a.shape[1]
-    if out is None:
-        out = torch.zeros(m, n, dtype=_f32, device=a.device) if lower_only else torch.empty(m, n, dtype=_f32, device=a.device)
+    if out is None:  # row pitch padded to a multiple of 4 floats so the result is TMA-loadable as an operand later
+        ld = -(-n // 4) * 4
+        out = (torch.zeros(m, ld, dtype=_f32, device=a.device) if lower_only or ld != n
+               else torch.empty(m, ld, dtype=_f32, device=a.device))[:, :n]
     h = _h(a)
     with torch.cuda.device(a.device):
         _lib.check(h.lib.gadm_gemm_tn(h.ptr, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
@@ -193,7 +205,7 @@ class TrakScorer:
         if y.shape[1] != self.k:
             raise ValueError(f"rows have {y.shape[1]} columns, the factored system has {self.k}")
         if not inplace or y.data_ptr() != rows.data_ptr():
-            y = y.clone()
+            y = _clone_padded(y)
         if y.stride(0) % 4 != 0:
             raise ValueError("row pitch must be a multiple of 4")
         h = _h(y)
@@ -209,7 +221,7 @@ class TrakScorer:
             # Woodbury: K^-1 = (I - Phi^T A^-1 Phi) / lam  (normwise accurate; the score paths below never need it)
             r = _check_cuda_f32(rows, "rows")
             z = self._solve(gemm_tn(r, self.phi_all), inplace=True)          # (rows Phi^T) A^-1   [m, N]
-            out = r.clone()
+            out = _clone_padded(r)
             return gemm_tn(z, transpose(self.phi_all), out=out, alpha=-1.0 / self.lam, beta=1.0 / self.lam)
         return self._solve(rows, inplace)
 
@@ -240,7 +252,7 @@ TRAK_VARIANTS = ("grad_sim", "trak", "relative_influence", "renorm_influence")
 
 def trak_scores(train_phi: torch.Tensor, gen_phi: torch.Tensor, lam: float = 5e-1,
                 variants: Sequence[str] = TRAK_VARIANTS, journey_phi: torch.Tensor | None = None,
-                group=None, gather: bool = True, return_scorer: bool = False):
+                group=None, gather: bool = True, return_scorer: bool = False, dual: bool | None = None):
     """Per-training-example attribution vectors of text_to_image/traks.py:139-173 (mean over generated images).
 
     Returns dict name -> fp32 tensor [N] (all ranks' examples when ``gather`` and torch.distributed is up).
@@ -258,7 +270,7 @@ def trak_scores(train_phi: torch.Tensor, gen_phi: torch.Tensor, lam: float = 5e-
         del cos
     scorer = None
     if any(v in variants for v in ("trak", "relative_influence", "renorm_influence")) or journey_phi is not None:
-        scorer = TrakScorer(lam, group).fit(train)
+        scorer = TrakScorer(lam, group).fit(train, dual=dual)  # dual=None: N x N system when N_total < k
         s = scorer.score_matrix(gen, train)  # [T, N]
         if "trak" in variants:
             out["trak"] = col_mean_scaled(s)  # traks.py:156-157

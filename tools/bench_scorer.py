@@ -21,12 +21,25 @@ def main():
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--k", type=int, default=4096)
     ap.add_argument("--t", type=int, default=1000)
+    ap.add_argument("--totals-only", action="store_true", help="skip the per-stage timings (large k)")
+    ap.add_argument("--primal-too", action="store_true", help="also time the forced k x k path when N < k")
     a = ap.parse_args()
     dev = "cuda:0"
     g = torch.Generator(device=dev).manual_seed(0)
     train = torch.randn(a.n, a.k, device=dev, generator=g)
     gen = torch.randn(a.t, a.k, device=dev, generator=g)
     res = {"n": a.n, "k": a.k, "t": a.t}
+    if a.totals_only:
+        ms, out = timed(lambda: G.trak_scores(train, gen, variants=("trak",), return_scorer=True)); res["trak_total_ms"] = ms
+        res["dual"] = bool(out[1].dual)
+        ms, _ = timed(lambda: G.trak_scores(train, gen)); res["all_variants_total_ms"] = ms
+        if a.primal_too:
+            ms, outp = timed(lambda: G.trak_scores(train, gen, variants=("trak",), dual=False), iters=1)
+            res["trak_total_primal_ms"] = ms
+            res["max_rel_diff_dual_vs_primal"] = float((out[0]["trak"] - outp["trak"]).abs().max() / outp["trak"].abs().max())
+        res["watchdog"] = G._lib.get_handle(dev).watchdog_code()
+        print(json.dumps(res))
+        return
     ms, phi_t = timed(lambda: G.transpose(train)); res["transpose_ms"] = ms
     ms, gram = timed(lambda: G.gemm_tn(phi_t, phi_t, lower_only=True, diag_add=0.5)); res["gram_ms"] = ms
     res["gram_tflops_fp32_equiv_full"] = 2.0 * a.n * a.k * a.k / ms / 1e9
