@@ -492,7 +492,8 @@ int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, i
                    int64_t ld_out, void* stream) {
   GADM_REQUIRE(h && in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "bad argument");
   DeviceGuard guard(h->device);
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  dim3 grid((unsigned)((cols + gadm::gemm::kTrCols - 1) / gadm::gemm::kTrCols),
+            (unsigned)((rows + gadm::gemm::kTrRows - 1) / gadm::gemm::kTrRows));
   GADM_REQUIRE(grid.y < 65536, "too many row tiles");
   gadm::gemm::transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, rows, cols, ld_in, out, ld_out);
   GADM_LAUNCHED(h);

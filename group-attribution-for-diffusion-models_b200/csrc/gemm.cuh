@@ -225,19 +225,42 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
 // ------------------------------------------------------------------ helpers around the GEMM
 
-// out[c, r] = in[r, c]; in: [R, C] pitch ld_in; out: [C, R_pad] pitch ld_out (columns R..ld_out untouched)
-__global__ void transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t ld_in,
-                                 float* __restrict__ out, int64_t ld_out) {
-  __shared__ float tile[32][33];
-  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32, r0 = static_cast<int64_t>(blockIdx.y) * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int64_t r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < Ccols) ? in[r * ld_in + c] : 0.f;
+// out[c, r] = in[r, c]; in: [R, C] pitch ld_in; out: [C, R_pad] pitch ld_out (columns R..ld_out untouched).
+// HBM-bound (8 B per element).  Tile = 128 rows x 64 columns: 256-byte read segments, 512-byte contiguous write
+// segments per output row -- with 32 x 32 tiles every 128-byte segment opened its own DRAM page on both sides
+// and the kernel ran at 300 GB/s (5.5 ms for the 50 000 x 4096 features of config 2).
+constexpr int kTrRows = 128, kTrCols = 64;
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t ld_in, float* __restrict__ out,
+                 int64_t ld_out) {
+  __shared__ float tile[kTrCols][kTrRows + 1];
+  const int x = threadIdx.x, y = threadIdx.y;  // (32, 8)
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kTrCols, r0 = static_cast<int64_t>(blockIdx.y) * kTrRows;
+  const bool vec_ok = (ld_in % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
+#pragma unroll 4
+  for (int i = y; i < kTrRows; i += 8) {
+    const int64_t r = r0 + i, c = c0 + 2 * x;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < R) {
+      if (vec_ok && c + 1 < Ccols) v = *reinterpret_cast<const float2*>(in + r * ld_in + c);
+      else {
+        if (c < Ccols) v.x = in[r * ld_in + c];
+        if (c + 1 < Ccols) v.y = in[r * ld_in + c + 1];
+      }
+    }
+    tile[2 * x][i] = v.x;
+    tile[2 * x + 1][i] = v.y;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int64_t c = c0 + i, r = r0 + threadIdx.x;
-    if (c < Ccols && r < R) out[c * ld_out + r] = tile[threadIdx.x][i];
+#pragma unroll 2
+  for (int cc = y; cc < kTrCols; cc += 8) {
+    const int64_t c = c0 + cc;
+    if (c >= Ccols) continue;
+#pragma unroll
+    for (int j = 0; j < kTrRows / 32; ++j) {
+      const int64_t r = r0 + x + 32 * j;
+      if (r < R) out[c * ld_out + r] = tile[cc][x + 32 * j];
+    }
   }
 }
 

@@ -199,3 +199,14 @@ def test_dual_path_when_fewer_examples_than_dimensions(N, k, T):
         s, sc = G.gradient_scores(train, gen, gtype)
         assert sc.dual
         assert np.abs(s.cpu().numpy() - w).max() < 2e-4 * np.abs(w).max(), gtype
+
+
+@pytest.mark.parametrize("R,C", [(1, 1), (33, 65), (129, 70), (128, 64), (1000, 4096), (257, 3)])
+def test_transpose_bit_exact(R, C):
+    import gadm_b200 as G
+
+    x = _rand((R, C), R + C)
+    assert torch.equal(G.transpose(x), x.T)
+    # non-contiguous / odd-pitch input (falls back to scalar loads)
+    wide = _rand((R, C + 3), 5)
+    assert torch.equal(G.transpose(wide[:, 1:C + 1]), wide[:, 1:C + 1].T)
