@@ -2,7 +2,7 @@
 from .projectors import BasicProjector, CudaProjector, DeferredProjection, ProjectionType, is_not_buffer  # noqa: F401
 from .aggregation import (PackedMasks, aoi_attr_batched, bootstrap_statistic, loo_attr_batched, data_banzhaf, data_banzhaf_batched, data_shapley,  # noqa: F401
                           data_shapley_batched, evaluate_lds, group_reduce, lds_per_test_set, masks_from_remaining_idx,
-                          spearman_matrix,
+                          spearman_matrix, lds_fit_sweep, convergence_metrics,
                           stable_rank, sym_pinv)
 from .scoring import (TrakScorer, aggregate_by_class, col_mean_scaled, compute_dtrak_trak_scores,  # noqa: F401
                       compute_gradient_scores, gemm_tn, gradient_scores, group_and_rank, row_norms, trak_scores,
@@ -16,7 +16,7 @@ __all__ = [
     "BasicProjector", "CudaProjector", "DeferredProjection", "ProjectionType", "is_not_buffer",
     "PackedMasks", "aoi_attr_batched", "loo_attr_batched", "bootstrap_statistic", "data_banzhaf", "data_banzhaf_batched", "data_shapley",
     "data_shapley_batched", "evaluate_lds", "group_reduce", "lds_per_test_set", "masks_from_remaining_idx", "spearman_matrix", "stable_rank",
-    "sym_pinv",
+    "sym_pinv", "lds_fit_sweep", "convergence_metrics",
     "TrakScorer", "aggregate_by_class", "col_mean_scaled", "compute_dtrak_trak_scores", "compute_gradient_scores",
     "gemm_tn", "gradient_scores", "group_and_rank", "row_norms", "trak_scores", "transpose",
     "counterfactual_split", "masks_from_seeds", "remove_data_by_datamodel", "remove_data_by_shapley",

@@ -308,3 +308,63 @@ def stable_rank(output, device=None) -> np.ndarray:
         rank = torch.empty(x.shape[0], dtype=torch.int64, device=dev)
         _lib.check(h.lib.gadm_stable_rank_desc(h.ptr, x.data_ptr(), x.shape[0], rank.data_ptr(), _lib.stream_ptr(dev)))
     return rank.cpu().numpy()
+
+
+def lds_fit_sweep(train_masks, train_targets, test_data_list, subset_sizes, removal_dist: str, full_targets=None,
+                  null_targets=None, train_indices=None, compat_loo_full_masks: bool = True, device=None):
+    """The fit-size sweep of lds.py:397-456: for every ``n`` in ``subset_sizes`` fit all behaviours on the first ``n``
+    rows of ``train_indices`` and evaluate the LDS on the three test sets.
+
+    ``removal_dist`` in {"datamodel", "shapley", "uniform", "loo", "add_one_in"} selects the estimator exactly like
+    ``args.removal_dist`` (RidgeCV / data_shapley / data_banzhaf / LOO / add-one-in).  The reference's LOO and
+    add-one-in branches use the *full* ``train_masks`` instead of the fold (lds.py:438,444); that is kept by default
+    (``compat_loo_full_masks``).  Returns a list of dicts {n, lds_mean, lds_ci, coef [d, K]}."""
+    from .datamodel import datamodel_ridge_batched
+
+    x = np.asarray(train_masks)
+    y = np.asarray(train_targets, dtype=np.float64)
+    if y.ndim == 1:
+        y = y[:, None]
+    K = y.shape[1]
+    idx = np.arange(x.shape[0]) if train_indices is None else np.asarray(train_indices)
+    out = []
+    for n in subset_sizes:
+        fold = idx[:n]
+        xf, yf = x[fold], y[fold]
+        if removal_dist == "datamodel":
+            coef = datamodel_ridge_batched(xf, yf, device=device)
+        elif removal_dist == "shapley":
+            coef = data_shapley_batched(xf, yf, np.asarray(full_targets, dtype=np.float64).reshape(-1)[:K],
+                                        np.asarray(null_targets, dtype=np.float64).reshape(-1)[:K], device=device)
+        elif removal_dist == "uniform":
+            coef = data_banzhaf_batched(xf, yf, device=device)
+        elif removal_dist == "loo":
+            xs, ys = (x, y) if compat_loo_full_masks else (xf, yf)
+            coef = loo_attr_batched(xs, ys, full_targets, device=device)
+        elif removal_dist == "add_one_in":
+            xs, ys = (x, y) if compat_loo_full_masks else (xf, yf)
+            coef = aoi_attr_batched(xs, ys, null_targets, device=device)
+        else:
+            raise ValueError(f"Removal distribution: {removal_dist} does not exist.")  # lds.py:447-450
+        lds_mean, lds_ci = evaluate_lds(coef, test_data_list, K, device=device)
+        out.append({"n": int(len(fold)), "lds_mean": float(lds_mean), "lds_ci": float(lds_ci), "coef": coef})
+    return out
+
+
+def convergence_metrics(baseline_attrs, attrs, device=None):
+    """MSE, Pearson and Spearman between two attribution vectors (text_to_image/shapley_convergence.py:261-268).
+    The rank correlation runs on the device kernel (scipy tie semantics); MSE / Pearson are d-element host sums."""
+    a = np.asarray(baseline_attrs, dtype=np.float64).reshape(-1)
+    b = np.asarray(attrs, dtype=np.float64).reshape(-1)
+    if a.shape != b.shape:
+        raise ValueError("attribution vectors must have the same length")
+    dev = _device(device)
+    h = _lib.get_handle(dev)
+    ta, tb = _dev_f64(a[:, None], dev), _dev_f64(b[:, None], dev)
+    rho = torch.empty(1, 1, dtype=_f64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(h.lib.gadm_lds_spearman(h.ptr, ta.data_ptr(), tb.data_ptr(), a.size, 1, None, 1, a.size, rho.data_ptr(),
+                                          _lib.stream_ptr(dev)))
+    am, bm = a - a.mean(), b - b.mean()
+    pearson = float((am @ bm) / np.sqrt((am @ am) * (bm @ bm)))
+    return {"mse": float(((a - b) ** 2).mean()), "pearson": pearson, "spearman": float(rho.item())}

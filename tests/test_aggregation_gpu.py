@@ -179,3 +179,57 @@ def test_loo_and_aoi_attributions():
     for k in range(K):
         _close(loo[:, k], oagg.loo_attr(X, Y[:, k], full[k]), 1e-11)
         _close(aoi[:, k], oagg.aoi_attr(X, Y[:, k], null[k]), 1e-11)
+
+
+@pytest.mark.parametrize("dist", ["datamodel", "shapley", "uniform", "loo", "add_one_in"])
+def test_fit_sweep_matches_reference_loop(dist):
+    """lds.py:397-456 restated with the oracle's per-behaviour estimators vs the batched device sweep."""
+    import gadm_b200 as G
+
+    d, K, m = 20, 6, 40
+    rng = np.random.RandomState(5)
+    sampler = {"datamodel": oagg.datamodel_masks, "shapley": oagg.shapley_masks, "uniform": oagg.uniform_masks,
+               "loo": oagg.datamodel_masks, "add_one_in": oagg.datamodel_masks}[dist]
+    X = sampler(d, list(range(120)))
+    w = rng.normal(size=(d, K))
+    Y = X @ w + 0.2 * rng.normal(size=(120, K))
+    full, null = np.ones(d) @ w, np.zeros(K)
+    tests = []
+    for t in range(3):
+        Xt = oagg.datamodel_masks(d, list(range(900 + m * t, 900 + m * (t + 1))))
+        tests.append((Xt, Xt @ w + 0.5 * rng.normal(size=(m, K))))
+    idx = rng.permutation(120)
+    sizes = [d, 40, 80, 120]
+    got = G.lds_fit_sweep(X, Y, tests, sizes, dist, full_targets=full, null_targets=null, train_indices=idx)
+    for n, g in zip(sizes, got):
+        xf, yf = X[idx[:n]], Y[idx[:n]]
+        if dist == "datamodel":
+            coef = oagg.datamodel_ridge(xf, yf)[0]
+        elif dist == "shapley":
+            coef = np.stack([oagg.data_shapley(d, xf, yf[:, i], full[i], null[i])[:, 0] for i in range(K)], axis=1)
+        elif dist == "uniform":
+            coef = np.stack([oagg.data_banzhaf(xf, yf[:, i]) for i in range(K)], axis=1)
+        elif dist == "loo":
+            coef = np.stack([oagg.loo_attr(X, Y[:, i], full[i]) for i in range(K)], axis=1)
+        else:
+            coef = np.stack([oagg.aoi_attr(X, Y[:, i], null[i]) for i in range(K)], axis=1)
+        np.testing.assert_allclose(g["coef"], coef, rtol=1e-7, atol=1e-9)
+        want_mean, want_ci = oagg.evaluate_lds(coef, tests, K)
+        assert g["n"] == n and abs(g["lds_mean"] - want_mean) < 1e-9 and abs(g["lds_ci"] - want_ci) < 1e-9
+    with pytest.raises(ValueError):
+        G.lds_fit_sweep(X, Y, tests, sizes, "gaussian")
+
+
+def test_convergence_metrics_vs_scipy():
+    from scipy.stats import pearsonr, spearmanr
+
+    import gadm_b200 as G
+
+    rng = np.random.RandomState(1)
+    a = rng.normal(size=258)
+    b = a + 0.3 * rng.normal(size=258)
+    b[10] = b[11]  # a tie
+    m = G.convergence_metrics(a, b)
+    assert abs(m["mse"] - ((a - b) ** 2).mean()) < 1e-15
+    assert abs(m["pearson"] - pearsonr(a, b)[0]) < 1e-12
+    assert abs(m["spearman"] - spearmanr(a, b)[0]) < 1e-12
