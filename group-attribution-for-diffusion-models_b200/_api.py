@@ -10,6 +10,7 @@ from .scoring import (TrakScorer, aggregate_by_class, col_mean_scaled, compute_d
 from .masks import (counterfactual_split, masks_from_seeds, remove_data_by_datamodel, remove_data_by_shapley,  # noqa: F401
                     remove_data_by_uniform)
 from .datamodel import RidgeCV, datamodel_ridge_batched, ridge_cv_batched  # noqa: F401
+from .formats import collect_data, load_lds_test_sets, read_behavior_db, run_traks, save_lds_outputs  # noqa: F401
 from ._lib import GadmError, load_library  # noqa: F401
 
 __all__ = [
@@ -22,5 +23,6 @@ __all__ = [
     "counterfactual_split", "masks_from_seeds", "remove_data_by_datamodel", "remove_data_by_shapley",
     "remove_data_by_uniform",
     "RidgeCV", "datamodel_ridge_batched", "ridge_cv_batched",
+    "collect_data", "load_lds_test_sets", "read_behavior_db", "run_traks", "save_lds_outputs",
     "GadmError", "load_library",
 ]

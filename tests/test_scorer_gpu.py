@@ -210,3 +210,43 @@ def test_transpose_bit_exact(R, C):
     # non-contiguous / odd-pitch input (falls back to scalar loads)
     wide = _rand((R, C + 3), 5)
     assert torch.equal(G.transpose(wide[:, 1:C + 1]), wide[:, 1:C + 1].T)
+
+
+def test_run_traks_reads_and_writes_the_reference_files(tmp_path):
+    """text_to_image/traks.py:main as a file-to-file drop-in: inputs laid out like the reference's gradient
+    directory, outputs compared with the files the reference's own main() wrote (traks_golden.npz)."""
+    import pandas as pd
+
+    import gadm_b200 as G
+
+    g = np.load(os.path.join(GOLDEN, "traks_golden.npz"))
+    k = g["in_train_loss"].shape[1]
+    ngroups = int(g["in_groups"].max()) + 1
+    out_dir = tmp_path / "t2i"
+    gd = out_dir / "gradients"
+    for sub in ("train", "generated", "generated_journey"):
+        (gd / sub).mkdir(parents=True)
+    sfx = f"num_timesteps=100_proj_dim={k}.pt"
+    torch.save(torch.from_numpy(g["in_train_loss"]), gd / "train" / f"emb_f=loss_{sfx}")
+    torch.save(torch.from_numpy(g["in_train_dtrak"]), gd / "train" / f"emb_f=mean-squared-l2-norm_{sfx}")
+    torch.save(torch.from_numpy(g["in_gen_loss"]), gd / "generated" / f"emb_f=loss_{sfx}")
+    torch.save(torch.from_numpy(g["in_gen_dtrak"]), gd / "generated" / f"emb_f=mean-squared-l2-norm_{sfx}")
+    torch.save(torch.from_numpy(g["in_journey"]),
+               gd / "generated_journey" / f"emb_f=loss_num_journey_points=50_num_journey_noises=1_proj_dim={k}.pt")
+    pd.DataFrame({"artist": [f"artist_{a}" for a in g["in_groups"]]}).to_csv(gd / "train" / "group.csv", index=False)
+    ddir = tmp_path / "data" / "artbench-10-imagefolder-split" / "train"
+    ddir.mkdir(parents=True)
+    pd.DataFrame({"artist": [f"artist_{a}" for a in range(ngroups)]}).to_csv(ddir / "post_impressionism_artists.csv", index=False)
+    args = argparse.Namespace(output_dir=str(out_dir), num_timesteps=100, proj_dim=k, dataset="artbench",
+                              cls="post_impressionism", group="artist", lam=5e-1)
+    G.run_traks(args, dataset_dir=str(tmp_path / "data"))
+    written = sorted(os.listdir(out_dir / "baselines"))
+    want_files = sorted(key[4:] + ".npy" for key in g.files if key.startswith("out_"))
+    assert written == want_files
+    for fn in written:
+        got, want = np.load(out_dir / "baselines" / fn), g["out_" + fn[:-4]]
+        assert got.shape == want.shape and got.dtype == want.dtype, fn
+        if "rank" in fn:
+            np.testing.assert_array_equal(got, want)
+        else:
+            assert np.allclose(got, want, rtol=2e-4, atol=2e-6), fn
