@@ -33,6 +33,8 @@ _SIGNATURES = {
     "gadm_transpose": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gadm_cholesky_workspace_bytes": (c_i64, [c_i64]),
     "gadm_cholesky": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),
+    "gadm_tri_inverse_workspace_bytes": (c_i64, [c_i64]),
+    "gadm_tri_inverse": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "gadm_solve_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "gadm_row_norms": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp]),
     "gadm_col_mean_scaled": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),

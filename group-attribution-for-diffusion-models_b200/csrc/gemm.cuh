@@ -208,7 +208,10 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint4 hi, lo;
         split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
         split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-        st_shared_v4(raw + off, hi);
+        // hi is NOT written back: kind::tf32 reads the fp32 bit pattern and ignores the low 13 mantissa bits, so the
+        // raw tile already is the hi operand.  Shared-memory bandwidth is this kernel's bound (a 128x128x8 tf32 UMMA
+        // reads 8 KiB per 64 clocks = 128 B/clk, the whole budget, and the split competes with it): one store less
+        // per element takes the splitter's traffic from 96 to 64 KiB per k-block.
         st_shared_v4(raw + 2 * kTileBytes + off, lo);
       }
       fence_proxy_async_smem();
@@ -265,70 +268,154 @@ transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t
 }
 
 // Cholesky of one nb x nb diagonal block (nb <= 128), in place (lower; strict upper zeroed), plus the
-// inverse of the factor and its transpose (dense nb x nb, pitch 128, identity-padded) for the GEMM-based
-// panel solves.  One CTA of 512 threads, block resident in shared memory; right-looking: per column one
-// scale phase and one rank-1 trailing update spread over all threads (16 x 32 thread grid), then a
-// column-parallel forward substitution for the inverse with 4 lanes sharing each column's dot product.
+// inverse of the factor and its transpose (dense 128 x 128, identity-padded) for the GEMM-based panel solves.
+// One CTA of 512 threads, block resident in shared memory.  The block is processed as 4 x 4 sub-blocks of 32:
+//   * the 32 x 32 diagonal sub-block is factored by ONE warp in registers (lane i owns row i, the column
+//     broadcasts are warp shuffles: no block barrier inside the 32 columns) and inverted by the same warp
+//     (lane j owns column j of the inverse, factor entries are smem broadcasts);
+//   * the sub-blocks below it are multiplied by that inverse and the trailing sub-blocks updated by all 16 warps;
+//   * the 128 x 128 inverse is assembled from the four 32 x 32 inverses by two levels of
+//     X21 = -X22 (L21 X11)  (32 -> 64 -> 128).
+// 4 block barriers per 32 columns instead of 2 per column: 177 us -> ~35 us per block, which was a quarter of the
+// whole TRAK score time at config 2 (32 blocks, strictly serial with the panel / trailing GEMMs).
 constexpr int kPotrfNb = 128;
 constexpr int kPotrfLd = kPotrfNb + 1;
+constexpr int kPotrfSb = 32;
 constexpr int kPotrfThreads = 512;
-constexpr int kPotrfSmem = 2 * kPotrfNb * kPotrfLd * 4;
+constexpr int kPotrfTLd = 65;
+constexpr int kPotrfSmem = (2 * kPotrfNb * kPotrfLd + 64 * kPotrfTLd) * 4;
+
+// C[r, c] (+)= sign * sum_t A[r, t] * B[t, c] (kBT = false) or A[r, t] * B[c, t] (kBT = true) over an R x Cn block with
+// inner length T; all operands are smem sub-matrices with leading dimensions lda / ldb / ldc.  Whole CTA.
+// (r, c) pairs are dealt c-fastest so that a warp reads one A row (broadcast) and 32 B columns / rows.
+template <bool kBT, bool kAccum>
+__device__ __forceinline__ void smem_block_mm(const float* A, int lda, const float* B, int ldb, float* Cm, int ldc, int R,
+                                              int Cn, int T, float sign) {
+  for (int idx = threadIdx.x; idx < R * Cn; idx += kPotrfThreads) {
+    const int r = idx / Cn, c = idx % Cn;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int t = 0; t < T; ++t) acc = fmaf(A[r * lda + t], kBT ? B[c * ldb + t] : B[t * ldb + c], acc);
+    Cm[r * ldc + c] = kAccum ? fmaf(sign, acc, Cm[r * ldc + c]) : sign * acc;
+  }
+}
+
 __global__ void __launch_bounds__(kPotrfThreads, 1)
 potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__ linv, float* __restrict__ linv_t,
                   int* __restrict__ info, int block_index) {
   extern __shared__ float potrf_smem[];
-  float* L = potrf_smem;                       // [nb][kPotrfLd]
+  float* L = potrf_smem;                        // [128][kPotrfLd]: the block, then its factor
   float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse of the factor
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  for (int idx = tid; idx < nb * nb; idx += kPotrfThreads) {
-    const int r = idx / nb, c = idx % nb;
-    L[r * kPotrfLd + c] = A[static_cast<int64_t>(r) * ld + c];
-  }
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    float d = L[j * kPotrfLd + j];
-    if (!(d > 0.f)) {
-      if (tid == 0 && info) atomicMax(info, block_index * kPotrfNb + j + 1);
-      d = 1.f;
-    }
-    const float sd = sqrtf(d);
-    const float inv = 1.f / sd;
-    __syncthreads();  // everyone has read the pivot before it is overwritten
-    if (tid == j) L[j * kPotrfLd + j] = sd;
-    if (tid > j && tid < nb) L[tid * kPotrfLd + j] *= inv;
-    __syncthreads();
-    for (int i = j + 1 + ty; i < nb; i += kPotrfThreads / 32) {
-      const float lij = L[i * kPotrfLd + j];
-      for (int c = j + 1 + tx; c <= i; c += 32) L[i * kPotrfLd + c] = fmaf(-lij, L[c * kPotrfLd + j], L[i * kPotrfLd + c]);
-    }
-    __syncthreads();
-  }
-  // X = L^-1: column c by lanes 4c..4c+3 of the block (same warp), forward substitution down the rows.
-  // Every lane runs the loops (warp-wide shuffles); lanes whose column is out of range only skip the memory ops.
-  {
-    const int c = tid >> 2, part = tid & 3;
-    const bool active = c < nb;
-    const int cc = active ? c : 0;
-    if (active && part == 0)
-      for (int r = 0; r < cc; ++r) X[r * kPotrfLd + cc] = 0.f;
-    for (int r = 0; r < nb; ++r) {
-      float s = 0.f;
-      if (active && r >= cc)
-        for (int t = cc + part; t < r; t += 4) s = fmaf(L[r * kPotrfLd + t], X[t * kPotrfLd + cc], s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (active && part == 0 && r >= cc) X[r * kPotrfLd + cc] = (((r == cc) ? 1.f : 0.f) - s) / L[r * kPotrfLd + r];
-      __syncwarp();
-    }
-  }
-  __syncthreads();
+  float* Tm = X + kPotrfNb * kPotrfLd;          // [64][kPotrfTLd] scratch
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // load; rows / columns >= nb are padded with the identity so that every sub-block step is well defined
   for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) {
     const int r = idx / kPotrfNb, c = idx % kPotrfNb;
-    const bool in = (r < nb && c < nb);
-    if (in) A[static_cast<int64_t>(r) * ld + c] = (c <= r) ? L[r * kPotrfLd + c] : 0.f;
-    const float x = in ? X[r * kPotrfLd + c] : ((r == c) ? 1.f : 0.f);  // identity padding keeps the block invertible
+    L[r * kPotrfLd + c] = (r < nb && c < nb) ? A[static_cast<int64_t>(r) * ld + c] : ((r == c) ? 1.f : 0.f);
+    X[r * kPotrfLd + c] = 0.f;
+  }
+  __syncthreads();
+
+  for (int jb = 0; jb < kPotrfNb / kPotrfSb; ++jb) {
+    const int j0 = jb * kPotrfSb;
+    if (warp == 0) {
+      // ---- factor the 32 x 32 diagonal sub-block in registers: lane i owns row i
+      float r[kPotrfSb];
+#pragma unroll
+      for (int c = 0; c < kPotrfSb; ++c) r[c] = L[(j0 + lane) * kPotrfLd + j0 + c];
+#pragma unroll
+      for (int c = 0; c < kPotrfSb; ++c) {
+        float d = __shfl_sync(0xffffffffu, r[c], c);
+        if (!(d > 0.f)) {
+          if (lane == 0 && info) atomicMax(info, block_index * kPotrfNb + j0 + c + 1);
+          d = 1.f;
+        }
+        const float sd = sqrtf(d);
+        const float lc = (lane == c) ? sd : r[c] / sd;  // column c of the factor, held by lane = row
+        r[c] = lc;
+#pragma unroll
+        for (int t = c + 1; t < kPotrfSb; ++t) {
+          const float ltc = __shfl_sync(0xffffffffu, lc, t);
+          r[t] = fmaf(-lc, ltc, r[t]);  // only rows >= t are meaningful; the others are never read again
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kPotrfSb; ++c) L[(j0 + lane) * kPotrfLd + j0 + c] = (c <= lane) ? r[c] : 0.f;
+      __syncwarp();
+      // ---- invert it: lane j owns column j of the inverse (forward substitution down the rows)
+      float x[kPotrfSb];
+#pragma unroll
+      for (int i = 0; i < kPotrfSb; ++i) {
+        float s = (i == lane) ? 1.f : 0.f;
+#pragma unroll
+        for (int t = 0; t < i; ++t) s = fmaf(-L[(j0 + i) * kPotrfLd + j0 + t], x[t], s);  // x[t] = 0 for t < lane
+        x[i] = (i >= lane) ? s / L[(j0 + i) * kPotrfLd + j0 + i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kPotrfSb; ++i) X[(j0 + i) * kPotrfLd + j0 + lane] = x[i];
+    }
+    __syncthreads();
+    const int rem = kPotrfNb - (j0 + kPotrfSb);  // rows below the diagonal sub-block
+    if (rem > 0) {
+      // ---- panel: P = A[below, j0:j0+32] * D^-T  (computed into scratch, then copied back: in-place rows)
+      // scratch Tm is 64 x 65; the panel has up to 96 rows -> two passes of <= 64 rows
+      for (int p0 = 0; p0 < rem; p0 += 64) {
+        const int pr = (rem - p0) < 64 ? (rem - p0) : 64;
+        smem_block_mm<true, false>(L + (j0 + kPotrfSb + p0) * kPotrfLd + j0, kPotrfLd, X + j0 * kPotrfLd + j0, kPotrfLd, Tm,
+                                   kPotrfTLd, pr, kPotrfSb, kPotrfSb, 1.f);
+        __syncthreads();
+        for (int idx = tid; idx < pr * kPotrfSb; idx += kPotrfThreads) {
+          const int rr = idx / kPotrfSb, c = idx % kPotrfSb;
+          L[(j0 + kPotrfSb + p0 + rr) * kPotrfLd + j0 + c] = Tm[rr * kPotrfTLd + c];
+        }
+        __syncthreads();
+      }
+      // ---- trailing update (lower part incl. diagonal sub-blocks): A22 -= P P^T
+      for (int idx = tid; idx < rem * rem; idx += kPotrfThreads) {
+        const int rr = idx / rem, c = idx % rem;
+        if ((c / kPotrfSb) > (rr / kPotrfSb)) continue;  // sub-blocks above the diagonal are never read
+        const float* pa = L + (j0 + kPotrfSb + rr) * kPotrfLd + j0;
+        const float* pb = L + (j0 + kPotrfSb + c) * kPotrfLd + j0;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int t = 0; t < kPotrfSb; ++t) acc = fmaf(pa[t], pb[t], acc);
+        L[(j0 + kPotrfSb + rr) * kPotrfLd + j0 + kPotrfSb + c] -= acc;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- X = L^-1 from the four 32 x 32 diagonal inverses: X21 = -X22 (L21 X11), level 32 -> 64, then 64 -> 128
+  for (int half = kPotrfSb; half < kPotrfNb; half *= 2) {
+    for (int g0 = 0; g0 < kPotrfNb; g0 += 2 * half) {
+      // groups are independent but share the scratch: serialised (2 groups at the first level, 1 at the second)
+      smem_block_mm<false, false>(L + (g0 + half) * kPotrfLd + g0, kPotrfLd, X + g0 * kPotrfLd + g0, kPotrfLd, Tm, kPotrfTLd,
+                                  half, half, half, 1.f);                                        // T = L21 X11
+      __syncthreads();
+      smem_block_mm<false, false>(X + (g0 + half) * kPotrfLd + g0 + half, kPotrfLd, Tm, kPotrfTLd,
+                                  X + (g0 + half) * kPotrfLd + g0, kPotrfLd, half, half, half, -1.f);  // X21 = -X22 T
+      __syncthreads();
+    }
+  }
+  for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) {
+    const int r = idx / kPotrfNb, c = idx % kPotrfNb;
+    if (r < nb && c < nb) A[static_cast<int64_t>(r) * ld + c] = (c <= r) ? L[r * kPotrfLd + c] : 0.f;
+    const float x = X[r * kPotrfLd + c];  // identity padding (rows >= nb) keeps the block invertible
     linv[r * kPotrfNb + c] = x;
     linv_t[c * kPotrfNb + r] = x;
+  }
+}
+
+// X (lower) and Xt (upper) <- the 128 x 128 diagonal-block inverses that potrf_diag_kernel left in the workspace;
+// everything else of the two k x k matrices is zeroed by the caller.  grid.x = diagonal block.
+__global__ void tri_inverse_init_kernel(const float* __restrict__ linv, const float* __restrict__ linv_t, int64_t k,
+                                        float* __restrict__ X, int64_t ldx, float* __restrict__ Xt, int64_t ldxt) {
+  const int64_t b = blockIdx.x, i0 = b * kPotrfNb;
+  for (int idx = threadIdx.x; idx < kPotrfNb * kPotrfNb; idx += blockDim.x) {
+    const int r = idx / kPotrfNb, c = idx % kPotrfNb;
+    if (i0 + r < k && i0 + c < k) {
+      X[(i0 + r) * ldx + i0 + c] = linv[b * kPotrfNb * kPotrfNb + idx];
+      Xt[(i0 + r) * ldxt + i0 + c] = linv_t[b * kPotrfNb * kPotrfNb + idx];
+    }
   }
 }
 

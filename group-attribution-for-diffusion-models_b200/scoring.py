@@ -147,6 +147,8 @@ class TrakScorer:
         self.k = None          # size of the factored system (k primal, N_total dual)
         self.L = None
         self.U = None
+        self.X = None          # L^-1 (lower) and
+        self.Xt = None         # L^-T (upper), explicit
         self.blocks = None
         self.info = None
         self.dual = False
@@ -189,8 +191,16 @@ class TrakScorer:
         with torch.cuda.device(gram.device):
             _lib.check(h.lib.gadm_cholesky(h.ptr, gram.data_ptr(), gram.stride(0), self.k, self.blocks.data_ptr(), nbytes,
                                           C.cast(self.info.data_ptr(), C.POINTER(C.c_int)), _lib.stream_ptr(gram.device)))
-        self.L = gram
-        self.U = transpose(gram)
+            self.L = gram
+            self.U = None
+            # explicit L^-1 / L^-T by recursive doubling: K^-1 is then applied by two full-size GEMMs
+            ld = -(-self.k // 4) * 4
+            self.X = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
+            self.Xt = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
+            ws = torch.empty(int(h.lib.gadm_tri_inverse_workspace_bytes(self.k)), dtype=torch.uint8, device=gram.device)
+            _lib.check(h.lib.gadm_tri_inverse(h.ptr, gram.data_ptr(), gram.stride(0), self.blocks.data_ptr(), self.k,
+                                              self.X.data_ptr(), self.X.stride(0), self.Xt.data_ptr(), self.Xt.stride(0),
+                                              ws.data_ptr(), ws.numel(), _lib.stream_ptr(gram.device)))
         return self
 
     def check(self) -> None:
@@ -200,14 +210,18 @@ class TrakScorer:
             raise _lib.GadmError(f"Gram matrix is not positive definite (pivot {bad - 1})")
 
     def _solve(self, rows: torch.Tensor, inplace: bool = False) -> torch.Tensor:
-        """rows [m, self.k] -> rows @ (factored matrix)^-1."""
+        """rows [m, self.k] -> rows @ (factored matrix)^-1 = (rows L^-T) L^-1: two GEMMs against the explicit
+        triangular inverse (``inplace`` is accepted for compatibility; a new tensor is returned)."""
         y = _check_cuda_f32(rows, "rows")
         if y.shape[1] != self.k:
             raise ValueError(f"rows have {y.shape[1]} columns, the factored system has {self.k}")
-        if not inplace or y.data_ptr() != rows.data_ptr():
-            y = _clone_padded(y)
-        if y.stride(0) % 4 != 0:
-            raise ValueError("row pitch must be a multiple of 4")
+        return gemm_tn(gemm_tn(y, self.X), self.Xt)
+
+    def solve_rows_blocked(self, rows: torch.Tensor) -> torch.Tensor:
+        """The same through blocked forward / backward substitution (gadm_solve_rows), kept as a cross-check."""
+        y = _clone_padded(_check_cuda_f32(rows, "rows"))
+        if self.U is None:
+            self.U = transpose(self.L)
         h = _h(y)
         with torch.cuda.device(y.device):
             _lib.check(h.lib.gadm_solve_rows(h.ptr, self.L.data_ptr(), self.L.stride(0), self.U.data_ptr(), self.U.stride(0),
@@ -227,8 +241,9 @@ class TrakScorer:
 
     def kernel_inverse(self) -> torch.Tensor:
         """Explicit K^-1 (what the reference caches as kernel_*.npy, compute_gradient_score.py:104-111)."""
-        kdim = self.phi_all.shape[1] if self.dual else self.k
-        eye = torch.eye(kdim, dtype=_f32, device=self.L.device)
+        if not self.dual:
+            return gemm_tn(self.Xt, self.Xt)  # K^-1 = L^-T L^-1
+        eye = torch.eye(self.phi_all.shape[1], dtype=_f32, device=self.L.device)
         return self.solve_rows(eye, inplace=True)
 
     def score_matrix(self, gen_phi: torch.Tensor, train_phi: torch.Tensor) -> torch.Tensor:

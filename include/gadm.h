@@ -113,6 +113,13 @@ int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, i
 int64_t gadm_cholesky_workspace_bytes(int64_t k);
 int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, int64_t blocks_bytes, int* info,
                   void* stream);
+/* x = L^-1 (lower) and xt = L^-T (upper), both [k, k], of the factor left by gadm_cholesky (recursive doubling over
+ * the 128-wide diagonal blocks whose inverses are in `blocks`).  rows @ K^-1 is then two GEMMs:
+ * gadm_gemm_tn(rows, x) = rows L^-T, gadm_gemm_tn(., xt) = (.) L^-1 -- what torch.inverse + matmul do in
+ * traks.py:151-154, without ever forming K^-1. */
+int64_t gadm_tri_inverse_workspace_bytes(int64_t k);
+int gadm_tri_inverse(gadm_handle h, const float* l, int64_t ldl, const void* blocks, int64_t k, float* x, int64_t ldx,
+                     float* xt, int64_t ldxt, void* workspace, int64_t workspace_bytes, void* stream);
 /* y[m, k] <- y * (L L^T)^-1 in place (every row of y is a right-hand side).  l: Cholesky factor from
  * gadm_cholesky, u: its transpose (gadm_transpose), blocks: the same workspace. */
 int gadm_solve_rows(gadm_handle h, const float* l, int64_t ldl, const float* u, int64_t ldu, const void* blocks,

@@ -69,7 +69,7 @@ def test_gram_diagonal_has_no_truncation_drift():
     assert rel < 6e-6, rel  # ~48 truncating accumulations per 128-element chunk + tf32 truncation of the lo parts
 
 
-@pytest.mark.parametrize("k,N", [(128, 400), (300, 1000), (1024, 3000)])
+@pytest.mark.parametrize("k,N", [(128, 400), (300, 1000), (1024, 3000), (1664, 2500), (77, 300)])
 def test_cholesky_and_solve(k, N):
     import gadm_b200 as G
 
@@ -84,8 +84,16 @@ def test_cholesky_and_solve(k, N):
     z = sc.solve_rows(rows)
     want = torch.linalg.solve(Kd, rows.double().T).T
     assert float((z.double() - want).abs().max()) < 5e-5 * float(want.abs().max())
+    zb = sc.solve_rows_blocked(rows)  # blocked substitution (gadm_solve_rows) agrees with the explicit triangular inverse
+    assert float((zb.double() - want).abs().max()) < 5e-5 * float(want.abs().max())
+    Ld = torch.tril(sc.L.double())
+    eye = torch.eye(k, device=DEV, dtype=torch.float64)
+    assert float((sc.X.double() @ Ld - eye).abs().max()) < 2e-5
+    # X^T and Xt come from GEMMs with the operand roles swapped: equal up to fp32 accumulation order
+    assert float((sc.X.T - sc.Xt).abs().max()) < 1e-5 * float(sc.X.abs().max())
+    assert float(torch.triu(sc.X, 1).abs().max()) == 0.0
     kinv = sc.kernel_inverse()
-    assert float((kinv.double() @ Kd - torch.eye(k, device=DEV, dtype=torch.float64)).abs().max()) < 1e-3
+    assert float((kinv.double() @ Kd - eye).abs().max()) < 1e-3
 
 
 def test_trak_scores_vs_fp64_oracle_and_reference_error():
