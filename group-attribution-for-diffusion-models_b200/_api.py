@@ -9,7 +9,8 @@ from .scoring import (TrakScorer, aggregate_by_class, col_mean_scaled, compute_d
                       transpose)
 from .masks import (counterfactual_split, masks_from_seeds, remove_data_by_datamodel, remove_data_by_shapley,  # noqa: F401
                     remove_data_by_uniform)
-from .datamodel import RidgeCV, datamodel_ridge_batched, ridge_cv_batched  # noqa: F401
+from .datamodel import (RidgeCV, compute_datamodel_scores, datamodel, datamodel_ridge_batched,  # noqa: F401
+                        ridge_cv_batched)
 from .formats import collect_data, load_lds_test_sets, read_behavior_db, run_traks, save_lds_outputs  # noqa: F401
 from ._lib import GadmError, load_library  # noqa: F401
 
@@ -22,7 +23,7 @@ __all__ = [
     "gemm_tn", "gradient_scores", "group_and_rank", "row_norms", "trak_scores", "transpose",
     "counterfactual_split", "masks_from_seeds", "remove_data_by_datamodel", "remove_data_by_shapley",
     "remove_data_by_uniform",
-    "RidgeCV", "datamodel_ridge_batched", "ridge_cv_batched",
+    "RidgeCV", "datamodel_ridge_batched", "ridge_cv_batched", "datamodel", "compute_datamodel_scores",
     "collect_data", "load_lds_test_sets", "read_behavior_db", "run_traks", "save_lds_outputs",
     "GadmError", "load_library",
 ]

@@ -59,6 +59,7 @@ __global__ void mask_gram_kernel(const uint32_t* __restrict__ colbits, int64_t d
     cj += __popc(b);
   }
   if (mode == 0) A[tid] = static_cast<double>(n11) / static_cast<double>(n);
+  else if (mode == 2) A[tid] = static_cast<double>(n11);  // raw co-occurrence count (X X^T when given the row bit planes)
   else A[tid] = static_cast<double>(n11) - 0.5 * static_cast<double>(ci + cj) + 0.25 * static_cast<double>(n);
 }
 
@@ -70,6 +71,31 @@ __global__ void mask_gram_kernel(const uint32_t* __restrict__ colbits, int64_t d
 // row segments; the mask word is a warp-wide broadcast).  Rows are visited in order: deterministic sums.
 constexpr int kXtyCols = 64;
 constexpr int kXtyWords = 4;
+
+// acc[t] += y for every set bit t < kBits of `bits`.  ptxas compiles the conditional add to R2P (7 predicates per
+// instruction) + an unconditional DADD + two FSELs per player -- also when it is written as a predicated
+// add.rn.f64 in PTX -- so a player costs ~3 issue slots next to the half-rate fp64 add: the kernel is fp64-issue
+// bound (ncu: fp64 pipe 28.6 %, issue 59 %), not HBM bound.
+template <int kBits>
+__device__ __forceinline__ void masked_accumulate(double (&acc)[32], uint32_t bits, double y) {
+#pragma unroll
+  for (int t = 0; t < kBits; ++t)
+    if ((bits >> t) & 1u) acc[t] += y;
+}
+
+template <int kBits>
+__device__ __forceinline__ void mask_xty_rows(const uint32_t* __restrict__ rowbits, int64_t wd, int64_t word,
+                                              const double* __restrict__ Y, int64_t n, int64_t K, int64_t k, double sh,
+                                              double (&acc)[32], double& tot) {
+#pragma unroll 2
+  for (int64_t r = 0; r < n; ++r) {
+    const double y = Y[r * K + k] - sh;
+    const uint32_t bits = rowbits[r * wd + word];
+    tot += y;
+    masked_accumulate<kBits>(acc, bits, y);
+  }
+}
+
 __global__ void __launch_bounds__(kXtyCols * kXtyWords)
 mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ Y, int64_t n, int64_t d,
                 int64_t K, const double* __restrict__ shift, double half, double scale, double* __restrict__ out) {
@@ -81,15 +107,12 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
 #pragma unroll
   for (int t = 0; t < 32; ++t) acc[t] = 0.0;
   double tot = 0.0;
-#pragma unroll 2
-  for (int64_t r = 0; r < n; ++r) {
-    const double y = Y[r * K + k] - sh;
-    const uint32_t bits = rowbits[r * wd + word];
-    tot += y;
-#pragma unroll
-    for (int t = 0; t < 32; ++t)
-      if ((bits >> t) & 1u) acc[t] += y;
-  }
+  // players of this word that exist (the last word of d = 100 holds 4): only those are accumulated, rounded up to 8
+  const int valid = static_cast<int>((d - word * 32) < 32 ? (d - word * 32) : 32);
+  if (valid > 24) mask_xty_rows<32>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
+  else if (valid > 16) mask_xty_rows<24>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
+  else if (valid > 8) mask_xty_rows<16>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
+  else mask_xty_rows<8>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
 #pragma unroll
   for (int t = 0; t < 32; ++t) {
     const int64_t i = word * 32 + t;

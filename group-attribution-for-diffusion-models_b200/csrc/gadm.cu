@@ -21,6 +21,7 @@
 
 #include "aggregate.cuh"
 #include "ridge.cuh"
+#include "datamodel.cuh"
 #include "gemm.cuh"
 
 struct gadm_ctx {
@@ -672,7 +673,7 @@ int gadm_pack_masks(gadm_handle h, const uint8_t* x, int64_t n, int64_t d, uint3
 }
 
 int gadm_mask_gram(gadm_handle h, const uint32_t* colbits, int64_t n, int64_t d, int mode, double* a, void* stream) {
-  GADM_REQUIRE(h && colbits && a && n > 0 && d > 0 && (mode == 0 || mode == 1), "bad argument");
+  GADM_REQUIRE(h && colbits && a && n > 0 && d > 0 && mode >= 0 && mode <= 2, "bad argument");
   DeviceGuard guard(h->device);
   gadm::agg::mask_gram_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, as_stream(stream)>>>(colbits, d, (n + 31) / 32,
                                                                                             n, mode, a);
@@ -829,6 +830,30 @@ int gadm_ridge_intercept(gadm_handle h, const double* coef, const double* xmean,
   DeviceGuard guard(h->device);
   gadm::ridge::ridge_intercept_kernel<<<(unsigned)((k + 127) / 128), 128, 0, as_stream(stream)>>>(coef, xmean, ymean, d,
                                                                                                   k, intercept);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+// ------------------------------------------------------------------ bootstrapped datamodel (datamodel.py:8-37)
+static_assert(sizeof(gadm_ridge_system) == sizeof(gadm::dm::System), "ABI struct and kernel struct must agree");
+
+int64_t gadm_datamodel_slot_bytes(int64_t n) { return (n * n + 4 * n) * (int64_t)sizeof(double); }
+
+int gadm_datamodel_ridge_systems(gadm_handle h, const double* g0, const double* y, const int32_t* idx, int64_t n,
+                                 const gadm_ridge_system* systems, int64_t n_systems, void* workspace,
+                                 int64_t workspace_bytes, double* scores, double* wdual, void* stream) {
+  GADM_REQUIRE(h && g0 && y && idx && systems && workspace && scores && wdual && n > 1 && n_systems > 0, "bad argument");
+  GADM_REQUIRE(n <= 16384, "n = %lld: one CTA factors an n x n fp64 system in place", (long long)n);
+  const int64_t slots = workspace_bytes / gadm_datamodel_slot_bytes(n);
+  if (slots < 1)
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < one slot of %lld B", (long long)workspace_bytes,
+                (long long)gadm_datamodel_slot_bytes(n));
+  DeviceGuard guard(h->device);
+  int64_t ctas = n_systems < slots ? n_systems : slots;
+  if (ctas > 2 * h->num_sms) ctas = 2 * h->num_sms;
+  gadm::dm::ridge_fold_kernel<<<(unsigned)ctas, gadm::dm::kThreads, 0, as_stream(stream)>>>(
+      g0, y, idx, (int)n, reinterpret_cast<const gadm::dm::System*>(systems), (int)n_systems,
+      reinterpret_cast<double*>(workspace), scores, wdual);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

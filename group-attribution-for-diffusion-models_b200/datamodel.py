@@ -142,3 +142,111 @@ class RidgeCV:
     def predict(self, X):
         X = np.asarray(X, dtype=np.float64)
         return X @ (self.coef_ if self.coef_.ndim == 1 else self.coef_.T) + self.intercept_
+
+
+# ---------------------------------------------------------------- bootstrapped datamodel (datamodel.py:8-37)
+
+_SYSTEM_DTYPE = np.dtype([("run", np.int32), ("f0", np.int32), ("f1", np.int32), ("out", np.int32), ("alpha", np.float64)])
+
+
+def _kfold_bounds(n: int, n_splits: int = 5):
+    """sklearn KFold(n_splits, shuffle=False): the first n % n_splits folds have one extra sample."""
+    sizes = np.full(n_splits, n // n_splits, dtype=np.int64)
+    sizes[: n % n_splits] += 1
+    ends = np.cumsum(sizes)
+    return list(zip((ends - sizes).tolist(), ends.tolist()))
+
+
+def datamodel(x_train, y_train, num_runs: int, alphas=(0.1, 1.0, 1e1), cv: int = 5, bootstrap_indices=None, device=None,
+              return_details: bool = False):
+    """Reference signature (src/attributions/methods/datamodel.py:8-37): ``num_runs`` bootstrap resamples, each fitted
+    with ``RidgeCV(cv=5, alphas=[0.1, 1.0, 10.0])``; returns the stacked coefficients ``[num_runs, d]``.
+
+    The resamples are drawn exactly like the reference, ``np.random.choice(n, n, replace=True)`` from numpy's *global*
+    state (seed it the same way to reproduce a run), unless ``bootstrap_indices`` [num_runs, n] is given.  x_train
+    must be 0/1 masks (they are ``remaining_idx`` indicators, datamodel.py:71); all ridge systems of all resamples are
+    solved in one kernel launch per stage (csrc/datamodel.cuh)."""
+    from .aggregation import PackedMasks
+
+    dev = _device(device)
+    h = _lib.get_handle(dev)
+    masks = x_train if isinstance(x_train, PackedMasks) else PackedMasks(x_train, dev)
+    n, d = masks.n, masks.d
+    y = _dev_f64(np.asarray(y_train, dtype=np.float64).reshape(-1), dev)
+    if y.shape[0] != n:
+        raise ValueError(f"Found input variables with inconsistent numbers of samples: [{n}, {y.shape[0]}]")
+    if n < cv:
+        raise ValueError(f"Cannot have number of splits n_splits={cv} greater than the number of samples: n_samples={n}.")
+    if bootstrap_indices is None:
+        idx = np.stack([np.random.choice(n, n, replace=True) for _ in range(num_runs)])  # datamodel.py:27
+    else:
+        idx = np.asarray(bootstrap_indices).reshape(num_runs, n)
+    idx_t = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32)).to(dev)
+    al = [float(a) for a in alphas]
+    folds = _kfold_bounds(n, cv)
+    st = _lib.stream_ptr(dev)
+    with torch.cuda.device(dev):
+        g0 = torch.empty(n, n, dtype=_f64, device=dev)  # X X^T: the row bit planes play the role of column planes
+        _lib.check(h.lib.gadm_mask_gram(h.ptr, masks.rowbits.data_ptr(), d, n, 2, g0.data_ptr(), st))
+        slot = int(h.lib.gadm_datamodel_slot_bytes(n))
+        free, _ = torch.cuda.mem_get_info(dev)
+        n_fold_sys = num_runs * len(al) * cv
+        slots = max(1, min(n_fold_sys, 2 * torch.cuda.get_device_properties(dev).multi_processor_count,
+                           int(0.5 * free) // slot))
+        ws = torch.empty(slots * slot, dtype=torch.uint8, device=dev)
+        # stage 1: every (resample, alpha, fold) system -> held-out R^2
+        sysv = np.zeros(n_fold_sys, dtype=_SYSTEM_DTYPE)
+        e = 0
+        for b in range(num_runs):
+            for ai, a in enumerate(al):
+                for fi, (f0, f1) in enumerate(folds):
+                    sysv[e] = (b, f0, f1, (b * len(al) + ai) * cv + fi, a)
+                    e += 1
+        scores = torch.empty(n_fold_sys, dtype=_f64, device=dev)
+        wdual = torch.zeros(num_runs, n, dtype=_f64, device=dev)
+        sys_t = torch.as_tensor(sysv.view(np.uint8)).to(dev)
+        _lib.check(h.lib.gadm_datamodel_ridge_systems(h.ptr, g0.data_ptr(), y.data_ptr(), idx_t.data_ptr(), n, sys_t.data_ptr(),
+                                                      n_fold_sys, ws.data_ptr(), ws.numel(), scores.data_ptr(),
+                                                      wdual.data_ptr(), st))
+        # GridSearchCV: mean test score over the folds, first best alpha (rank 'min' + argmin)
+        mean_scores = scores.cpu().numpy().reshape(num_runs, len(al), cv).mean(axis=2)
+        best = np.argmax(mean_scores, axis=1)
+        # stage 2: refit every resample on all of its rows with its alpha
+        sys2 = np.zeros(num_runs, dtype=_SYSTEM_DTYPE)
+        for b in range(num_runs):
+            sys2[b] = (b, 0, 0, b, al[best[b]])
+        sys2_t = torch.as_tensor(sys2.view(np.uint8)).to(dev)
+        _lib.check(h.lib.gadm_datamodel_ridge_systems(h.ptr, g0.data_ptr(), y.data_ptr(), idx_t.data_ptr(), n, sys2_t.data_ptr(),
+                                                      num_runs, ws.data_ptr(), ws.numel(), scores.data_ptr(),
+                                                      wdual.data_ptr(), st))
+        coef = masks.xty(wdual.T.contiguous(), None, 0.0, 1.0)  # X^T w  -> [d, num_runs]
+    coeff = coef.T.contiguous().cpu().numpy()
+    if return_details:
+        return coeff, {"alpha": np.asarray(al)[best], "mean_test_score": mean_scores, "bootstrap_indices": idx}
+    return coeff
+
+
+def compute_datamodel_scores(args, model_behavior_all, train_idx, val_idx, total_data_num: int | None = None, device=None):
+    """Reference signature (datamodel.py:40-80): masks / behaviours from the jsonl records, bootstrapped datamodel on
+    ``train_idx``, predictions ``X[val_idx] @ coeff.T`` -> [len(val_idx), num_runs].  ``total_data_num`` replaces
+    ``len(create_dataset(args.dataset, train=True))`` (dataset I/O is out of scope)."""
+    from .aggregation import PackedMasks
+
+    if total_data_num is None:
+        from src.datasets import create_dataset  # the reference's module
+
+        total_data_num = len(create_dataset(dataset_name=args.dataset, train=True))
+    train_val_index = list(train_idx) + list(val_idx)
+    X = np.zeros((len(train_val_index), total_data_num), dtype=np.uint8)
+    Y = np.zeros(len(train_val_index))
+    for i in train_val_index:
+        remaining_idx = model_behavior_all[i].get("remaining_idx", [])
+        removed_idx = model_behavior_all[i].get("removed_idx", [])
+        if total_data_num != len(remaining_idx) + len(removed_idx):
+            print(f"AssertionError for index {i}: Total data number mismatch.")  # datamodel.py:62-76 (row stays zero)
+            continue
+        X[i, remaining_idx] = 1
+        Y[i] = model_behavior_all[i].get(args.model_behavior)
+    coeff = datamodel(X[list(train_idx)], Y[list(train_idx)], args.num_runs, device=device)  # [runs, d]
+    val = PackedMasks(X[list(val_idx)], device)
+    return val.times(_dev_f64(coeff.T, val.device)).cpu().numpy()

@@ -145,7 +145,8 @@ enum { GADM_DTYPE_F64 = 3 };
 int gadm_pack_masks(gadm_handle h, const uint8_t* x, int64_t n, int64_t d, uint32_t* rowbits, uint32_t* colbits,
                     void* stream);
 /* A [d, d] fp64: mode SHAPLEY  A = X^T X / n (datashapley.py:29);
- *                mode BANZHAF  A = (X - 1/2)^T (X - 1/2) (databanzhaf.py:19-22) -- exact from popcounts */
+ *                mode BANZHAF  A = (X - 1/2)^T (X - 1/2) (databanzhaf.py:19-22) -- exact from popcounts;
+ *                mode 2        raw co-occurrence counts (pass the row bit planes with n and d swapped for X X^T) */
 int gadm_mask_gram(gadm_handle h, const uint32_t* colbits, int64_t n, int64_t d, int mode, double* a, void* stream);
 /* out[i, k] = (sum_r X[r,i] * (Y[r,k] - shift[k]) - half * sum_r (Y[r,k] - shift[k])) * scale ; Y [n, K], out [d, K]
  * Shapley b_hat: shift = v0, half = 0, scale = 1/n ; Banzhaf rhs: shift = NULL, half = 0.5, scale = 1 */
@@ -191,6 +192,21 @@ int gadm_ridge_select(gadm_handle h, const double* score, int64_t n_alphas, int6
 /* intercept[k] = ymean[k] - xmean . coef[:, k] */
 int gadm_ridge_intercept(gadm_handle h, const double* coef, const double* xmean, const double* ymean, int64_t d,
                          int64_t k, double* intercept, void* stream);
+/* ---- bootstrapped datamodel: replaces `RidgeCV(cv=5, alphas=[0.1, 1.0, 10.0]).fit(x[idx], y[idx])` per resample
+ * (src/attributions/methods/datamodel.py:8-37; sklearn GridSearchCV over Ridge(fit_intercept=True), KFold(5), R^2).
+ * Every ridge fit runs in Gram space on g0 = X X^T of the original rows (gadm_mask_gram mode 2 on the row bit planes):
+ * one CTA per system = (resample, held-out positions [f0, f1) or f0 == f1 for the refit, alpha).  Fold systems write
+ * the held-out R^2 to scores[out]; refit systems write the centred dual weights w to wdual[out, :] so that
+ * coef = X^T w (gadm_mask_xty).  idx: int32 [runs, n] resample indices.  workspace: any number of slots of
+ * gadm_datamodel_slot_bytes(n); systems beyond the slot count are processed in turn. */
+typedef struct gadm_ridge_system {
+  int32_t run, f0, f1, out;
+  double alpha;
+} gadm_ridge_system;
+int64_t gadm_datamodel_slot_bytes(int64_t n);
+int gadm_datamodel_ridge_systems(gadm_handle h, const double* g0, const double* y, const int32_t* idx, int64_t n,
+                                 const gadm_ridge_system* systems, int64_t n_systems, void* workspace,
+                                 int64_t workspace_bytes, double* scores, double* wdual, void* stream);
 /* Efficiency-constraint step of closed-form KernelSHAP (datashapley.py:38-43):
  * rhs[:, k] = b[:, k] - (1^T Ainv b[:, k] - v1[k] + v0[k]) / (1^T Ainv 1) ; colsum_work: d + 1 doubles */
 int gadm_shapley_rhs(gadm_handle h, const double* ainv, const double* b, int64_t d, int64_t k, const double* v1,

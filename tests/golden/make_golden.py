@@ -290,10 +290,37 @@ def make_ridge():
     print("ridge_golden.npz", {k: v.shape for k, v in res.items()})
 
 
+def make_datamodel():
+    """src/attributions/methods/datamodel.py:8-37 executed through the reference's own function (bootstrapped
+    RidgeCV(cv=5)); the module's `from src.datasets import create_dataset` is satisfied by the injected environment."""
+    dm = _load("src/attributions/methods/datamodel.py", "ref_datamodel")
+    from oracle.aggregation import datamodel_masks
+
+    res = {}
+    for tag, n, d, runs, noise, seed in (("wide", 60, 200, 4, 0.3, 11), ("tall", 150, 40, 3, 1.0, 12), ("odd", 23, 64, 2, 0.1, 13)):
+        rng = np.random.RandomState(seed)
+        X = datamodel_masks(d, list(range(3000, 3000 + n)), alpha=0.5)
+        Y = X @ rng.normal(size=d) + noise * rng.normal(size=n)
+        np.random.seed(seed)
+        coeff = dm.datamodel(X, Y, runs)
+        res[f"{tag}_X"] = X.astype(np.uint8)
+        res[f"{tag}_Y"] = Y
+        res[f"{tag}_seed"] = np.array(seed)
+        res[f"{tag}_coeff"] = coeff
+    np.savez_compressed(os.path.join(HERE, "datamodel_golden.npz"), **res)
+    print("datamodel_golden.npz", {k: v.shape for k, v in res.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "ridge":  # regenerate only the sklearn-based fixture
-        sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))  # repo root (oracle/)
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "ridge":  # regenerate only the sklearn-based fixture
         make_ridge()
+        sys.exit(0)
+    if only == "datamodel":
+        with tempfile.TemporaryDirectory() as tmp:
+            _inject_env(tmp)
+            make_datamodel()
         sys.exit(0)
     with tempfile.TemporaryDirectory() as tmp:
         consts = _inject_env(tmp)
@@ -301,4 +328,5 @@ if __name__ == "__main__":
         make_traks(tmp, consts)
         make_gradient_scores(tmp, consts)
         make_lds_py(tmp)
+        make_datamodel()
     make_ridge()

@@ -91,3 +91,49 @@ def test_general_real_features_and_errors():
         G.ridge_cv_batched(X, y, device="cpu")
     with pytest.raises(NotImplementedError):
         G.RidgeCV(cv=5)
+
+
+@pytest.mark.parametrize("tag", ["wide", "tall", "odd"])
+def test_bootstrapped_datamodel_golden(tag):
+    """datamodel.py:8-37 through csrc/datamodel.cuh against the coefficients the reference's function produced
+    (same global numpy seed => same resamples; same alpha per resample; coefficients to 1e-7)."""
+    import gadm_b200 as G
+
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "datamodel_golden.npz"))
+    X, Y = g[f"{tag}_X"], g[f"{tag}_Y"]
+    want = g[f"{tag}_coeff"]
+    np.random.seed(int(g[f"{tag}_seed"]))
+    got, det = G.datamodel(X, Y, want.shape[0], return_details=True)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9)
+    # the grid-search scores themselves, against sklearn on the same resamples
+    from sklearn.linear_model import Ridge
+    from sklearn.model_selection import GridSearchCV
+
+    for b in range(want.shape[0]):
+        idx = det["bootstrap_indices"][b]
+        gs = GridSearchCV(Ridge(), {"alpha": [0.1, 1.0, 10.0]}, cv=5).fit(X[idx].astype(np.float64), Y[idx])
+        np.testing.assert_allclose(det["mean_test_score"][b], gs.cv_results_["mean_test_score"], rtol=1e-8, atol=1e-10)
+        assert det["alpha"][b] == gs.best_params_["alpha"]
+
+
+def test_compute_datamodel_scores_shape_and_values():
+    import argparse
+
+    import gadm_b200 as G
+
+    d, n = 50, 40
+    rng = np.random.RandomState(2)
+    X = oagg.datamodel_masks(d, list(range(n)), alpha=0.5)
+    w = rng.normal(size=d)
+    recs = [{"remaining_idx": np.where(X[i] == 1)[0].tolist(), "removed_idx": np.where(X[i] == 0)[0].tolist(),
+             "fid": float(X[i] @ w + 0.1 * rng.normal())} for i in range(n)]
+    args = argparse.Namespace(dataset="cifar", model_behavior="fid", num_runs=3)
+    train_idx, val_idx = list(range(30)), list(range(30, 40))
+    np.random.seed(5)
+    got = G.compute_datamodel_scores(args, recs, train_idx, val_idx, total_data_num=d)
+    np.random.seed(5)
+    Y = np.array([r["fid"] for r in recs])
+    want = X[val_idx] @ oagg.datamodel(X[train_idx], Y[train_idx], 3).T
+    assert got.shape == (10, 3)
+    np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9)
