@@ -30,6 +30,8 @@ struct gadm_ctx {
   int64_t launches = 0;
   uint32_t* scratch = nullptr;  // small device scratch owned by the handle (lockstep counter)
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
+  cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start / panel / rest / end
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
 
@@ -317,6 +319,8 @@ int gadm_create(gadm_handle* out, int device) {
 
 int gadm_destroy(gadm_handle h) {
   if (h && h->scratch) cudaFree(h->scratch);
+  if (h && h->hp_stream) cudaStreamDestroy(h->hp_stream);
+  if (h) for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return GADM_OK;
 }
@@ -527,21 +531,64 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
     attr_set = true;
   }
   if (info) GADM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), as_stream(stream)));
+  // Look-ahead: the critical path (diagonal block -> panel -> update of the NEXT block column) runs on a
+  // high-priority stream of the handle, the rest of the trailing update on the caller's stream, so that
+  // potrf(b+1) + panel(b+1) overlap with the bulk of the trailing update of step b.  Ordering rules:
+  //   rest(b)  after panel(b)                 (reads the panel)            -- event ev_panel
+  //   next(b)  after rest(b-1)                (both update block column b+1) -- event ev_rest
+  // Events are re-recorded every step: cudaStreamWaitEvent captures the record that is current when it is called.
+  static const bool lookahead = [] { const char* e = getenv("GADM_CHOL_LOOKAHEAD"); return !(e && atoi(e) == 0); }();
+  cudaStream_t user = as_stream(stream);
+  cudaStream_t crit = user;
+  if (lookahead && nblk > 2) {
+    if (!h->hp_stream) {
+      int least = 0, greatest = 0;
+      GADM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      GADM_CUDA(cudaStreamCreateWithPriority(&h->hp_stream, cudaStreamNonBlocking, greatest));
+      for (auto& e : h->ev) GADM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    crit = h->hp_stream;
+    GADM_CUDA(cudaEventRecord(h->ev[0], user));
+    GADM_CUDA(cudaStreamWaitEvent(crit, h->ev[0], 0));
+  }
+  const bool split = crit != user;
+  bool rest_pending = false;
   for (int64_t b = 0; b < nblk; ++b) {
     const int64_t j0 = b * NB;
     const int nb = (int)((k - j0) < NB ? (k - j0) : NB);
-    potrf<<<1, gadm::gemm::kPotrfThreads, gadm::gemm::kPotrfSmem, as_stream(stream)>>>(a + j0 * ld + j0, ld, nb, linv + b * NB * NB,
-                                                               linv_t + b * NB * NB, info, (int)b);
+    potrf<<<1, gadm::gemm::kPotrfThreads, gadm::gemm::kPotrfSmem, crit>>>(a + j0 * ld + j0, ld, nb, linv + b * NB * NB,
+                                                                         linv_t + b * NB * NB, info, (int)b);
     GADM_LAUNCHED(h);
     const int64_t rem = k - (j0 + nb);
     if (rem > 0) {
       float* panel = a + (j0 + nb) * ld + j0;
       // panel <- panel * L_jj^-T   (in place: one column tile, each CTA owns its rows)
-      GADM_TRY(gadm_gemm_tn(h, panel, ld, linv + b * NB * NB, NB, panel, ld, rem, nb, nb, 1.f, 0.f, 0.f, 0, stream));
-      // trailing update (lower tiles only): A22 -= panel * panel^T
+      GADM_TRY(gadm_gemm_tn(h, panel, ld, linv + b * NB * NB, NB, panel, ld, rem, nb, nb, 1.f, 0.f, 0.f, 0, crit));
       float* trail = a + (j0 + nb) * ld + (j0 + nb);
-      GADM_TRY(gadm_gemm_tn(h, panel, ld, panel, ld, trail, ld, rem, rem, nb, -1.f, 1.f, 0.f, 1, stream));
+      if (!split) {
+        // trailing update (lower tiles only): A22 -= panel * panel^T
+        GADM_TRY(gadm_gemm_tn(h, panel, ld, panel, ld, trail, ld, rem, rem, nb, -1.f, 1.f, 0.f, 1, user));
+        continue;
+      }
+      GADM_CUDA(cudaEventRecord(h->ev[1], crit));  // panel(b) done
+      const int64_t nn = rem < NB ? rem : NB;       // width of the next block column
+      if (rest_pending) GADM_CUDA(cudaStreamWaitEvent(crit, h->ev[2], 0));  // rest(b-1) also wrote block column b+1
+      // next(b): block column b+1 (all remaining rows) -= panel * panel[0:nn]^T
+      GADM_TRY(gadm_gemm_tn(h, panel, ld, panel, ld, trail, ld, rem, nn, nb, -1.f, 1.f, 0.f, 0, crit));
+      rest_pending = false;
+      if (rem > nn) {
+        // rest(b): the lower triangle right of that column, on the caller's stream
+        GADM_CUDA(cudaStreamWaitEvent(user, h->ev[1], 0));
+        float* p2 = panel + nn * ld;
+        GADM_TRY(gadm_gemm_tn(h, p2, ld, p2, ld, trail + nn * ld + nn, ld, rem - nn, rem - nn, nb, -1.f, 1.f, 0.f, 1, user));
+        GADM_CUDA(cudaEventRecord(h->ev[2], user));
+        rest_pending = true;
+      }
     }
+  }
+  if (split) {  // join: everything after this call on the caller's stream sees the finished factor
+    GADM_CUDA(cudaEventRecord(h->ev[3], crit));
+    GADM_CUDA(cudaStreamWaitEvent(user, h->ev[3], 0));
   }
   return GADM_OK;
 }

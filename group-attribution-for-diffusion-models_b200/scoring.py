@@ -181,8 +181,34 @@ class TrakScorer:
         allreduce_sum_(gram, self.group)  # one NCCL all-reduce over NVLink (sum of per-rank Grams)
         return self.factor_(gram)
 
+    def partial_fit(self, phi_rows: torch.Tensor) -> "TrakScorer":
+        """Streaming form of ``fit`` for the featurisation loop: accumulate Phi^T Phi batch by batch (e.g. every 1024
+        rows that ``CudaProjector.deferred()`` produces) so that the Gram GEMM hides behind the gradient computation.
+        Call ``finalize()`` once all of this rank's rows have been seen (primal k x k form only)."""
+        phi = _check_cuda_f32(phi_rows, "phi_rows")
+        phi_t = transpose(phi)
+        if getattr(self, "_gram_acc", None) is None:
+            self._gram_acc = gemm_tn(phi_t, phi_t, lower_only=True)
+        else:
+            gemm_tn(phi_t, phi_t, out=self._gram_acc, beta=1.0, lower_only=True)
+        return self
+
+    def finalize(self) -> "TrakScorer":
+        """All-reduce the accumulated Gram, add lam*I and factor (the tail of ``fit``)."""
+        if getattr(self, "_gram_acc", None) is None:
+            raise RuntimeError("finalize() before any partial_fit()")
+        gram, self._gram_acc = self._gram_acc, None
+        allreduce_sum_(gram, self.group)
+        gram.diagonal().add_(self.lam)
+        self.dual = False
+        return self.factor_(gram)
+
     def factor_(self, gram: torch.Tensor) -> "TrakScorer":
-        """In-place Cholesky of an already regularised symmetric matrix (lower triangle is read)."""
+        """In-place Cholesky of an already regularised symmetric matrix (lower triangle is read), then the explicit
+        triangular inverse."""
+        return self._cholesky_(gram)._tri_inverse_()
+
+    def _cholesky_(self, gram: torch.Tensor) -> "TrakScorer":
         self.k = gram.shape[0]
         h = _h(gram)
         nbytes = int(h.lib.gadm_cholesky_workspace_bytes(self.k))
@@ -191,13 +217,19 @@ class TrakScorer:
         with torch.cuda.device(gram.device):
             _lib.check(h.lib.gadm_cholesky(h.ptr, gram.data_ptr(), gram.stride(0), self.k, self.blocks.data_ptr(), nbytes,
                                           C.cast(self.info.data_ptr(), C.POINTER(C.c_int)), _lib.stream_ptr(gram.device)))
-            self.L = gram
-            self.U = None
-            # explicit L^-1 / L^-T by recursive doubling: K^-1 is then applied by two full-size GEMMs
-            ld = -(-self.k // 4) * 4
-            self.X = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
-            self.Xt = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
-            ws = torch.empty(int(h.lib.gadm_tri_inverse_workspace_bytes(self.k)), dtype=torch.uint8, device=gram.device)
+        self.L = gram
+        self.U = None
+        return self
+
+    def _tri_inverse_(self) -> "TrakScorer":
+        """Explicit L^-1 / L^-T by recursive doubling: K^-1 is then applied by two full-size GEMMs."""
+        gram = self.L
+        h = _h(gram)
+        ld = -(-self.k // 4) * 4
+        self.X = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
+        self.Xt = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
+        ws = torch.empty(int(h.lib.gadm_tri_inverse_workspace_bytes(self.k)), dtype=torch.uint8, device=gram.device)
+        with torch.cuda.device(gram.device):
             _lib.check(h.lib.gadm_tri_inverse(h.ptr, gram.data_ptr(), gram.stride(0), self.blocks.data_ptr(), self.k,
                                               self.X.data_ptr(), self.X.stride(0), self.Xt.data_ptr(), self.Xt.stride(0),
                                               ws.data_ptr(), ws.numel(), _lib.stream_ptr(gram.device)))

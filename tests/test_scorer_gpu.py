@@ -258,3 +258,19 @@ def test_run_traks_reads_and_writes_the_reference_files(tmp_path):
             np.testing.assert_array_equal(got, want)
         else:
             assert np.allclose(got, want, rtol=2e-4, atol=2e-6), fn
+
+
+def test_partial_fit_streams_the_gram():
+    import gadm_b200 as G
+
+    N, k, T = 2500, 512, 16
+    train, gen = _rand((N, k), 31), _rand((T, k), 32)
+    whole = G.TrakScorer(0.5).fit(train, dual=False)
+    stream = G.TrakScorer(0.5)
+    for lo in range(0, N, 1024):
+        stream.partial_fit(train[lo:lo + 1024])
+    stream.finalize()
+    a, b = whole.score_matrix(gen, train), stream.score_matrix(gen, train)
+    assert float((a - b).abs().max()) < 2e-5 * float(a.abs().max())
+    with pytest.raises(RuntimeError):
+        G.TrakScorer(0.5).finalize()

@@ -45,7 +45,10 @@ def main():
     res["gram_tflops_fp32_equiv_full"] = 2.0 * a.n * a.k * a.k / ms / 1e9
     res["gram_tflops_computed_lower"] = res["gram_tflops_fp32_equiv_full"] * (0.5 + 64.0 / a.k)
     sc = G.TrakScorer(0.5)
-    ms, _ = timed(lambda: sc.factor_(gram.clone()), iters=1); res["cholesky_ms"] = ms
+    g2 = [gram.clone() for _ in range(3)]
+    it = iter(g2)
+    ms, _ = timed(lambda: sc._cholesky_(next(it)), iters=3); res["cholesky_ms"] = ms
+    ms, _ = timed(lambda: sc._tri_inverse_(), iters=3); res["tri_inverse_ms"] = ms
     ms, z = timed(lambda: sc.solve_rows(gen)); res["solve_gen_ms"] = ms
     ms, s = timed(lambda: G.gemm_tn(z, train)); res["score_gemm_ms"] = ms
     res["score_gemm_tflops"] = 2.0 * a.t * a.k * a.n / ms / 1e9
