@@ -233,11 +233,11 @@ int quad_cluster_count(gadm_handle h) {
   return n;
 }
 
-template <int kWarpsPerGroup>
+template <int kWarpsPerGroup, int kGroups = gadm::proj::kMaxGenGroups>
 int launch_project_quad(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Args& args, uint32_t n_clusters,
                         cudaStream_t stream) {
   using C = gadm::proj::Cfg<2>;
-  auto kernel = gadm::proj::project_quad_kernel<kWarpsPerGroup>;
+  auto kernel = gadm::proj::project_quad_kernel<kWarpsPerGroup, kGroups>;
   GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   cudaLaunchConfig_t cfg{};
   const uint32_t clusters = args.n_units < n_clusters ? args.n_units : n_clusters;
@@ -429,8 +429,13 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
   // generator warps per pipeline slot: 2 for Rademacher (cheap bits -> signs), 4 for the MUFU-heavy Box-Muller
   int gw = (proj_type == GADM_PROJ_NORMAL) ? 4 : 2;
   if (const char* e = getenv("GADM_PROJ_GEN_WARPS")) gw = (atoi(e) == 4) ? 4 : 2;  // tuning override
-  if (cta_group == 4)
-    rc = (gw == 4) ? launch_project_quad<4>(h, tmap, a, p.n_clusters, st) : launch_project_quad<2>(h, tmap, a, p.n_clusters, st);
+  if (cta_group == 4) {
+    int groups = 4;  // generator groups of the quad kernel (project_quad.cuh); GADM_QUAD_GEN_GROUPS = 2 | 1 for tuning
+    if (const char* e = getenv("GADM_QUAD_GEN_GROUPS")) groups = atoi(e);
+    if (gw == 4 && groups == 2) rc = launch_project_quad<4, 2>(h, tmap, a, p.n_clusters, st);
+    else if (gw == 4 && groups == 1) rc = launch_project_quad<4, 1>(h, tmap, a, p.n_clusters, st);
+    else rc = (gw == 4) ? launch_project_quad<4>(h, tmap, a, p.n_clusters, st) : launch_project_quad<2>(h, tmap, a, p.n_clusters, st);
+  }
   else if (cta_group == 2)
     rc = (gw == 4) ? launch_project<2, 4>(h, tmap, a, p.n_clusters, st) : launch_project<2, 2>(h, tmap, a, p.n_clusters, st);
   else

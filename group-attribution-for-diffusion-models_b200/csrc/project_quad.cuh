@@ -63,11 +63,17 @@ __device__ __forceinline__ void gen_normal_rows(uint32_t smem_b, int row_base, u
   }
 }
 
-template <int kWarpsPerGroup>
+// kGroups generator groups of kGenWarps / kGroups warps: group g fills the k-blocks with it % kGroups == g.
+// kGroups == 4: one group per pipeline slot (a slot's 8 KiB half tile takes one group ~4 k-block times);
+// kGroups == 2: twice the warps per k-block, so a slot is ready in half the time -- the per-slot chain
+// generate -> fence -> ship over DSMEM -> relay -> MMA -> commit has to fit into the 4-slot window.
+template <int kWarpsPerGroup, int kGroups = kMaxGenGroups>
 __global__ void __launch_bounds__(Roles<kWarpsPerGroup>::kThreads, 1)
 project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   using C = Cfg<2>;
   using R = Roles<kWarpsPerGroup>;
+  constexpr int kGroupWarps = R::kGenWarps / kGroups;
+  constexpr int kGroupThreadsQ = kGroupWarps * 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
@@ -94,7 +100,7 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   if (warp == R::kTmaWarp && lane == 0) prefetch_tensormap(&tmap_g);
   if (warp == R::kMmaWarp && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(full_bar(s), 1 + kWarpsPerGroup * 2 + 1);
+      mbar_init(full_bar(s), 1 + kGroupWarps * 2 + 1);
       mbar_init(empty_bar(s), 2);
       mbar_init(rfull_bar(s), 1);
     }
@@ -205,8 +211,8 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
     }
   } else if (warp < R::kGenWarps) {
     // ===================== generators: own 64 rows of the P tile -> local smem -> shipped to the partner CTA
-    const int group = warp / kWarpsPerGroup;
-    const int tig = (warp % kWarpsPerGroup) * 32 + lane;
+    const int group = warp / kGroupWarps;
+    const int tig = (warp % kGroupWarps) * 32 + lane;
     const int row_base = pair * kQuadOwnRows;
     uint32_t it = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
@@ -215,17 +221,17 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
       const uint32_t j0 = tile * kTileN + rank * C::kBRows;
       const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
       for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-        if (static_cast<int>(it % C::kGenGroups) != group) continue;
-        const int s = group;
+        if (static_cast<int>(it % kGroups) != group) continue;
+        const int s = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x2500 + s);
         const uint32_t p_div64 = a.p_base_div64 + kb;
         if (a.proj_type == kProjRademacher)
-          gen_rademacher_rows<kQuadOwnRows, R::kGroupThreads>(smem_b(s), row_base, p_div64 * 2u, j0, a.key0, a.key1, tig, lane);
+          gen_rademacher_rows<kQuadOwnRows, kGroupThreadsQ>(smem_b(s), row_base, p_div64 * 2u, j0, a.key0, a.key1, tig, lane);
         else
-          gen_normal_rows<kQuadOwnRows, R::kGroupThreads>(smem_b(s), row_base, p_div64 * 8u, j0, a.key0, a.key1, tig);
+          gen_normal_rows<kQuadOwnRows, kGroupThreadsQ>(smem_b(s), row_base, p_div64 * 8u, j0, a.key0, a.key1, tig);
         fence_proxy_async_smem();                           // my generic writes -> async proxy (UMMA and the bulk copy)
-        named_bar_sync(1 + group, R::kGroupThreads);        // the whole 64-row half is written and fenced
+        named_bar_sync(1 + group, kGroupThreadsQ);          // the whole 64-row half is written and fenced
         if (tig == 0) {
           const uint32_t src = smem_b(s) + row_base * 128;
           const uint32_t dst_bar = (rank == 0) ? full_bar(s) : rfull_bar(s);
