@@ -181,6 +181,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
+    if world > 1:  # several ranks stream host->device at once in the e2e leg: keep each rank's pinned buffers NUMA-local
+        from gadm_b200.distributed import bind_to_gpu_numa
+
+        numa_cpus = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -308,7 +313,8 @@ def main():
         e2e = {"value": rows * world / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": rows * GRAD_DIM * 4, "d2h_bytes_per_step": rows * PROJ_DIM * 4,
                "ms_per_step": e2e_ms, "steps": n_e2e,
-               "api": "CudaProjector.deferred().add(fp32 grads from pinned host) -> result() -> host"}
+               "api": "CudaProjector.deferred().add(fp32 grads from pinned host) -> result() -> host",
+               "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
         del bufs, host
     proj.free_memory()
     del stage

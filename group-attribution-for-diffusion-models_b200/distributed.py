@@ -59,3 +59,34 @@ def allgather_cat(t: torch.Tensor, n_total: int | None = None, dim: int = -1, gr
     dist.all_gather(parts, moved, group=group)
     out = torch.cat([p[:n] for p, n in zip(parts, lens)], dim=0)
     return out.movedim(0, dim)
+
+
+def bind_to_gpu_numa(device_index: int) -> list[int] | None:
+    """Pin this process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe root), so that pinned
+    host buffers allocated afterwards are first-touched next to the GPU.  Matters when several ranks stream
+    gradients host->device at once: without it all ranks' buffers tend to land on one socket.  Returns the CPU list,
+    or None when NVML / sched_setaffinity are unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+            dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+            dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpus = max(os.cpu_count() or 1, max(os.sched_getaffinity(0)) + 1)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)  # the container's cpuset
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
