@@ -488,15 +488,27 @@ int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int
   args.C = c; args.ldc = ldc;
   args.M = (int32_t)m; args.N = (int32_t)n; args.K = (int32_t)k;
   args.alpha = alpha; args.beta = beta; args.diag_add = diag_add; args.lower_only = lower_only;
-  auto kernel = gadm::gemm::gemm_tn_3xtf32_kernel;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kSmemBytes));
-    attr_set = true;
-  }
+  // default: A operand staged in tensor memory (gemm.cuh, "TS" variant); GADM_GEMM_TS=0 selects the smem-smem kernel
+  static const bool use_ts = [] { const char* e = getenv("GADM_GEMM_TS"); return !(e && atoi(e) == 0); }();
   dim3 grid((unsigned)((n + gadm::gemm::kBN - 1) / gadm::gemm::kBN), (unsigned)((m + gadm::gemm::kBM - 1) / gadm::gemm::kBM));
   GADM_REQUIRE(grid.y < 65536, "too many row tiles (%u)", grid.y);
-  kernel<<<grid, gadm::gemm::kThreads, gadm::gemm::kSmemBytes, as_stream(stream)>>>(ta, tb, args);
+  if (use_ts) {
+    auto kernel = gadm::gemm::gemm_tn_3xtf32_ts_kernel;
+    static bool attr_set_ts = false;
+    if (!attr_set_ts) {
+      GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kTsSmemBytes));
+      attr_set_ts = true;
+    }
+    kernel<<<grid, gadm::gemm::kThreads, gadm::gemm::kTsSmemBytes, as_stream(stream)>>>(ta, tb, args);
+  } else {
+    auto kernel = gadm::gemm::gemm_tn_3xtf32_kernel;
+    static bool attr_set = false;
+    if (!attr_set) {
+      GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kSmemBytes));
+      attr_set = true;
+    }
+    kernel<<<grid, gadm::gemm::kThreads, gadm::gemm::kSmemBytes, as_stream(stream)>>>(ta, tb, args);
+  }
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

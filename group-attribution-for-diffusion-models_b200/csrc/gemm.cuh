@@ -226,6 +226,192 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------ "TS" variant: A operand in tensor memory
+// Shared-memory bandwidth bounds the kernel above: per 32-wide k-block the MMAs read 12 x 8 KiB of operands, the
+// splitter moves 64 KiB and TMA writes 32 KiB -- 192 KiB at 128 B/clk = 1536 clocks for 768 clocks of tf32 math
+// (ncu: tensor pipe 43-50 %).  Here the splitter warps put the A tile (hi = raw and lo) into TENSOR memory with
+// tcgen05.st (lane = row, 32 columns per k-block each) and the MMAs take A from there
+// (tcgen05.mma ... [d], [a_tmem], b_desc): operand reads from smem halve (48 KiB), the lo-A smem tile and its store
+// disappear (splitter 48 KiB), a stage shrinks to 48 KiB (4 stages) -- 128 KiB per k-block = 1024 clocks, a 75 % bound.
+// Measured on the config-2 Gram (50 000 x 4096, lower tiles): tensor pipe 43 % -> 61 % of elapsed cycles (68 % inside
+// the 3.57 -> 4 wave quantisation), 4.63 -> 4.17 ms; L2 at 27 % and LSU smem wavefronts at 43 % are not the limit any
+// more -- what is left is the TMA -> split -> MMA round trip against only four stages in flight.
+// TMEM map (512 columns): [0, 256) two accumulator buffers, [256 + 64 s, +32) hi-A and [+32, +64) lo-A of stage s.
+constexpr int kTsStages = 4;
+constexpr int kTsStageBytes = 3 * kTileBytes;  // rawA | rawB (= hi B, read in place) | lo B
+constexpr int kTsSmemBytes = kTsStages * kTsStageBytes + 256 + 1024;
+constexpr int kTsTmemCols = 512;
+constexpr int kTsACol0 = 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  if (a.lower_only && tile_n * kBN > tile_m * kBM + (kBM - 1)) return;  // whole CTA exits together
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kTsStages * kTsStageBytes;
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };
+  auto split_full = [&](int s) { return bar_base + 8u * (kTsStages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kTsStages + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (3 * kTsStages + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (3 * kTsStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * kTsStages + 4);
+  auto raw_a = [&](int s) { return smem_base + s * kTsStageBytes; };
+  auto hi_b = [&](int s) { return smem_base + s * kTsStageBytes + kTileBytes; };
+  auto lo_b = [&](int s) { return smem_base + s * kTsStageBytes + 2 * kTileBytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (a.K + kBK - 1) / kBK;
+  const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
+
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kTsStages; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(split_full(s), kSplitWarps);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, kTsTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kTsStages;
+        const uint32_t ph = (kb / kTsStages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u, 0x1900 + s);
+        mbar_arrive_expect_tx(raw_full(s), 2 * kTileBytes);
+        tma_load_2d(raw_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM);
+        tma_load_2d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, kBM, kBN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(acc_empty(buf), ((c >> 1) & 1u) ^ 1u, 0x1d00 + buf);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        const int kb_end = (c + 1) * kChunkKB < nkb ? (c + 1) * kChunkKB : nkb;
+        for (int kb = c * kChunkKB; kb < kb_end; ++kb) {
+          const int s = kb % kTsStages;
+          const uint32_t ph = (kb / kTsStages) & 1u;
+          mbar_wait(split_full(s), ph, 0x1a00 + s);
+          tcgen05_fence_after();
+          const uint64_t dhb = umma_desc_kmajor_sw128(hi_b(s)), dlb = umma_desc_kmajor_sw128(lo_b(s));
+          const uint32_t a_hi = tmem_base + kTsACol0 + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint32_t first = (kb == c * kChunkKB && k == 0) ? 0u : 1u;
+            umma_tf32_ts(d_tmem, a_lo + k * kUmmaK, dhb + 2u * k, idesc, first);  // small terms first
+            umma_tf32_ts(d_tmem, a_hi + k * kUmmaK, dlb + 2u * k, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_hi + k * kUmmaK, dhb + 2u * k, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstSplitWarp) {
+    const int e = warp - kFirstEpiWarp;
+    const int q = warp & 3;       // TMEM lane quarter this warp may read
+    const int half = e >> 2;      // which 64 of the 128 accumulator columns
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(acc_full(buf), (c >> 1) & 1u, 0x1b00 + buf);
+      tcgen05_fence_after();
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBN + half * 64;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t0 + j * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(v[i]));
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+    const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
+    const int64_t col0 = static_cast<int64_t>(tile_n) * kBN + half * 64;
+    if (row < a.M) {
+      float* crow = a.C + row * a.ldc;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const int64_t col = col0 + i;
+        if (col < a.N) {
+          float r = a.alpha * acc[i];
+          if (a.beta != 0.f) r += a.beta * crow[col];
+          if (col == row) r += a.diag_add;
+          crow[col] = r;
+        }
+      }
+    }
+  } else if (warp >= kFirstSplitWarp) {
+    const int q = warp & 3;                            // TMEM lane quarter this warp may write (kFirstSplitWarp % 4 == 0)
+    const int t = threadIdx.x - kFirstSplitWarp * 32;  // 0..127
+    const int row = q * 32 + lane;                     // row of the A tile owned by this thread
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kTsStages;
+      const uint32_t ph = (kb / kTsStages) & 1u;
+      mbar_wait(raw_full(s), ph, 0x1c00 + s);
+      // ---- A: this thread's 128-byte row (8 swizzled 16-byte chunks) -> hi (= raw) and lo columns in TMEM
+      {
+        uint32_t x[32], lo[32];
+        const uint32_t rbase = raw_a(s) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = ld_shared_v4(rbase + ((c ^ (row & 7)) << 4));
+          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { uint32_t hi; split_tf32(x[i], hi, lo[i]); }
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kTsACol0 + s * 64;
+        tmem_st_32x32b_x32(ta, x);        // kind::tf32 ignores the low 13 mantissa bits: raw == hi
+        tmem_st_32x32b_x32(ta + 32, lo);
+      }
+      // ---- B: elementwise lo tile next to the raw (= hi) tile
+      const uint32_t raw = hi_b(s);
+#pragma unroll 8
+      for (int i = 0; i < kTileBytes / 16 / (kSplitWarps * 32); ++i) {
+        const uint32_t off = (static_cast<uint32_t>(i) * (kSplitWarps * 32) + t) * 16u;
+        const uint4 v = ld_shared_v4(raw + off);
+        uint4 hi, lo;
+        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+        split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+        st_shared_v4(raw + kTileBytes + off, lo);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(split_full(s));
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, kTsTmemCols);
+}
+
 // ------------------------------------------------------------------ helpers around the GEMM
 
 // out[c, r] = in[r, c]; in: [R, C] pitch ld_in; out: [C, R_pad] pitch ld_out (columns R..ld_out untouched).
