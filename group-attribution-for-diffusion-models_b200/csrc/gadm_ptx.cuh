@@ -94,12 +94,21 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// kBackoffNs > 0: sleep that long between polls.  mbarrier.try_wait suspends for a few tens of ns only, whatever
+// its time hint says, so a warp that waits microseconds polls dozens of times, and every poll is ~15 instructions
+// with the watchdog check -- in the quad projection kernel 62 % of all executed warp instructions were generator
+// warps polling their slot's empty barrier (42 polls per wait) and epilogue warps polling for the end of a
+// 230-us segment (ncu source view), issue slots and power taken from the generators under a 1 kW cap.  Waits on
+// the critical path (MMA issuer, relay) keep kBackoffNs = 0.
+template <int kBackoffNs = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t code) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   const uint64_t limit = *reinterpret_cast<volatile unsigned long long*>(&g_watchdog_ns);
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (limit != 0 && globaltimer_ns() - t0 > limit) watchdog_fire(code);
+    if (kBackoffNs > 0) __nanosleep(kBackoffNs);
+    if ((++polls & 15u) == 0 && limit != 0 && globaltimer_ns() - t0 > limit) watchdog_fire(code);
   }
 }
 

@@ -196,7 +196,7 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
       const uint32_t split = u / a.n_tiles;
       const uint32_t nseg = num_segments(kb_begin(split), kb_begin(split + 1), a.seg_kb);
       for (uint32_t seg = 0; seg < nseg; ++seg, ++seg_iter) {
-        mbar_wait(tmem_full_bar, seg_iter & 1u, 0x2400);
+        mbar_wait<kEpiBackoffNs>(tmem_full_bar, seg_iter & 1u, 0x2400);
         tcgen05_fence_after();
         for (uint32_t acc = 0; acc < kNumAcc; ++acc) {
           const uint32_t row = pair * pair_rows + acc * (kAccRows * 2) + rank * kAccRows + q * 32;
@@ -224,7 +224,7 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
         if (static_cast<int>(it % kGroups) != group) continue;
         const int s = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u, 0x2500 + s);
+        mbar_wait<kGenBackoffNs>(empty_bar(s), ph ^ 1u, 0x2500 + s);
         const uint32_t p_div64 = a.p_base_div64 + kb;
         if (a.proj_type == kProjRademacher)
           gen_rademacher_rows<kQuadOwnRows, kGroupThreadsQ>(smem_b(s), row_base, p_div64 * 2u, j0, a.key0, a.key1, tig, lane);
