@@ -353,7 +353,7 @@ def main():
                          "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                          "peak_kind": f"bf16_tflops_sustained of measured ({peaks['source']}); timed inside a multi-step loop",
                          "frac_of_burst_peak": achieved / peaks["bf16_burst"], "flops_per_launch": flops_per_launch,
-                         "kernel": "gadm::proj::project_quad_kernel<4>" if args.proj_type == "normal"
+                         "kernel": "gadm::proj::project_quad_kernel<4, 4>" if args.proj_type == "normal"
                          else "gadm::proj::project_kernel<2,2>"},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "tflops": achieved * world, "extra": extra,
