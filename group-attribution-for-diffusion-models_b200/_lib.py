@@ -60,6 +60,15 @@ _SIGNATURES = {
     "gadm_lds_mean": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gadm_group_reduce": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
     "gadm_stable_rank_desc": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "gadm_project": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, C.c_float, c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp,
+                               c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp]),
+    "gadm_gram": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, C.c_float, C.c_int, c_vp]),
+    "gadm_score": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64,
+                             c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "gadm_shapley_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "gadm_shapley": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "gadm_banzhaf": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "gadm_lds": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "gadm_row_mean": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
 }
 

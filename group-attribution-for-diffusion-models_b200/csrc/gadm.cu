@@ -992,4 +992,102 @@ int gadm_row_mean(gadm_handle h, const double* x, int64_t n, int64_t k, double* 
   return GADM_OK;
 }
 
+// ------------------------------------------------------------------ composite entry points
+
+int gadm_project(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
+                 void* staged, int64_t d_pad, int64_t m_cap, int64_t proj_dim, uint64_t seed64, int proj_type, float* out,
+                 int64_t ld_out, int accumulate, void* workspace, int64_t workspace_bytes, int cta_group, void* stream) {
+  GADM_REQUIRE(h && blocks && n_blocks > 0 && staged && out && batch > 0, "bad argument");
+  for (int b = 0; b < n_blocks; ++b) {
+    const gadm_block& blk = blocks[b];
+    GADM_REQUIRE(blk.ptr && blk.numel_per_example > 0 && blk.row_offset >= 0 &&
+                     blk.row_offset + blk.numel_per_example <= d_pad,
+                 "block %d does not fit the staged gradient length %lld", b, (long long)d_pad);
+    GADM_TRY(gadm_pack_block(h, blk.ptr, dtype, batch, blk.numel_per_example, blk.example_stride, staged, d_pad, m_cap, 0,
+                             blk.row_offset, scale, stream));
+  }
+  return gadm_project_staged(h, staged, batch, d_pad, m_cap, 0, proj_dim, seed64, proj_type, out, ld_out, accumulate,
+                             workspace, workspace_bytes, cta_group, stream);
+}
+
+int gadm_gram(gadm_handle h, const float* phi, int64_t n, int64_t k, int64_t ld_phi, float* phi_t_work, int64_t ld_t,
+              float* g, int64_t ldg, float diag_add, int accumulate, void* stream) {
+  GADM_REQUIRE(h && phi && phi_t_work && g && n > 0 && k > 0 && ld_t >= n && ld_t % 4 == 0, "bad argument");
+  GADM_TRY(gadm_transpose(h, phi, n, k, ld_phi, phi_t_work, ld_t, stream));
+  return gadm_gemm_tn(h, phi_t_work, ld_t, phi_t_work, ld_t, g, ldg, k, k, n, 1.f, accumulate ? 1.f : 0.f, diag_add, 1, stream);
+}
+
+int gadm_score(gadm_handle h, const float* gen, int64_t t, int64_t ld_gen, const float* x, int64_t ldx, const float* xt,
+               int64_t ldxt, int64_t k, const float* train, int64_t n_loc, int64_t ld_train, float* z_work, int64_t ldz,
+               float* s, int64_t lds, const float* col_scale, float* mean_out, void* stream) {
+  GADM_REQUIRE(h && gen && x && xt && train && z_work && s && t > 0 && k > 0 && n_loc > 0 && ldz >= k && ldz % 4 == 0,
+               "bad argument");
+  float* z1 = z_work;
+  float* z2 = z_work + t * ldz;
+  GADM_TRY(gadm_gemm_tn(h, gen, ld_gen, x, ldx, z1, ldz, t, k, k, 1.f, 0.f, 0.f, 0, stream));   // gen L^-T
+  GADM_TRY(gadm_gemm_tn(h, z1, ldz, xt, ldxt, z2, ldz, t, k, k, 1.f, 0.f, 0.f, 0, stream));     // ... L^-1
+  GADM_TRY(gadm_gemm_tn(h, z2, ldz, train, ld_train, s, lds, t, n_loc, k, 1.f, 0.f, 0.f, 0, stream));
+  if (mean_out) GADM_TRY(gadm_col_mean_scaled(h, s, t, n_loc, lds, nullptr, col_scale, mean_out, stream));
+  return GADM_OK;
+}
+
+int64_t gadm_shapley_workspace_bytes(int64_t d, int64_t k) {
+  // A [d, d] | Ainv [d, d] | b [d, k] | rhs [d, k] | colsum [d + 1] | info | pinv workspace
+  return (2 * d * d + 2 * d * k + d + 1 + 2) * (int64_t)sizeof(double) + gadm_sym_pinv_workspace_bytes(d) + 256;
+}
+
+static int mask_regression(gadm_handle h, int mode, const uint32_t* rowbits, const uint32_t* colbits, int64_t n, int64_t d,
+                           const double* y, int64_t k, const double* v1, const double* v0, void* workspace,
+                           int64_t workspace_bytes, double* phi, void* stream) {
+  GADM_REQUIRE(h && rowbits && colbits && y && workspace && phi && n > 0 && d > 0 && k > 0, "bad argument");
+  if (workspace_bytes < gadm_shapley_workspace_bytes(d, k))
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes,
+                (long long)gadm_shapley_workspace_bytes(d, k));
+  double* a = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  double* ainv = a + d * d;
+  double* b = ainv + d * d;
+  double* rhs = b + d * k;
+  double* colsum = rhs + d * k;
+  int* info = reinterpret_cast<int*>(colsum + d + 1);
+  void* pws = reinterpret_cast<void*>(colsum + d + 3);
+  GADM_TRY(gadm_mask_gram(h, colbits, n, d, mode, a, stream));
+  if (mode == 0) {  // Shapley: datashapley.py:29-45
+    GADM_REQUIRE(v1 && v0, "v1 / v0 missing");
+    GADM_TRY(gadm_mask_xty(h, rowbits, y, n, d, k, v0, 0.0, 1.0 / (double)n, b, stream));
+    GADM_TRY(gadm_sym_pinv(h, a, d, 1e-15, ainv, pws, gadm_sym_pinv_workspace_bytes(d), info, stream));
+    GADM_TRY(gadm_shapley_rhs(h, ainv, b, d, k, v1, v0, colsum, rhs, stream));
+    return gadm_dgemm_dk(h, ainv, rhs, d, k, 1e-10, phi, stream);
+  }
+  // Banzhaf: databanzhaf.py:19-25 (lstsq(rcond=None) cut-off = eps * d)
+  GADM_TRY(gadm_mask_xty(h, rowbits, y, n, d, k, nullptr, 0.5, 1.0, b, stream));
+  GADM_TRY(gadm_sym_pinv(h, a, d, 2.220446049250313e-16 * (double)d, ainv, pws, gadm_sym_pinv_workspace_bytes(d), info, stream));
+  return gadm_dgemm_dk(h, ainv, b, d, k, 0.0, phi, stream);
+}
+
+int gadm_shapley(gadm_handle h, const uint32_t* rowbits, const uint32_t* colbits, int64_t n, int64_t d, const double* y,
+                 int64_t k, const double* v1, const double* v0, void* workspace, int64_t workspace_bytes, double* phi,
+                 void* stream) {
+  return mask_regression(h, 0, rowbits, colbits, n, d, y, k, v1, v0, workspace, workspace_bytes, phi, stream);
+}
+
+int gadm_banzhaf(gadm_handle h, const uint32_t* rowbits, const uint32_t* colbits, int64_t n, int64_t d, const double* y,
+                 int64_t k, void* workspace, int64_t workspace_bytes, double* phi, void* stream) {
+  return mask_regression(h, 1, rowbits, colbits, n, d, y, k, nullptr, nullptr, workspace, workspace_bytes, phi, stream);
+}
+
+int gadm_lds(gadm_handle h, const uint32_t* test_colbits, int64_t m, int64_t d, const double* y_test, const double* phi,
+             int64_t k, const int32_t* idx, int64_t n_eval, int64_t rows_per_eval, void* workspace,
+             int64_t workspace_bytes, double* lds_out, void* stream) {
+  GADM_REQUIRE(h && test_colbits && y_test && phi && workspace && lds_out && m > 0 && d > 0 && k > 0 && n_eval > 0,
+               "bad argument");
+  if (workspace_bytes < (m + n_eval) * k * (int64_t)sizeof(double))
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes,
+                (long long)((m + n_eval) * k * (int64_t)sizeof(double)));
+  double* pred = reinterpret_cast<double*>(workspace);
+  double* rho = pred + m * k;
+  GADM_TRY(gadm_mask_times_matrix(h, test_colbits, phi, m, d, k, pred, stream));
+  GADM_TRY(gadm_lds_spearman(h, pred, y_test, m, k, idx, n_eval, rows_per_eval, rho, stream));
+  return gadm_lds_mean(h, rho, n_eval, k, lds_out, stream);
+}
+
 }  // extern "C"

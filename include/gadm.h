@@ -13,16 +13,19 @@
  *       requirements.txt:10-11); call sites src/attributions/methods/d_trak_grad.py:504-511,776 and
  *       text_to_image/grad_text_to_image_lora.py:561-568,765,813; vectorize_and_ignore_buffers
  *       (d_trak_grad.py:188-226) is subsumed by per-block packing.
- *   gadm_gemm_tn / gadm_gram / gadm_cholesky / gadm_solve_rows / gadm_transpose / gadm_row_norms /
- *   gadm_col_mean_scaled
+ *   gadm_gemm_tn / gadm_gram / gadm_cholesky / gadm_tri_inverse / gadm_solve_rows / gadm_score /
+ *   gadm_transpose / gadm_row_norms / gadm_col_mean_scaled
  *       text_to_image/traks.py:141-186 (torch.matmul / torch.inverse / norms / mean) and
  *       src/attributions/methods/compute_gradient_score.py:75-79,108-130.
  *   gadm_group_reduce / gadm_stable_rank_desc
  *       text_to_image/traks.py:188-225, src/attributions/methods/attribution_utils.py:15-48,
  *       text_to_image/shapley_lds.py:294.
- *   gadm_pack_masks / gadm_mask_gram / gadm_mask_xty / gadm_sym_pinv / gadm_dgemm / gadm_shapley_finish
+ *   gadm_shapley / gadm_banzhaf (= gadm_pack_masks, gadm_mask_gram, gadm_mask_xty, gadm_sym_pinv, gadm_shapley_rhs,
+ *   gadm_dgemm_dk in sequence)
  *       src/attributions/methods/datashapley.py:8-48, src/attributions/methods/databanzhaf.py:5-26.
- *   gadm_lds_spearman
+ *   gadm_center_columns / gadm_dgemm / gadm_sym_eig / gadm_ridge_gcv / gadm_ridge_select / gadm_ridge_intercept
+ *       RidgeCV datamodel estimator, lds.py:411-421;  gadm_datamodel_ridge_systems: datamodel.py:8-37.
+ *   gadm_lds (= gadm_mask_times_matrix, gadm_lds_spearman, gadm_lds_mean)
  *       evaluate_lds: text_to_image/shapley_lds.py:138-150, lds.py:158-170 and bootstrap statistic
  *       lds.py:458-485.
  */
@@ -224,6 +227,48 @@ int gadm_group_reduce(gadm_handle h, const void* values, int dtype, const int32_
 int gadm_stable_rank_desc(gadm_handle h, const double* x, int64_t n, int64_t* rank, void* stream);
 /* out[i] = mean_k x[i, k] */
 int gadm_row_mean(gadm_handle h, const double* x, int64_t n, int64_t k, double* out, void* stream);
+
+/* ------------------------------------------------------------------ composite entry points
+ * One call per reference function; each is the documented sequence of the calls above on
+ * the same stream, with caller-owned workspace.  The Python host layer may call either level. */
+
+/* One gradient block of a batch: `numel_per_example` values per example, consecutive examples `example_stride`
+ * elements apart, landing at position `row_offset` of the flattened gradient (d_trak_grad.py:188-226). */
+typedef struct gadm_block {
+  const void* ptr;
+  int64_t numel_per_example;
+  int64_t example_stride;
+  int64_t row_offset;
+} gadm_block;
+/* CudaProjector.project on per-parameter blocks: pack every block (x scale) into `staged` rows 0..batch, then
+ * project them.  staged / workspace as for gadm_pack_block / gadm_project_staged. */
+int gadm_project(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
+                 void* staged, int64_t d_pad, int64_t m_cap, int64_t proj_dim, uint64_t seed64, int proj_type, float* out,
+                 int64_t ld_out, int accumulate, void* workspace, int64_t workspace_bytes, int cta_group, void* stream);
+/* G (+)= Phi^T Phi (+ diag_add on the diagonal), lower tiles only (traks.py:149-150).  phi [n, k] pitch ld_phi;
+ * phi_t_work: [k, ld_t] scratch with ld_t >= n, ld_t % 4 == 0; g [k, k] pitch ldg. */
+int gadm_gram(gadm_handle h, const float* phi, int64_t n, int64_t k, int64_t ld_phi, float* phi_t_work, int64_t ld_t,
+              float* g, int64_t ldg, float diag_add, int accumulate, void* stream);
+/* S = gen K^-1 train^T [t, n_loc] with K^-1 = L^-T L^-1 from gadm_tri_inverse (traks.py:152-156), and optionally
+ * mean_out[j] = mean_t S[t, j] * col_scale[j] (traks.py:157,162-168; col_scale may be NULL).
+ * z_work: 2 * t * ldz floats (ldz >= k, ldz % 4 == 0). */
+int gadm_score(gadm_handle h, const float* gen, int64_t t, int64_t ld_gen, const float* x, int64_t ldx, const float* xt,
+               int64_t ldxt, int64_t k, const float* train, int64_t n_loc, int64_t ld_train, float* z_work, int64_t ldz,
+               float* s, int64_t lds, const float* col_scale, float* mean_out, void* stream);
+/* data_shapley for all behaviours (datashapley.py:8-48): phi [d, k].  workspace >= gadm_shapley_workspace_bytes(d, k). */
+int64_t gadm_shapley_workspace_bytes(int64_t d, int64_t k);
+int gadm_shapley(gadm_handle h, const uint32_t* rowbits, const uint32_t* colbits, int64_t n, int64_t d, const double* y,
+                 int64_t k, const double* v1, const double* v0, void* workspace, int64_t workspace_bytes, double* phi,
+                 void* stream);
+/* data_banzhaf for all behaviours (databanzhaf.py:5-26): phi [d, k]; same workspace size. */
+int gadm_banzhaf(gadm_handle h, const uint32_t* rowbits, const uint32_t* colbits, int64_t n, int64_t d, const double* y,
+                 int64_t k, void* workspace, int64_t workspace_bytes, double* phi, void* stream);
+/* LDS of one test set (evaluate_lds inner loop / lds.py:my_lds): lds_out[e] = 100 * mean_k Spearman(X_test[idx[e]] phi_k,
+ * y_test[idx[e], k]).  test_colbits: column bit planes of the test masks [m, d]; idx NULL -> one identity evaluation.
+ * workspace >= (m + n_eval) * k doubles. */
+int gadm_lds(gadm_handle h, const uint32_t* test_colbits, int64_t m, int64_t d, const double* y_test, const double* phi,
+             int64_t k, const int32_t* idx, int64_t n_eval, int64_t rows_per_eval, void* workspace,
+             int64_t workspace_bytes, double* lds_out, void* stream);
 
 #ifdef __cplusplus
 }
