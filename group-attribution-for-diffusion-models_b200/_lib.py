@@ -30,6 +30,8 @@ _SIGNATURES = {
     "gadm_materialize_p": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_vp]),
     "gadm_gemm_tn": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_float, C.c_float,
                                C.c_float, C.c_int, c_vp]),
+    "gadm_gemm_tn_batched": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                       c_i64, C.c_float, C.c_float, C.c_float, C.c_int, c_vp]),
     "gadm_transpose": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gadm_cholesky_workspace_bytes": (c_i64, [c_i64]),
     "gadm_cholesky": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),

@@ -98,6 +98,23 @@ int make_tmap_2d(gadm_handle h, CUtensorMap* map, CUtensorMapDataType dt, int el
   return GADM_OK;
 }
 
+// fp32 [batch][rows][cols] (row pitch / batch stride in bytes), box = box_cols x box_rows x 1: GEMM operands
+int make_tmap_3d_f32(gadm_handle h, CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
+                     uint64_t pitch_bytes, uint64_t batch_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t gdim[3] = {cols, rows, batch};
+  cuuint64_t gstride[2] = {pitch_bytes, batch_stride_bytes};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  GADM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor base %p is not 16-byte aligned", base);
+  GADM_REQUIRE(pitch_bytes % 16 == 0 && batch_stride_bytes % 16 == 0, "pitch / batch stride must be multiples of 16 B");
+  GADM_REQUIRE(box_cols * 4 == 128, "box inner extent must be 128 B for SWIZZLE_128B");
+  CUresult r = h->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box,
+                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GADM_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return GADM_OK;
+}
+
 // staged gradients: bf16 [nkb][m_cap][64]; box = 64 x 128 x 1 (one contiguous 16 KiB tile)
 int make_tmap_staged(gadm_handle h, CUtensorMap* map, const void* base, uint64_t m_cap, uint64_t nkb) {
   cuuint64_t gdim[3] = {64, m_cap, nkb};
@@ -472,25 +489,29 @@ int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_
     if (_rc != GADM_OK) return _rc; \
   } while (0)
 
-int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
-                 int64_t m, int64_t n, int64_t k, float alpha, float beta, float diag_add, int lower_only,
-                 void* stream) {
+int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t stride_a, const float* b, int64_t ldb,
+                         int64_t stride_b, float* c, int64_t ldc, int64_t stride_c, int64_t m, int64_t n, int64_t k,
+                         int64_t batch, float alpha, float beta, float diag_add, int lower_only, void* stream) {
   GADM_REQUIRE(h && a && b && c, "null argument");
   GADM_REQUIRE(m > 0 && n > 0 && k > 0 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "bad shape");
   GADM_REQUIRE(lda >= k && ldb >= k && ldc >= n && lda % 4 == 0 && ldb % 4 == 0, "bad leading dimension");
+  GADM_REQUIRE(batch >= 1 && batch < 65536, "bad batch count");
+  if (batch > 1) GADM_REQUIRE(stride_a % 4 == 0 && stride_b % 4 == 0 && stride_a > 0 && stride_b > 0, "bad batch stride");
   DeviceGuard guard(h->device);
   CUtensorMap ta, tb;
-  GADM_TRY(make_tmap_2d(h, &ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda * 4,
-                        gadm::gemm::kBK, gadm::gemm::kBM));
-  GADM_TRY(make_tmap_2d(h, &tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb * 4,
-                        gadm::gemm::kBK, gadm::gemm::kBN));
+  const uint64_t sa = (uint64_t)(batch > 1 ? stride_a : lda * m) * 4, sb = (uint64_t)(batch > 1 ? stride_b : ldb * n) * 4;
+  GADM_TRY(make_tmap_3d_f32(h, &ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)batch, (uint64_t)lda * 4, sa, gadm::gemm::kBK,
+                            gadm::gemm::kBM));
+  GADM_TRY(make_tmap_3d_f32(h, &tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)batch, (uint64_t)ldb * 4, sb, gadm::gemm::kBK,
+                            gadm::gemm::kBN));
   gadm::gemm::Args args;
-  args.C = c; args.ldc = ldc;
+  args.C = c; args.ldc = ldc; args.stride_c = batch > 1 ? stride_c : 0;
   args.M = (int32_t)m; args.N = (int32_t)n; args.K = (int32_t)k;
   args.alpha = alpha; args.beta = beta; args.diag_add = diag_add; args.lower_only = lower_only;
   // default: A operand staged in tensor memory (gemm.cuh, "TS" variant); GADM_GEMM_TS=0 selects the smem-smem kernel
   static const bool use_ts = [] { const char* e = getenv("GADM_GEMM_TS"); return !(e && atoi(e) == 0); }();
-  dim3 grid((unsigned)((n + gadm::gemm::kBN - 1) / gadm::gemm::kBN), (unsigned)((m + gadm::gemm::kBM - 1) / gadm::gemm::kBM));
+  dim3 grid((unsigned)((n + gadm::gemm::kBN - 1) / gadm::gemm::kBN), (unsigned)((m + gadm::gemm::kBM - 1) / gadm::gemm::kBM),
+            (unsigned)batch);
   GADM_REQUIRE(grid.y < 65536, "too many row tiles (%u)", grid.y);
   if (use_ts) {
     auto kernel = gadm::gemm::gemm_tn_3xtf32_ts_kernel;
@@ -511,6 +532,12 @@ int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int
   }
   GADM_LAUNCHED(h);
   return GADM_OK;
+}
+
+int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
+                 int64_t m, int64_t n, int64_t k, float alpha, float beta, float diag_add, int lower_only,
+                 void* stream) {
+  return gadm_gemm_tn_batched(h, a, lda, 0, b, ldb, 0, c, ldc, 0, m, n, k, 1, alpha, beta, diag_add, lower_only, stream);
 }
 
 int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
@@ -645,7 +672,29 @@ int gadm_tri_inverse(gadm_handle h, const float* l, int64_t ldl, const void* blo
   while (groups.size() > 1) {
     std::vector<std::pair<int64_t, int64_t>> next;
     int64_t woff = 0;
+    // leading run of pairs whose four blocks all have the same full size b: one batched launch per product
+    // (their X / Xt / L blocks lie 2b rows and 2b columns apart -> constant batch strides)
+    const int64_t b = groups[0].second - groups[0].first;
+    size_t uniform_pairs = 0;
     for (size_t g = 0; g + 1 < groups.size(); g += 2) {
+      if (groups[g].second - groups[g].first != b || groups[g + 1].second - groups[g + 1].first != b) break;
+      ++uniform_pairs;
+    }
+    if (uniform_pairs >= 2) {
+      const int64_t a0 = groups[0].first, c0 = groups[1].first, P = (int64_t)uniform_pairs;
+      float* tt = work;  // T^T of pair p at tt + p * b * b (pitch b)
+      woff = P * b * b;
+      GADM_TRY(gadm_gemm_tn_batched(h, xt + a0 * ldxt + a0, ldxt, 2 * b * ldxt + 2 * b, l + c0 * ldl + a0, ldl,
+                                    2 * b * ldl + 2 * b, tt, b, b * b, b, b, b, P, 1.f, 0.f, 0.f, 0, stream));
+      GADM_TRY(gadm_gemm_tn_batched(h, x + c0 * ldx + c0, ldx, 2 * b * ldx + 2 * b, tt, b, b * b, x + c0 * ldx + a0, ldx,
+                                    2 * b * ldx + 2 * b, b, b, b, P, -1.f, 0.f, 0.f, 0, stream));
+      GADM_TRY(gadm_gemm_tn_batched(h, tt, b, b * b, x + c0 * ldx + c0, ldx, 2 * b * ldx + 2 * b, xt + a0 * ldxt + c0, ldxt,
+                                    2 * b * ldxt + 2 * b, b, b, b, P, -1.f, 0.f, 0.f, 0, stream));
+      for (size_t p = 0; p < uniform_pairs; ++p) next.emplace_back(groups[2 * p].first, groups[2 * p + 1].second);
+    } else {
+      uniform_pairs = 0;
+    }
+    for (size_t g = 2 * uniform_pairs; g + 1 < groups.size(); g += 2) {
       const int64_t a0 = groups[g].first, b0 = groups[g].second - a0;       // first group: offset, size
       const int64_t c0 = groups[g + 1].first, b1 = groups[g + 1].second - c0;  // second group
       const int64_t ldt = (b1 + 3) / 4 * 4;

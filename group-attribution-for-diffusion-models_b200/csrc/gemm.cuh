@@ -45,6 +45,7 @@ constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
 struct Args {
   float* C;
   int64_t ldc;
+  int64_t stride_c;   // elements between the C matrices of consecutive batch entries (blockIdx.z)
   int32_t M, N, K;
   float alpha, beta;
   float diag_add;     // added to C[i, i] (global indices, after alpha/beta)
@@ -121,8 +122,8 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const uint32_t ph = (kb / kStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x1100 + s);
         mbar_arrive_expect_tx(raw_full(s), 2 * kTileBytes);
-        tma_load_2d(hi_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM);
-        tma_load_2d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN);
+        tma_load_3d(hi_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM, blockIdx.z);
+        tma_load_3d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN, blockIdx.z);
       }
     }
   } else if (warp == 1) {
@@ -180,7 +181,7 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
     const int64_t col0 = static_cast<int64_t>(tile_n) * kBN + half * 64;
     if (row < a.M) {
-      float* crow = a.C + row * a.ldc;
+      float* crow = a.C + static_cast<int64_t>(blockIdx.z) * a.stride_c + row * a.ldc;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         const int64_t col = col0 + i;
@@ -293,8 +294,8 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t ph = (kb / kTsStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x1900 + s);
         mbar_arrive_expect_tx(raw_full(s), 2 * kTileBytes);
-        tma_load_2d(raw_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM);
-        tma_load_2d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN);
+        tma_load_3d(raw_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM, blockIdx.z);
+        tma_load_3d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN, blockIdx.z);
       }
     }
   } else if (warp == 1) {
@@ -352,7 +353,7 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
     const int64_t col0 = static_cast<int64_t>(tile_n) * kBN + half * 64;
     if (row < a.M) {
-      float* crow = a.C + row * a.ldc;
+      float* crow = a.C + static_cast<int64_t>(blockIdx.z) * a.stride_c + row * a.ldc;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         const int64_t col = col0 + i;

@@ -104,6 +104,12 @@ int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_
 int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
                  int64_t m, int64_t n, int64_t k, float alpha, float beta, float diag_add, int lower_only,
                  void* stream);
+/* The same product for `batch` independent problems whose operands / results lie stride_a / stride_b / stride_c
+ * elements apart (blockIdx.z; 3-D tensor maps).  Used by gadm_tri_inverse: the merges of one recursion level are
+ * one launch. */
+int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t stride_a, const float* b, int64_t ldb,
+                         int64_t stride_b, float* c, int64_t ldc, int64_t stride_c, int64_t m, int64_t n, int64_t k,
+                         int64_t batch, float alpha, float beta, float diag_add, int lower_only, void* stream);
 /* out[c, r] = in[r, c]  (in: [rows, cols] pitch ld_in; out: [cols, rows] pitch ld_out) */
 int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
                    int64_t ld_out, void* stream);
