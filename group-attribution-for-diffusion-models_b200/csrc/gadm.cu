@@ -30,6 +30,7 @@ struct gadm_ctx {
   int64_t launches = 0;
   uint32_t* scratch = nullptr;  // small device scratch owned by the handle (lockstep counter)
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
+  bool attr_gemm = false, attr_gemm_ts = false, attr_potrf = false;  // per-device kernel attributes already set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start / panel / rest / end
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
@@ -515,18 +516,16 @@ int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t str
   GADM_REQUIRE(grid.y < 65536, "too many row tiles (%u)", grid.y);
   if (use_ts) {
     auto kernel = gadm::gemm::gemm_tn_3xtf32_ts_kernel;
-    static bool attr_set_ts = false;
-    if (!attr_set_ts) {
+    if (!h->attr_gemm_ts) {  // the attribute is per device: remembered in the handle, not in a process-wide static
       GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kTsSmemBytes));
-      attr_set_ts = true;
+      h->attr_gemm_ts = true;
     }
     kernel<<<grid, gadm::gemm::kThreads, gadm::gemm::kTsSmemBytes, as_stream(stream)>>>(ta, tb, args);
   } else {
     auto kernel = gadm::gemm::gemm_tn_3xtf32_kernel;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->attr_gemm) {
       GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kSmemBytes));
-      attr_set = true;
+      h->attr_gemm = true;
     }
     kernel<<<grid, gadm::gemm::kThreads, gadm::gemm::kSmemBytes, as_stream(stream)>>>(ta, tb, args);
   }
@@ -569,10 +568,9 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
   float* linv = reinterpret_cast<float*>(blocks);
   float* linv_t = linv + nblk * NB * NB;
   auto potrf = gadm::gemm::potrf_diag_kernel;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_potrf) {
     GADM_CUDA(cudaFuncSetAttribute(potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kPotrfSmem));
-    attr_set = true;
+    h->attr_potrf = true;
   }
   if (info) GADM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), as_stream(stream)));
   // Look-ahead: the critical path (diagonal block -> panel -> update of the NEXT block column) runs on a
