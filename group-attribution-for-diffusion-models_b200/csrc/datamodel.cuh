@@ -152,7 +152,8 @@ ridge_fold_kernel(const double* __restrict__ G0, const double* __restrict__ y, c
         }
       }
       const double r = block_sum(ss_res, red), tt = block_sum(ss_tot, red);
-      if (tid == 0) scores[sys.out] = 1.0 - r / tt;
+      // sklearn.metrics.r2_score(force_finite=True): a constant held-out target scores 1 if predicted exactly, else 0
+      if (tid == 0) scores[sys.out] = (tt != 0.0) ? 1.0 - r / tt : ((r != 0.0) ? 0.0 : 1.0);
     } else {
       // ---- refit: w_i = sum_{p: id_p = i} c_p - count_i * sum(c) / n  (one thread per original row, fixed order)
       double cs = 0.0;

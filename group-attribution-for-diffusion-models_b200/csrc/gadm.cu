@@ -508,7 +508,9 @@ int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t str
   gadm::gemm::Args args;
   args.C = c; args.ldc = ldc; args.stride_c = batch > 1 ? stride_c : 0;
   args.M = (int32_t)m; args.N = (int32_t)n; args.K = (int32_t)k;
-  args.alpha = alpha; args.beta = beta; args.diag_add = diag_add; args.lower_only = lower_only;
+  args.alpha = alpha; args.beta = beta; args.diag_add = diag_add;
+  args.lower_only = lower_only & 1;                                   // flag bit 0
+  args.tri_b = (lower_only & 2) ? 1 : ((lower_only & 4) ? 2 : 0);      // bit 1: B lower-triangular, bit 2: upper
   // default: A operand staged in tensor memory (gemm.cuh, "TS" variant); GADM_GEMM_TS=0 selects the smem-smem kernel
   static const bool use_ts = [] { const char* e = getenv("GADM_GEMM_TS"); return !(e && atoi(e) == 0); }();
   dim3 grid((unsigned)((n + gadm::gemm::kBN - 1) / gadm::gemm::kBN), (unsigned)((m + gadm::gemm::kBM - 1) / gadm::gemm::kBM),

@@ -50,7 +50,18 @@ struct Args {
   float alpha, beta;
   float diag_add;     // added to C[i, i] (global indices, after alpha/beta)
   int32_t lower_only; // skip tiles entirely above the diagonal
+  int32_t tri_b;      // 1: B is lower-triangular (B[j, c] = 0 for c > j), 2: upper-triangular (0 for c < j):
+                      //    the contraction of output tile column tile_n stops / starts at its diagonal block
 };
+
+// contraction k-block range [kb0, kb1) of an output tile
+__device__ __forceinline__ void kblock_range(const Args& a, int tile_n, int& kb0, int& kb1) {
+  const int nkb = (a.K + kBK - 1) / kBK;
+  kb0 = 0;
+  kb1 = nkb;
+  if (a.tri_b == 1) { const int e = (tile_n + 1) * (kBN / kBK); kb1 = e < nkb ? e : nkb; }
+  else if (a.tri_b == 2) { const int b = tile_n * (kBN / kBK); kb0 = b < nkb ? b : nkb; }
+}
 
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
@@ -92,7 +103,9 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   auto lo_b = [&](int s) { return smem_base + s * kStageBytes + 3 * kTileBytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (a.K + kBK - 1) / kBK;
+  int kb0, kb1;
+  kblock_range(a, tile_n, kb0, kb1);
+  const int nkb = kb1 - kb0;  // >= 1: the diagonal block is always inside the range
   const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_b); }
@@ -122,8 +135,8 @@ gemm_tn_3xtf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const uint32_t ph = (kb / kStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x1100 + s);
         mbar_arrive_expect_tx(raw_full(s), 2 * kTileBytes);
-        tma_load_3d(hi_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM, blockIdx.z);
-        tma_load_3d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN, blockIdx.z);
+        tma_load_3d(hi_a(s), &tmap_a, raw_full(s), (kb0 + kb) * kBK, tile_m * kBM, blockIdx.z);
+        tma_load_3d(hi_b(s), &tmap_b, raw_full(s), (kb0 + kb) * kBK, tile_n * kBN, blockIdx.z);
       }
     }
   } else if (warp == 1) {
@@ -264,7 +277,9 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   auto lo_b = [&](int s) { return smem_base + s * kTsStageBytes + 2 * kTileBytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (a.K + kBK - 1) / kBK;
+  int kb0, kb1;
+  kblock_range(a, tile_n, kb0, kb1);
+  const int nkb = kb1 - kb0;  // >= 1: the diagonal block is always inside the range
   const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_b); }
@@ -294,8 +309,8 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t ph = (kb / kTsStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x1900 + s);
         mbar_arrive_expect_tx(raw_full(s), 2 * kTileBytes);
-        tma_load_3d(raw_a(s), &tmap_a, raw_full(s), kb * kBK, tile_m * kBM, blockIdx.z);
-        tma_load_3d(hi_b(s), &tmap_b, raw_full(s), kb * kBK, tile_n * kBN, blockIdx.z);
+        tma_load_3d(raw_a(s), &tmap_a, raw_full(s), (kb0 + kb) * kBK, tile_m * kBM, blockIdx.z);
+        tma_load_3d(hi_b(s), &tmap_b, raw_full(s), (kb0 + kb) * kBK, tile_n * kBN, blockIdx.z);
       }
     }
   } else if (warp == 1) {

@@ -61,8 +61,9 @@ def _h(t: torch.Tensor):
 
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, alpha: float = 1.0, beta: float = 0.0,
-            diag_add: float = 0.0, lower_only: bool = False) -> torch.Tensor:
-    """out = alpha * a @ b.T + beta * out  (fp32-grade accuracy, 3xTF32 tcgen05 kernel)."""
+            diag_add: float = 0.0, lower_only: bool = False, b_tri: str | None = None) -> torch.Tensor:
+    """out = alpha * a @ b.T + beta * out  (fp32-grade accuracy, 3xTF32 tcgen05 kernel).
+    ``b_tri`` = "lower" / "upper": b is square triangular, the contraction skips its zero blocks."""
     a = _check_cuda_f32(a, "a")
     b = _check_cuda_f32(b, "b")
     if a.shape[1] != b.shape[1]:
@@ -76,7 +77,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, a
     with torch.cuda.device(a.device):
         _lib.check(h.lib.gadm_gemm_tn(h.ptr, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
                                      out.stride(0), m, n, k, float(alpha), float(beta), float(diag_add),
-                                     int(lower_only), _lib.stream_ptr(a.device)))
+                                     int(lower_only) | {None: 0, "lower": 2, "upper": 4}[b_tri], _lib.stream_ptr(a.device)))
     return out
 
 
@@ -247,7 +248,7 @@ class TrakScorer:
         y = _check_cuda_f32(rows, "rows")
         if y.shape[1] != self.k:
             raise ValueError(f"rows have {y.shape[1]} columns, the factored system has {self.k}")
-        return gemm_tn(gemm_tn(y, self.X), self.Xt)
+        return gemm_tn(gemm_tn(y, self.X, b_tri="lower"), self.Xt, b_tri="upper")
 
     def solve_rows_blocked(self, rows: torch.Tensor) -> torch.Tensor:
         """The same through blocked forward / backward substitution (gadm_solve_rows), kept as a cross-check."""
@@ -274,7 +275,7 @@ class TrakScorer:
     def kernel_inverse(self) -> torch.Tensor:
         """Explicit K^-1 (what the reference caches as kernel_*.npy, compute_gradient_score.py:104-111)."""
         if not self.dual:
-            return gemm_tn(self.Xt, self.Xt)  # K^-1 = L^-T L^-1
+            return gemm_tn(self.Xt, self.Xt, b_tri="upper")  # K^-1 = L^-T L^-1
         eye = torch.eye(self.phi_all.shape[1], dtype=_f32, device=self.L.device)
         return self.solve_rows(eye, inplace=True)
 

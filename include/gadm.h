@@ -98,7 +98,10 @@ int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_
 
 /* C[M, N] = alpha * A[M, K] * B[N, K]^T + beta * C, then C[i, i] += diag_add.
  *   A, B, C fp32 row-major (contraction index contiguous in A and B); lda, ldb multiples of 4; A, B 16-byte
- *   aligned.  lower_only != 0 skips 128x128 tiles strictly above the diagonal (symmetric results).
+ *   aligned.  lower_only is a flag word: bit 0 skips 128x128 tiles strictly above the diagonal (symmetric results);
+ *   bit 1 (value 2) declares B lower-triangular (B[j, c] = 0 for c > j), bit 2 (value 4) upper-triangular
+ *   (B[j, c] = 0 for c < j): the contraction of every output tile then stops / starts at its diagonal block, which
+ *   halves the work of the two solve GEMMs against L^-1 and L^-T.
  *   Replaces torch.matmul at text_to_image/traks.py:141,149,152,156,171,176,181,184 and the numpy products at
  *   src/attributions/methods/compute_gradient_score.py:75,79,108,126 (fp32-grade accuracy via 3xTF32). */
 int gadm_gemm_tn(gadm_handle h, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,

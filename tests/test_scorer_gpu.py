@@ -274,3 +274,19 @@ def test_partial_fit_streams_the_gram():
     assert float((a - b).abs().max()) < 2e-5 * float(a.abs().max())
     with pytest.raises(RuntimeError):
         G.TrakScorer(0.5).finalize()
+
+
+@pytest.mark.parametrize("n", [128, 300, 1000])
+def test_gemm_triangular_operand_skips_zero_blocks(n):
+    import gadm_b200 as G
+
+    a = _rand((77, n), 41)
+    low = torch.tril(_rand((n, n), 42))
+    up = low.T.contiguous()
+    for tri, b in (("lower", low), ("upper", up)):
+        full = G.gemm_tn(a, b)
+        fast = G.gemm_tn(a, b, b_tri=tri)
+        want = a.double() @ b.double().T
+        assert float((fast.double() - want).abs().max()) < 4e-6 * float(a.double().norm(dim=1).max() * b.double().norm(dim=1).max())
+        # the skipped blocks are exact zeros, so the two results agree to accumulation-order rounding
+        assert float((fast - full).abs().max()) < 1e-5 * float(full.abs().max())
