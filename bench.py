@@ -407,14 +407,15 @@ def side_measurements(dev, rank, world):
         for t in range(3):
             Xt = G.masks_from_seeds(d, list(range(5000 + 100 * t, 5000 + 100 * t + m)), "datamodel").astype(np.float64)
             tests.append((Xt, Xt @ w + 0.5 * rng.normal(size=(m, K))))
-        for it in range(2):
+        agg_ms = float("inf")
+        for it in range(4):  # best of 4: the first passes pay cudaMalloc after the empty_cache() above
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             phi = G.data_shapley_batched(Xs, Ys, w.sum(axis=0), np.zeros(K))
             phb = G.data_banzhaf_batched(Xs, Ys)
             lds = G.evaluate_lds(phi, tests, K)
             torch.cuda.synchronize()
-            agg_ms = (time.perf_counter() - t0) * 1e3
+            agg_ms = min(agg_ms, (time.perf_counter() - t0) * 1e3)
         bytes_alg = n * d + 8 * n * K + 8 * d * K + 3 * (m * d + 8 * m * K) + 8 * d * K + 8 * 3 * K
         out["aggregation"] = {"ms_host_to_host": agg_ms, "n_masks": n, "contributors": d, "behaviors": K,
                               "algorithmic_bytes": bytes_alg, "lds": list(map(float, lds)),
