@@ -416,6 +416,15 @@ def side_measurements(dev, rank, world):
             lds = G.evaluate_lds(phi, tests, K)
             torch.cuda.synchronize()
             agg_ms = min(agg_ms, (time.perf_counter() - t0) * 1e3)
+        ridge_ms = float("inf")
+        for it in range(3):  # datamodel estimator of lds.py:411-421: RidgeCV over 100 alphas for every behaviour
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = G.ridge_cv_batched(Xs, Ys)
+            torch.cuda.synchronize()
+            ridge_ms = min(ridge_ms, (time.perf_counter() - t0) * 1e3)
+        out["ridge_cv"] = {"ms_host_to_host": ridge_ms, "n_masks": n, "contributors": d, "behaviors": K, "alphas": 100,
+                           "what": "RidgeCV(alphas=linspace(0.01, 10, 100)) leave-one-out fit of every behaviour, numpy in / numpy out"}
         bytes_alg = n * d + 8 * n * K + 8 * d * K + 3 * (m * d + 8 * m * K) + 8 * d * K + 8 * 3 * K
         out["aggregation"] = {"ms_host_to_host": agg_ms, "n_masks": n, "contributors": d, "behaviors": K,
                               "algorithmic_bytes": bytes_alg, "lds": list(map(float, lds)),
