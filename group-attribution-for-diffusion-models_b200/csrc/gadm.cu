@@ -283,6 +283,7 @@ int launch_project_quad(gadm_handle h, const CUtensorMap& tmap, const gadm::proj
   const char* coop = getenv("GADM_PROJ_COOPERATIVE");
   a.sync_counter = h->scratch;
   a.sync_every = gadm::proj::kSyncEvery;
+  if (const char* e = getenv("GADM_PROJ_SYNC_EVERY")) { const int v = atoi(e); if (v >= 4) a.sync_every = (uint32_t)v; }
   a.sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / a.sync_every) * a.sync_every);
   if (a.sync_iters) {
     GADM_CUDA(cudaMemsetAsync(h->scratch, 0, sizeof(uint32_t), stream));
