@@ -25,8 +25,13 @@ _SIGNATURES = {
     "gadm_project_workspace_bytes": (c_i64, [c_vp, c_i64, c_i64, c_i64, C.c_int]),
     "gadm_pack_block": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_float,
                                   c_vp]),
-    "gadm_project_staged": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_i64,
-                                      C.c_int, c_vp, c_i64, C.c_int, c_vp]),
+    "gadm_stage_scale_count": (c_i64, [c_i64]),
+    "gadm_stage_rows": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, C.c_float, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp,
+                                  c_vp]),
+    "gadm_accumulate_rows": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, C.c_float, c_vp, c_i64, c_i64, c_i64, C.c_int,
+                                       c_vp]),
+    "gadm_project_staged": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp,
+                                      c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp]),
     "gadm_materialize_p": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_vp]),
     "gadm_gemm_tn": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_float, C.c_float,
                                C.c_float, C.c_int, c_vp]),
@@ -62,8 +67,8 @@ _SIGNATURES = {
     "gadm_lds_mean": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gadm_group_reduce": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
     "gadm_stable_rank_desc": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
-    "gadm_project": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, C.c_float, c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp,
-                               c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp]),
+    "gadm_project": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, C.c_float, c_vp, C.c_int, c_vp, c_i64, c_i64, c_i64, c_u64,
+                               C.c_int, c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp]),
     "gadm_gram": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, C.c_float, C.c_int, c_vp]),
     "gadm_score": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64,
                              c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -76,6 +81,12 @@ _SIGNATURES = {
 
 _lib = None
 _lock = threading.Lock()
+
+
+class Block(C.Structure):
+    """gadm_block (include/gadm.h)."""
+
+    _fields_ = [("ptr", c_vp), ("numel_per_example", c_i64), ("example_stride", c_i64), ("row_offset", c_i64)]
 
 
 class GadmError(RuntimeError):

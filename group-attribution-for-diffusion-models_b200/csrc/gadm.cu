@@ -16,6 +16,7 @@
 #include "philox.cuh"
 #include "project.cuh"
 #include "project_quad.cuh"
+#include "stage.cuh"
 #include <utility>
 #include <vector>
 
@@ -28,7 +29,9 @@ struct gadm_ctx {
   int device = 0;
   int num_sms = 0;
   int64_t launches = 0;
-  uint32_t* scratch = nullptr;  // small device scratch owned by the handle (lockstep counter)
+  uint32_t* scratch = nullptr;  // device scratch owned by the handle: ring of kLockstepSlots lockstep counters
+  uint32_t lockstep_seq = 0;    // next ring slot: every projection launch gets its own counter word, so launches in
+                                // flight on different streams of one device never share a barrier
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
   bool attr_gemm = false, attr_gemm_ts = false, attr_potrf = false;  // per-device kernel attributes already set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
@@ -62,6 +65,12 @@ int fail(int code, const char* fmt, ...) {
     if (!(cond)) return fail(GADM_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+#define GADM_TRY_RC(expr)           \
+  do {                              \
+    int _rc = (expr);               \
+    if (_rc != GADM_OK) return _rc; \
+  } while (0)
+
 #define GADM_LAUNCHED(h)           \
   do {                             \
     GADM_CUDA(cudaGetLastError()); \
@@ -82,23 +91,6 @@ struct DeviceGuard {
   }
 };
 
-// 2-D row-major tensor map: inner dimension `cols` (contiguous), outer `rows`, pitch in bytes.
-int make_tmap_2d(gadm_handle h, CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base,
-                 uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_cols, uint32_t box_rows) {
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {pitch_bytes};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estride[2] = {1, 1};
-  GADM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor base %p is not 16-byte aligned", base);
-  GADM_REQUIRE(pitch_bytes % 16 == 0, "row pitch %llu B is not a multiple of 16", (unsigned long long)pitch_bytes);
-  GADM_REQUIRE(box_cols * elem_bytes == 128, "box inner extent must be 128 B for SWIZZLE_128B");
-  CUresult r = h->encode_tiled(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(GADM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return GADM_OK;
-}
-
 // fp32 [batch][rows][cols] (row pitch / batch stride in bytes), box = box_cols x box_rows x 1: GEMM operands
 int make_tmap_3d_f32(gadm_handle h, CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
                      uint64_t pitch_bytes, uint64_t batch_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
@@ -117,15 +109,16 @@ int make_tmap_3d_f32(gadm_handle h, CUtensorMap* map, const void* base, uint64_t
 }
 
 // staged gradients: bf16 [nkb][m_cap][64]; box = 64 x 128 x 1 (one contiguous 16 KiB tile)
-int make_tmap_staged(gadm_handle h, CUtensorMap* map, const void* base, uint64_t m_cap, uint64_t nkb) {
+int make_tmap_staged(gadm_handle h, CUtensorMap* map, const void* base, uint64_t m_cap, uint64_t nkb, bool f16) {
   cuuint64_t gdim[3] = {64, m_cap, nkb};
   cuuint64_t gstride[2] = {128, m_cap * 128};
   cuuint32_t box[3] = {64, 128, 1};
   cuuint32_t estride[3] = {1, 1, 1};
   GADM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 127) == 0, "staging buffer %p is not 128-byte aligned", base);
-  CUresult r = h->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box,
-                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = h->encode_tiled(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                               const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GADM_ERR_CUDA, "cuTensorMapEncodeTiled(staged) failed with CUresult %d", (int)r);
   return GADM_OK;
 }
@@ -175,46 +168,61 @@ int plan_projection(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_d
   return GADM_OK;
 }
 
-template <int kCtaGroup, int kWarpsPerGroup>
-int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Args& args, uint32_t n_clusters,
-                   cudaStream_t stream) {
-  using C = gadm::proj::Cfg<kCtaGroup>;
-  auto kernel = gadm::proj::project_kernel<kCtaGroup, kWarpsPerGroup>;
-  GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+constexpr uint32_t kLockstepSlots = 1024;  // ring of counter words in the handle scratch (4 KiB)
+
+// Inter-cluster lockstep set-up shared by the pair and quad launchers.  Picks this launch's own counter word from
+// the handle's ring (two projections in flight on different streams must not share a barrier), zeroes it on the
+// launch stream and bounds the lockstep to the k-block count every launched cluster reaches (clusters own whole
+// units round-robin).  The spin barrier needs every cluster resident at once, which only a cooperative launch
+// guarantees: GADM_PROJ_COOPERATIVE=0 (plain launch, e.g. for profilers that cannot replay cooperative grids)
+// therefore also switches the lockstep off unless GADM_PROJ_UNSAFE_LOCKSTEP=1 vouches that the kernel runs alone.
+int setup_lockstep(gadm_handle h, gadm::proj::Args* a, uint32_t clusters, cudaStream_t stream, bool* cooperative) {
+  uint64_t min_iters = ~0ull;
+  for (uint32_t c = 0; c < clusters; ++c) {
+    uint64_t iters = 0;
+    for (uint32_t u = c; u < a->n_units; u += clusters) {
+      const uint64_t split = u / a->n_tiles;
+      iters += (split + 1) * a->nkb_total / a->n_splits - split * a->nkb_total / a->n_splits;
+    }
+    if (iters < min_iters) min_iters = iters;
+  }
+  const char* nosync = getenv("GADM_PROJ_NO_LOCKSTEP");
+  const char* coop = getenv("GADM_PROJ_COOPERATIVE");
+  const char* unsafe = getenv("GADM_PROJ_UNSAFE_LOCKSTEP");
+  *cooperative = !(coop && atoi(coop) == 0);
+  a->sync_every = gadm::proj::kSyncEvery;
+  if (const char* e = getenv("GADM_PROJ_SYNC_EVERY")) { const int v = atoi(e); if (v >= 4) a->sync_every = (uint32_t)v; }
+  a->sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / a->sync_every) * a->sync_every);
+  if (!*cooperative && !(unsafe && atoi(unsafe))) a->sync_iters = 0;
+  a->sync_counter = h->scratch + (h->lockstep_seq++ % kLockstepSlots);
+  if (a->sync_iters) GADM_CUDA(cudaMemsetAsync(a->sync_counter, 0, sizeof(uint32_t), stream));
+  return GADM_OK;
+}
+
+template <typename Kernel>
+int launch_clusters(gadm_handle h, Kernel kernel, int cluster_size, int threads, int smem_bytes, const CUtensorMap& tmap,
+                    const gadm::proj::Args& args, uint32_t n_clusters, cudaStream_t stream) {
+  GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   cudaLaunchConfig_t cfg{};
   const uint32_t clusters = args.n_units < n_clusters ? args.n_units : n_clusters;
-  cfg.gridDim = dim3(clusters * kCtaGroup);
-  cfg.blockDim = dim3(gadm::proj::Roles<kWarpsPerGroup>::kThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.gridDim = dim3(clusters * cluster_size);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.x = cluster_size;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeCooperative;  // co-residency guarantee for the inter-cluster lockstep
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
   gadm::proj::Args a = args;
-  // lockstep only over the k-block count every launched cluster reaches (clusters own whole units round-robin)
-  uint64_t min_iters = ~0ull;
-  for (uint32_t c = 0; c < clusters; ++c) {
-    uint64_t iters = 0;
-    for (uint32_t u = c; u < a.n_units; u += clusters) {
-      const uint64_t split = u / a.n_tiles;
-      iters += (split + 1) * a.nkb_total / a.n_splits - split * a.nkb_total / a.n_splits;
-    }
-    if (iters < min_iters) min_iters = iters;
-  }
-  const char* nosync = getenv("GADM_PROJ_NO_LOCKSTEP");
-  a.sync_counter = h->scratch;
-  a.sync_every = gadm::proj::kSyncEvery;
-  if (const char* e = getenv("GADM_PROJ_SYNC_EVERY")) { const int v = atoi(e); if (v >= 4) a.sync_every = (uint32_t)v; }
-  a.sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / a.sync_every) * a.sync_every);
-  const char* coop = getenv("GADM_PROJ_COOPERATIVE");  // "0": plain launch, lockstep kept (ncu cannot replay cooperative launches)
-  if (a.sync_iters) {
-    GADM_CUDA(cudaMemsetAsync(h->scratch, 0, sizeof(uint32_t), stream));
-    cfg.numAttrs = (coop && atoi(coop) == 0) ? 1 : 2;
+  bool cooperative = true;
+  int rc = setup_lockstep(h, &a, clusters, stream, &cooperative);
+  if (rc != GADM_OK) return rc;
+  if (a.sync_iters && cooperative) {
+    cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, a);
     if (e == cudaSuccess) {
       h->launches++;
@@ -227,6 +235,14 @@ int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Arg
   GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, a));
   h->launches++;
   return GADM_OK;
+}
+
+template <int kCtaGroup, int kWarpsPerGroup>
+int launch_project(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Args& args, uint32_t n_clusters,
+                   cudaStream_t stream) {
+  return launch_clusters(h, gadm::proj::project_kernel<kCtaGroup, kWarpsPerGroup>, kCtaGroup,
+                         gadm::proj::Roles<kWarpsPerGroup>::kThreads, gadm::proj::Cfg<kCtaGroup>::kSmemBytes, tmap, args,
+                         n_clusters, stream);
 }
 
 int quad_cluster_count(gadm_handle h) {
@@ -254,48 +270,65 @@ int quad_cluster_count(gadm_handle h) {
 template <int kWarpsPerGroup, int kGroups = gadm::proj::kMaxGenGroups>
 int launch_project_quad(gadm_handle h, const CUtensorMap& tmap, const gadm::proj::Args& args, uint32_t n_clusters,
                         cudaStream_t stream) {
-  using C = gadm::proj::Cfg<2>;
-  auto kernel = gadm::proj::project_quad_kernel<kWarpsPerGroup, kGroups>;
-  GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-  cudaLaunchConfig_t cfg{};
-  const uint32_t clusters = args.n_units < n_clusters ? args.n_units : n_clusters;
-  cfg.gridDim = dim3(clusters * 4);
-  cfg.blockDim = dim3(gadm::proj::Roles<kWarpsPerGroup>::kThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeCooperative;
-  attr[1].val.cooperative = 1;
-  cfg.attrs = attr;
-  gadm::proj::Args a = args;
-  uint64_t min_iters = ~0ull;
-  for (uint32_t c = 0; c < clusters; ++c) {
-    uint64_t iters = 0;
-    for (uint32_t u = c; u < a.n_units; u += clusters) {
-      const uint64_t split = u / a.n_tiles;
-      iters += (split + 1) * a.nkb_total / a.n_splits - split * a.nkb_total / a.n_splits;
+  return launch_clusters(h, gadm::proj::project_quad_kernel<kWarpsPerGroup, kGroups>, 4,
+                         gadm::proj::Roles<kWarpsPerGroup>::kThreads, gadm::proj::Cfg<2>::kSmemBytes, tmap, args,
+                         n_clusters, stream);
+}
+
+// host-side block list -> kernel-parameter table (sorted by position; gaps are staged as zeros)
+int fill_block_table(const gadm_block* blocks, int n_blocks, int64_t batch, int64_t d_pad, gadm::stage::BlockTable* tab) {
+  GADM_REQUIRE(blocks && n_blocks > 0, "empty block list");
+  GADM_REQUIRE(n_blocks <= gadm::stage::kMaxBlocks, "%d parameter blocks exceed the %d one launch takes; concatenate "
+               "neighbouring blocks first", n_blocks, gadm::stage::kMaxBlocks);
+  int64_t prev_end = 0;
+  int n = 0;
+  for (int b = 0; b < n_blocks; ++b) {
+    const gadm_block& blk = blocks[b];
+    if (blk.numel_per_example == 0) continue;
+    GADM_REQUIRE(blk.ptr && blk.numel_per_example > 0 && blk.row_offset >= prev_end &&
+                     blk.row_offset + blk.numel_per_example <= d_pad &&
+                     (batch == 1 || blk.example_stride >= blk.numel_per_example),
+                 "block %d (offset %lld, numel %lld, stride %lld) is unsorted, overlaps its predecessor or leaves the "
+                 "staged gradient length %lld", b, (long long)blk.row_offset, (long long)blk.numel_per_example,
+                 (long long)blk.example_stride, (long long)d_pad);
+    if (blk.row_offset > prev_end) {  // gap: a table entry without a source, staged as zeros
+      GADM_REQUIRE(n < gadm::stage::kMaxBlocks, "too many parameter blocks (gaps count as blocks)");
+      tab->start[n] = prev_end;
+      tab->stride[n] = 0;
+      tab->ptr[n] = nullptr;
+      ++n;
     }
-    if (iters < min_iters) min_iters = iters;
+    GADM_REQUIRE(n < gadm::stage::kMaxBlocks, "too many parameter blocks (gaps count as blocks)");
+    tab->start[n] = blk.row_offset;
+    tab->stride[n] = blk.example_stride;
+    tab->ptr[n] = blk.ptr;
+    prev_end = blk.row_offset + blk.numel_per_example;
+    ++n;
+    tab->start[n] = prev_end;  // columns from here to d_pad (or to the next block) read as zeros
   }
-  const char* nosync = getenv("GADM_PROJ_NO_LOCKSTEP");
-  const char* coop = getenv("GADM_PROJ_COOPERATIVE");
-  a.sync_counter = h->scratch;
-  a.sync_every = gadm::proj::kSyncEvery;
-  if (const char* e = getenv("GADM_PROJ_SYNC_EVERY")) { const int v = atoi(e); if (v >= 4) a.sync_every = (uint32_t)v; }
-  a.sync_iters = (nosync && atoi(nosync)) ? 0u : (uint32_t)((min_iters / a.sync_every) * a.sync_every);
-  if (a.sync_iters) {
-    GADM_CUDA(cudaMemsetAsync(h->scratch, 0, sizeof(uint32_t), stream));
-    cfg.numAttrs = (coop && atoi(coop) == 0) ? 1 : 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, a);
-    if (e == cudaSuccess) { h->launches++; return GADM_OK; }
-    (void)cudaGetLastError();
-    a.sync_iters = 0;
-  }
-  cfg.numAttrs = 1;
-  GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, a));
-  h->launches++;
+  GADM_REQUIRE(n > 0, "all blocks are empty");
+  tab->n = n;
+  tab->pad = 0;
+  return GADM_OK;
+}
+
+inline int64_t stage_scale_count(int64_t d_pad) {
+  return (d_pad / gadm::proj::kBlockK + gadm::stage::kGroupKb - 1) / gadm::stage::kGroupKb;
+}
+
+template <typename T>
+int launch_stage(gadm_handle h, const gadm::stage::BlockTable& tab, int64_t batch, float scale, void* staged,
+                        int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale, cudaStream_t st) {
+  const int64_t groups = stage_scale_count(d_pad);
+  dim3 grid((unsigned)groups, (unsigned)batch);
+  auto* dst = reinterpret_cast<uint16_t*>(staged);
+  if (stage_dtype == GADM_STAGE_F16G)
+    gadm::stage::stage_groups_kernel<T, true><<<grid, gadm::stage::kThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
+                                                                                      inv_scale, groups);
+  else
+    gadm::stage::stage_groups_kernel<T, false><<<grid, gadm::stage::kThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
+                                                                                       nullptr, groups);
+  GADM_LAUNCHED(h);
   return GADM_OK;
 }
 
@@ -328,7 +361,7 @@ int gadm_create(gadm_handle* out, int device) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  if (cudaMalloc(&h->scratch, 256) != cudaSuccess) {
+  if (cudaMalloc(&h->scratch, kLockstepSlots * sizeof(uint32_t)) != cudaSuccess) {
     delete h;
     return fail(GADM_ERR_CUDA, "cudaMalloc of the handle scratch failed");
   }
@@ -402,10 +435,59 @@ int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, in
   return GADM_OK;
 }
 
-int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t m_cap, int64_t p_base,
-                        int64_t proj_dim, uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate,
-                        void* workspace, int64_t workspace_bytes, int cta_group, void* stream) {
+int64_t gadm_stage_scale_count(int64_t d_pad) { return stage_scale_count(d_pad); }
+
+int gadm_stage_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
+                    void* staged, int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale,
+                    void* stream) {
+  GADM_REQUIRE(h && staged, "null argument");
+  GADM_REQUIRE(stage_dtype == GADM_STAGE_BF16 || stage_dtype == GADM_STAGE_F16G, "unknown stage_dtype %d", stage_dtype);
+  GADM_REQUIRE(stage_dtype == GADM_STAGE_BF16 || inv_scale, "the F16G staging format needs the inv_scale array");
+  GADM_REQUIRE(batch > 0 && batch < 65536 && d_pad > 0 && d_pad % 64 == 0 && row0 >= 0 && row0 + batch <= m_cap,
+               "bad staging geometry (batch %lld d_pad %lld m_cap %lld row0 %lld)", (long long)batch, (long long)d_pad,
+               (long long)m_cap, (long long)row0);
+  GADM_REQUIRE((reinterpret_cast<uintptr_t>(staged) & 127) == 0, "staging buffer must be 128-byte aligned");
+  static thread_local gadm::stage::BlockTable tab;  // 24 KiB: kept off the stack
+  GADM_TRY_RC(fill_block_table(blocks, n_blocks, batch, d_pad, &tab));
+  DeviceGuard guard(h->device);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == GADM_DTYPE_F32) return launch_stage<float>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, st);
+  if (dtype == GADM_DTYPE_BF16) return launch_stage<__nv_bfloat16>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, st);
+  if (dtype == GADM_DTYPE_F16) return launch_stage<__half>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, st);
+  return fail(GADM_ERR_INVALID, "unknown dtype %d", dtype);
+}
+
+int gadm_accumulate_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
+                         float* slab, int64_t d_pad, int64_t slab_rows, int64_t row0, int accumulate, void* stream) {
+  GADM_REQUIRE(h && slab, "null argument");
+  GADM_REQUIRE(batch > 0 && batch < 65536 && d_pad > 0 && d_pad % 64 == 0 && row0 >= 0 && row0 + batch <= slab_rows,
+               "bad slab geometry (batch %lld d_pad %lld rows %lld row0 %lld)", (long long)batch, (long long)d_pad,
+               (long long)slab_rows, (long long)row0);
+  GADM_REQUIRE((reinterpret_cast<uintptr_t>(slab) & 31) == 0, "slab must be 32-byte aligned");
+  static thread_local gadm::stage::BlockTable tab;
+  GADM_TRY_RC(fill_block_table(blocks, n_blocks, batch, d_pad, &tab));
+  DeviceGuard guard(h->device);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((unsigned)((d_pad + gadm::stage::kAccCols - 1) / gadm::stage::kAccCols), (unsigned)batch);
+  if (dtype == GADM_DTYPE_F32)
+    gadm::stage::accumulate_rows_kernel<float><<<grid, gadm::stage::kThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
+  else if (dtype == GADM_DTYPE_BF16)
+    gadm::stage::accumulate_rows_kernel<__nv_bfloat16><<<grid, gadm::stage::kThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
+  else if (dtype == GADM_DTYPE_F16)
+    gadm::stage::accumulate_rows_kernel<__half><<<grid, gadm::stage::kThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
+  else
+    return fail(GADM_ERR_INVALID, "unknown dtype %d", dtype);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_project_staged(gadm_handle h, const void* staged, int stage_dtype, const float* inv_scale, int64_t m_rows,
+                        int64_t d_pad, int64_t m_cap, int64_t p_base, int64_t proj_dim, uint64_t seed64, int proj_type,
+                        float* out, int64_t ld_out, int accumulate, void* workspace, int64_t workspace_bytes,
+                        int cta_group, void* stream) {
   GADM_REQUIRE(h && staged && out && workspace, "null argument");
+  GADM_REQUIRE(stage_dtype == GADM_STAGE_BF16 || stage_dtype == GADM_STAGE_F16G, "unknown stage_dtype %d", stage_dtype);
+  GADM_REQUIRE(stage_dtype == GADM_STAGE_BF16 || inv_scale, "the F16G staging format needs the inv_scale array");
   GADM_REQUIRE(proj_type == GADM_PROJ_NORMAL || proj_type == GADM_PROJ_RADEMACHER, "unknown proj_type %d", proj_type);
   GADM_REQUIRE(p_base >= 0 && p_base % 64 == 0, "p_base %lld must be a non-negative multiple of 64", (long long)p_base);
   GADM_REQUIRE(m_cap >= m_rows, "m_cap %lld must be >= m_rows %lld", (long long)m_cap, (long long)m_rows);
@@ -421,7 +503,8 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
   GADM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
   DeviceGuard guard(h->device);
   CUtensorMap tmap;
-  rc = make_tmap_staged(h, &tmap, staged, (uint64_t)m_cap, (uint64_t)(d_pad / gadm::proj::kBlockK));
+  rc = make_tmap_staged(h, &tmap, staged, (uint64_t)m_cap, (uint64_t)(d_pad / gadm::proj::kBlockK),
+                        stage_dtype == GADM_STAGE_F16G);
   if (rc != GADM_OK) return rc;
   gadm::proj::Args a;
   a.partial = reinterpret_cast<float*>(workspace);
@@ -440,6 +523,16 @@ int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64
   // GADM_PROJ_SEG_KB overrides for tuning.
   a.seg_kb = (proj_type == gadm::kProjRademacher) ? 512u : 256u;
   if (const char* e = getenv("GADM_PROJ_SEG_KB")) { const long v = atol(e); if (v >= 1) a.seg_kb = (uint32_t)v; }
+  a.m_rows = (uint32_t)m_rows;
+  a.a_fmt = (stage_dtype == GADM_STAGE_F16G) ? gadm::UMMA_FMT_F16 : gadm::UMMA_FMT_BF16;
+  a.inv_scale = (stage_dtype == GADM_STAGE_F16G) ? inv_scale : nullptr;
+  a.scale_groups = (uint32_t)gadm_stage_scale_count(d_pad);
+  a.group_kb = (uint32_t)gadm::stage::kGroupKb;
+  if (a.inv_scale) {
+    // a segment must not straddle two scale groups, and the scale groups are laid out from column 0 of the buffer
+    GADM_REQUIRE(a.group_kb % a.seg_kb == 0, "segment length %u does not divide the scale group (%u k-blocks)", a.seg_kb,
+                 a.group_kb);
+  }
   {
     const char* dbg = getenv("GADM_PROJ_DEBUG");  // perf ablation only; results are garbage when set
     a.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
@@ -1045,19 +1138,13 @@ int gadm_row_mean(gadm_handle h, const double* x, int64_t n, int64_t k, double* 
 // ------------------------------------------------------------------ composite entry points
 
 int gadm_project(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
-                 void* staged, int64_t d_pad, int64_t m_cap, int64_t proj_dim, uint64_t seed64, int proj_type, float* out,
-                 int64_t ld_out, int accumulate, void* workspace, int64_t workspace_bytes, int cta_group, void* stream) {
+                 void* staged, int stage_dtype, float* inv_scale, int64_t d_pad, int64_t m_cap, int64_t proj_dim,
+                 uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate, void* workspace,
+                 int64_t workspace_bytes, int cta_group, void* stream) {
   GADM_REQUIRE(h && blocks && n_blocks > 0 && staged && out && batch > 0, "bad argument");
-  for (int b = 0; b < n_blocks; ++b) {
-    const gadm_block& blk = blocks[b];
-    GADM_REQUIRE(blk.ptr && blk.numel_per_example > 0 && blk.row_offset >= 0 &&
-                     blk.row_offset + blk.numel_per_example <= d_pad,
-                 "block %d does not fit the staged gradient length %lld", b, (long long)d_pad);
-    GADM_TRY(gadm_pack_block(h, blk.ptr, dtype, batch, blk.numel_per_example, blk.example_stride, staged, d_pad, m_cap, 0,
-                             blk.row_offset, scale, stream));
-  }
-  return gadm_project_staged(h, staged, batch, d_pad, m_cap, 0, proj_dim, seed64, proj_type, out, ld_out, accumulate,
-                             workspace, workspace_bytes, cta_group, stream);
+  GADM_TRY(gadm_stage_rows(h, blocks, n_blocks, dtype, batch, scale, staged, stage_dtype, d_pad, m_cap, 0, inv_scale, stream));
+  return gadm_project_staged(h, staged, stage_dtype, inv_scale, batch, d_pad, m_cap, 0, proj_dim, seed64, proj_type, out,
+                             ld_out, accumulate, workspace, workspace_bytes, cta_group, stream);
 }
 
 int gadm_gram(gadm_handle h, const float* phi, int64_t n, int64_t k, int64_t ld_phi, float* phi_t_work, int64_t ld_t,

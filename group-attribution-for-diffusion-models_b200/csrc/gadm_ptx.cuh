@@ -242,6 +242,11 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// A and B formats may differ inside one kind (kind::f16: each of f16 / bf16)
+__host__ __device__ constexpr uint32_t umma_idesc_ab(uint32_t afmt, uint32_t bfmt, uint32_t M, uint32_t N) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 covers bf16/fp16 inputs, kind::tf32 fp32 inputs read as tf32
 template <int kCtaGroup>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

@@ -94,6 +94,11 @@ struct Args {
   uint32_t sync_iters;    // lockstep only while the cluster-local k-block counter is below this (multiple of sync_every)
   uint32_t sync_every;    // k-blocks between lockstep points
   uint32_t seg_kb;        // k-blocks accumulated in TMEM before the accumulators are promoted into the partial tile
+  uint32_t m_rows;        // staged rows in use (rows beyond it are never scaled nor reduced)
+  uint32_t a_fmt;         // UMMA format of the staged gradients: UMMA_FMT_BF16 or UMMA_FMT_F16 (P is always bf16)
+  const float* inv_scale; // F16G staging: [m_cap][scale_groups] inverse power-of-two scales (nullptr: unscaled)
+  uint32_t scale_groups;  // scale groups per row = ceil(nkb_total / group_kb)
+  uint32_t group_kb;      // k-blocks per scale group (multiple of seg_kb)
 };
 
 // Why segments: tcgen05 adds each MMA result into the fp32 TMEM accumulator with truncation.  Over a
@@ -105,9 +110,14 @@ struct Args {
 // load, so the accumulators are released after ~16 TMEM loads instead of an HBM round trip per 64 B.  One thread
 // owns an address for the whole launch and its st / red operations on it are ordered (same-thread, same
 // location), so the sum order is fixed and the result deterministic.
-__device__ __forceinline__ uint32_t num_segments(uint32_t kb0, uint32_t kb1, uint32_t seg_kb) {
-  return (kb1 - kb0 + seg_kb - 1) / seg_kb;
+// Segment boundaries lie on the GLOBAL k-block grid (multiples of seg_kb), not relative to the unit's first k-block:
+// the F16G staging format carries one scale per (row, group of group_kb k-blocks) and a segment must not straddle
+// two groups (group_kb % seg_kb == 0).  A unit's first and last segment may be short.
+__device__ __forceinline__ uint32_t seg_end(uint32_t seg0, uint32_t kb1, uint32_t seg_kb) {
+  const uint32_t e = (seg0 / seg_kb + 1) * seg_kb;
+  return e < kb1 ? e : kb1;
 }
+
 
 // The partial tiles in flight (one per cluster, 33-37 MB in total) are re-touched once per segment; in between the
 // gradient stream pushes them out of L2, so every segment costs a DRAM read + write of the tile.  An evict_last
@@ -157,10 +167,17 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 // instruction covers 4 rows x 128 contiguous bytes.
 constexpr int kEpiPitch = 144;
 constexpr int kEpiWarpBytes = 32 * kEpiPitch;
+// `scale` (nullable): inverse staging scale of this segment's group for row i * 4 + rr of the warp's 32 rows is
+// scale[(i * 4 + rr) * scale_ld]; rows >= rows_valid are not scaled (their partials are never reduced).
 __device__ __forceinline__ void drain_accumulator(uint32_t tmem_addr, float* __restrict__ dst_warp, bool first,
-                                                  uint32_t buf, int lane, uint64_t pol) {
+                                                  uint32_t buf, int lane, uint64_t pol, const float* __restrict__ scale,
+                                                  uint32_t scale_ld, int rows_valid) {
   const uint32_t my_row = buf + lane * kEpiPitch;
   const int rr = lane >> 3, cc = lane & 7;
+  float sc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    sc[i] = (scale != nullptr && i * 4 + rr < rows_valid) ? __ldg(scale + static_cast<size_t>(i * 4 + rr) * scale_ld) : 1.f;
 #pragma unroll 1
   for (int c = 0; c < kTileN; c += 32) {
     uint32_t v[32];
@@ -172,7 +189,11 @@ __device__ __forceinline__ void drain_accumulator(uint32_t tmem_addr, float* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = i * 4 + rr;
-      const uint4 w = ld_shared_v4(buf + row * kEpiPitch + cc * 16);
+      uint4 w = ld_shared_v4(buf + row * kEpiPitch + cc * 16);
+      if (scale != nullptr) {  // exact: the scales are powers of two
+        w.x = __float_as_uint(__uint_as_float(w.x) * sc[i]); w.y = __float_as_uint(__uint_as_float(w.y) * sc[i]);
+        w.z = __float_as_uint(__uint_as_float(w.z) * sc[i]); w.w = __float_as_uint(__uint_as_float(w.w) * sc[i]);
+      }
       float* g = dst_warp + static_cast<size_t>(row) * kTileN + c + cc * 4;
       if (first) st_global_v4_hint(g, w, pol);
       else red_add_v4(g, w, pol);
@@ -322,13 +343,13 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp == R::kMmaWarp) {
     // ===================== MMA issuer (leader CTA, one thread)
     if (rank == 0 && lane == 0) {
-      const uint32_t idesc = umma_idesc(UMMA_FMT_BF16, kAccRows * kCtaGroup, kTileN);
+      const uint32_t idesc = umma_idesc_ab(a.a_fmt, UMMA_FMT_BF16, kAccRows * kCtaGroup, kTileN);
       uint32_t it = 0, seg_iter = 0;
       for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
         const uint32_t split = u / a.n_tiles;
         const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
-        for (uint32_t seg0 = kb0; seg0 < kb1; seg0 += a.seg_kb, ++seg_iter) {
-          const uint32_t seg1 = (seg0 + a.seg_kb < kb1) ? seg0 + a.seg_kb : kb1;
+        for (uint32_t seg0 = kb0, seg1; seg0 < kb1; seg0 = seg1, ++seg_iter) {
+          seg1 = seg_end(seg0, kb1, a.seg_kb);
           if (seg_iter > 0) mbar_wait(tmem_empty_bar, (seg_iter - 1) & 1u, 0x200);
           tcgen05_fence_after();
           for (uint32_t kb = seg0; kb < seg1; ++kb, ++it) {
@@ -359,15 +380,18 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
     uint32_t seg_iter = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
       const uint32_t split = u / a.n_tiles;
-      const uint32_t nseg = num_segments(kb_begin(split), kb_begin(split + 1), a.seg_kb);
-      for (uint32_t seg = 0; seg < nseg; ++seg, ++seg_iter) {
+      const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
+      uint32_t seg = 0;
+      for (uint32_t seg0 = kb0; seg0 < kb1; seg0 = seg_end(seg0, kb1, a.seg_kb), ++seg, ++seg_iter) {
         mbar_wait<kEpiBackoffNs>(tmem_full_bar, seg_iter & 1u, 0x400);
         tcgen05_fence_after();
         for (uint32_t acc = 0; acc < a.n_acc; ++acc) {
           const uint32_t row = acc * (kAccRows * kCtaGroup) + rank * kAccRows + q * 32;
           float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
+          const float* sc = a.inv_scale ? a.inv_scale + static_cast<size_t>(row) * a.scale_groups + seg0 / a.group_kb : nullptr;
           drain_accumulator(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN, dst, seg == 0,
-                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane, pol);
+                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane, pol, sc, a.scale_groups,
+                            static_cast<int>(a.m_rows) - static_cast<int>(row));
         }
         tcgen05_fence_before();
         __syncwarp();

@@ -144,14 +144,14 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
     if (lane == 0) {
       if (rank == 0) {
         // ===================== MMA issuer of this pair
-        const uint32_t idesc = umma_idesc(UMMA_FMT_BF16, kAccRows * 2, kTileN);
+        const uint32_t idesc = umma_idesc_ab(a.a_fmt, UMMA_FMT_BF16, kAccRows * 2, kTileN);
         const uint16_t pair_mask = static_cast<uint16_t>(0x3u << leader4);
         uint32_t it = 0, seg_iter = 0;
         for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
           const uint32_t split = u / a.n_tiles;
           const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
-          for (uint32_t seg0 = kb0; seg0 < kb1; seg0 += a.seg_kb, ++seg_iter) {
-            const uint32_t seg1 = (seg0 + a.seg_kb < kb1) ? seg0 + a.seg_kb : kb1;
+          for (uint32_t seg0 = kb0, seg1; seg0 < kb1; seg0 = seg1, ++seg_iter) {
+            seg1 = seg_end(seg0, kb1, a.seg_kb);
             if (seg_iter > 0) mbar_wait(tmem_empty_bar, (seg_iter - 1) & 1u, 0x2200);
             tcgen05_fence_after();
             for (uint32_t kb = seg0; kb < seg1; ++kb, ++it) {
@@ -194,15 +194,18 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
     uint32_t seg_iter = 0;
     for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
       const uint32_t split = u / a.n_tiles;
-      const uint32_t nseg = num_segments(kb_begin(split), kb_begin(split + 1), a.seg_kb);
-      for (uint32_t seg = 0; seg < nseg; ++seg, ++seg_iter) {
+      const uint32_t kb0 = kb_begin(split), kb1 = kb_begin(split + 1);
+      uint32_t seg = 0;
+      for (uint32_t seg0 = kb0; seg0 < kb1; seg0 = seg_end(seg0, kb1, a.seg_kb), ++seg, ++seg_iter) {
         mbar_wait<kEpiBackoffNs>(tmem_full_bar, seg_iter & 1u, 0x2400);
         tcgen05_fence_after();
         for (uint32_t acc = 0; acc < kNumAcc; ++acc) {
           const uint32_t row = pair * pair_rows + acc * (kAccRows * 2) + rank * kAccRows + q * 32;
           float* dst = a.partial + (static_cast<size_t>(u) * a.unit_rows + row) * kTileN;
+          const float* sc = a.inv_scale ? a.inv_scale + static_cast<size_t>(row) * a.scale_groups + seg0 / a.group_kb : nullptr;
           drain_accumulator(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN, dst, seg == 0,
-                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane, pol);
+                            bar_base + C::kBarBytes + q * kEpiWarpBytes, lane, pol, sc, a.scale_groups,
+                            static_cast<int>(a.m_rows) - static_cast<int>(row));
         }
         tcgen05_fence_before();
         __syncwarp();

@@ -1,0 +1,215 @@
+// Gradient staging for the JL projection: per-example gradients (one tensor, or the dict of per-parameter
+// tensors that vmap(grad(f)) returns) -> the projection kernel's 16-bit tile-major staging buffer, in ONE launch
+// per batch, plus the fp32 timestep accumulator that precedes it.
+//
+// Replaces, on the reference's featurisation loop (src/attributions/methods/d_trak_grad.py:718-792,
+// text_to_image/grad_text_to_image_lora.py:773-814):
+//   vectorize_and_ignore_buffers (d_trak_grad.py:188-226: B x n_params flatten / cat launches + a B*D*4-byte copy),
+//   emb += grads per timestep and emb / K (d_trak_grad.py:764-770),
+//   the fp32 -> 16-bit conversion fast_jl performs inside project_*.
+//
+// Staging formats (include/gadm.h):
+//   GADM_STAGE_BF16  bf16(v), no scaling (round-1 format);
+//   GADM_STAGE_F16G  fp16(v * 2^s) with one power-of-two scale per (example row, group of 32768 columns), chosen so
+//                    that the group's largest magnitude lands in [2^13, 2^14): 11 significant bits instead of 8 and
+//                    no fp16 range problem (gradients span many decades between layers and examples).  The
+//                    projection kernel multiplies each accumulation segment by the inverse scale (an exact power
+//                    of two) when it promotes the TMEM accumulators, so results are independent of the scales up
+//                    to fp16 rounding of the inputs.  A group is the unit because a kernel segment (256 / 512
+//                    k-blocks) never crosses a group boundary.
+//
+// Bound: HBM.  Algorithmic bytes per staged element: sizeof(src) read + 2 written (the group is read twice --
+// absmax pass, convert pass -- but it is 128 KiB per CTA, so the second read hits L2).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace gadm {
+namespace stage {
+
+constexpr int kGroupKb = 512;                 // k-blocks (of 64 columns) per scale group
+constexpr int kGroupCols = kGroupKb * 64;     // 32768
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 1024;              // parameter blocks per launch (kernel-parameter space: 24 B each)
+
+// Parameter blocks of one example, sorted by position in the flattened gradient.  Entry i covers columns
+// [start[i], start[i + 1]); an entry with ptr == nullptr is a gap.  Gaps and columns >= start[n] are staged as zeros.
+struct BlockTable {
+  int32_t n;
+  int32_t pad;
+  int64_t start[kMaxBlocks + 1];  // start[n] = end of the last block
+  int64_t stride[kMaxBlocks];     // elements between consecutive examples of the block
+  const void* ptr[kMaxBlocks];
+};
+
+// index of the last block with start <= c (blocks are sorted); -1 if c lies before the first block
+__device__ __noinline__ int find_block(const BlockTable& t, int64_t c) {
+  int lo = 0, hi = t.n;  // invariant: start[lo - 1] <= c < start[hi] (with start[-1] = -inf)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t.start[mid] <= c) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p) { return static_cast<float>(*p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+// Walks the columns [c_lo, c_hi) of example `ex` eight at a time on the global column grid (c_lo % 64 == 0, so an octet
+// never straddles a 64-column row of the staging buffer): f(p, v[8]); columns no block covers read as 0.  Thread t
+// takes octets t, t + kThreads, ...; the block that held the previous octet is cached, the table is only searched
+// when an octet leaves it (~n_blocks times per row), and an octet that straddles a block boundary takes the
+// per-element path.  Values are returned unscaled.
+template <typename T>
+struct BlockCursor {
+  const BlockTable& tab;
+  int64_t ex;
+  int bi = -2;
+  int64_t lo = 0, hi = 0;  // cached block covers [lo, hi)
+  const T* base = nullptr;  // address of column lo of example ex
+  __device__ __forceinline__ BlockCursor(const BlockTable& t, int64_t e) : tab(t), ex(e) {}
+  __device__ __forceinline__ void seek(int64_t c) {
+    bi = find_block(tab, c);
+    if (bi >= 0 && tab.ptr[bi] != nullptr) {
+      lo = tab.start[bi];
+      hi = tab.start[bi + 1];
+      base = reinterpret_cast<const T*>(tab.ptr[bi]) + ex * tab.stride[bi];
+    } else {
+      lo = hi = -1;
+    }
+  }
+  __device__ __forceinline__ float at(int64_t c) {
+    if (!(c >= lo && c < hi)) seek(c);
+    return (c >= lo && c < hi) ? load_as_float(base + (c - lo)) : 0.f;
+  }
+  __device__ __forceinline__ void octet(int64_t p, float (&v)[8]) {
+    if (!(p >= lo && p < hi)) seek(p);
+    if (p >= lo && p + 8 <= hi) {
+      const T* s = base + (p - lo);
+      if (sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+        const float4 q0 = reinterpret_cast<const float4*>(s)[0], q1 = reinterpret_cast<const float4*>(s)[1];
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+      } else if (sizeof(T) == 2 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+        const uint4 q = *reinterpret_cast<const uint4*>(s);
+        const T* h = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = load_as_float(h + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = load_as_float(s + i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = at(p + i);  // straddles a block boundary or a gap (rare)
+    }
+  }
+};
+
+__device__ __forceinline__ float block_max(float v, float* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = smem[0];
+#pragma unroll
+  for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, smem[w]);
+  return m;
+}
+
+// scale exponent for a group whose largest magnitude is amax: amax * 2^s in [2^13, 2^14); clamped so that both
+// 2^s and 2^-s are normal fp32 numbers.  amax == 0 (or NaN / Inf, which then propagate) -> s = 0.
+__device__ __forceinline__ int group_scale_exponent(float amax) {
+  if (!(amax > 0.f) || !(amax < __int_as_float(0x7f800000))) return 0;
+  int e = static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu) - 127;  // floor(log2(amax)) for normal amax
+  if (e < -100) e = -100;
+  if (e > 100) e = 100;
+  return 13 - e;
+}
+__device__ __forceinline__ float exp2_int(int s) { return __uint_as_float(static_cast<uint32_t>(s + 127) << 23); }
+
+// grid = (groups, batch).  CTA (g, b) stages columns [g * 32768, ...) of example b into row row0 + b.
+// v * scale is formed once (pass 2): |.| and the rounding of a product by a constant are monotonic, so the group
+// maximum of |v * scale| is |max|v| * scale|, and 2^s is folded into the multiplier (exact).
+template <typename T, bool kF16>
+__global__ void __launch_bounds__(kThreads)
+stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
+                    int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
+  __shared__ float red[kThreads / 32];
+  const int64_t g = blockIdx.x, b = blockIdx.y;
+  const int64_t row = row0 + b;
+  const int64_t c_lo = g * kGroupCols;
+  const int64_t c_hi = (c_lo + kGroupCols < d_pad) ? c_lo + kGroupCols : d_pad;
+  BlockCursor<T> cur(tab, b);
+  float mul = scale;
+  if constexpr (kF16) {
+    float amax = 0.f;
+    for (int64_t p = c_lo + 8 * threadIdx.x; p < c_hi; p += 8 * kThreads) {
+      float v[8];
+      cur.octet(p, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));  // NaNs are skipped here and stored as NaN below
+    }
+    amax = block_max(amax, red) * fabsf(scale);
+    const int s = group_scale_exponent(amax);
+    mul = scale * exp2_int(s);  // exact unless it leaves the normal range, which the exponent clamp excludes for
+                                // |scale| in [2^-20, 2^20]
+    if (threadIdx.x == 0) inv_scale[row * groups_per_row + g] = exp2_int(-s);
+  }
+  uint16_t* drow = dst + row * 64;
+  for (int64_t p = c_lo + 8 * threadIdx.x; p < c_hi; p += 8 * kThreads) {
+    float v[8];
+    cur.octet(p, v);
+    uint4 out;
+    uint32_t* o = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (kF16) {
+        const __half2 h = __floats2half2_rn(__fmul_rn(v[2 * i], mul), __fmul_rn(v[2 * i + 1], mul));  // |.| < 2^14
+        o[i] = *reinterpret_cast<const uint32_t*>(&h);
+      } else {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(__fmul_rn(v[2 * i], mul), __fmul_rn(v[2 * i + 1], mul));
+        o[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    *reinterpret_cast<uint4*>(drow + (p >> 6) * (m_cap * 64) + (p & 63)) = out;
+  }
+}
+
+// Timestep accumulator: slab[row0 + b, p] = (accumulate ? slab : 0) + scale * src   (fp32 slab [rows][d_pad]).
+// grid = (ceil(d_pad / 8192), batch)
+constexpr int kAccCols = 8192;
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+accumulate_rows_kernel(const __grid_constant__ BlockTable tab, float* __restrict__ slab, int64_t d_pad, int64_t row0,
+                       float scale, int accumulate) {
+  const int64_t b = blockIdx.y;
+  const int64_t c_lo = static_cast<int64_t>(blockIdx.x) * kAccCols;
+  const int64_t c_hi = (c_lo + kAccCols < d_pad) ? c_lo + kAccCols : d_pad;
+  float* out = slab + (row0 + b) * d_pad;
+  BlockCursor<T> cur(tab, b);
+  for (int64_t p = c_lo + 8 * threadIdx.x; p < c_hi; p += 8 * kThreads) {
+    float v[8];
+    cur.octet(p, v);
+    float4* o = reinterpret_cast<float4*>(out + p);  // d_pad % 64 == 0 and p % 8 == 0: 32-byte aligned
+    // separate round-to-nearest multiply and add (no FMA contraction): bit-identical to emb += grads * scale in fp32
+    float4 r0 = make_float4(__fmul_rn(v[0], scale), __fmul_rn(v[1], scale), __fmul_rn(v[2], scale), __fmul_rn(v[3], scale));
+    float4 r1 = make_float4(__fmul_rn(v[4], scale), __fmul_rn(v[5], scale), __fmul_rn(v[6], scale), __fmul_rn(v[7], scale));
+    if (accumulate) {
+      const float4 a0 = o[0], a1 = o[1];
+      r0.x = __fadd_rn(a0.x, r0.x); r0.y = __fadd_rn(a0.y, r0.y); r0.z = __fadd_rn(a0.z, r0.z); r0.w = __fadd_rn(a0.w, r0.w);
+      r1.x = __fadd_rn(a1.x, r1.x); r1.y = __fadd_rn(a1.y, r1.y); r1.z = __fadd_rn(a1.z, r1.z); r1.w = __fadd_rn(a1.w, r1.w);
+    }
+    o[0] = r0;
+    o[1] = r1;
+  }
+}
+
+}  // namespace stage
+}  // namespace gadm

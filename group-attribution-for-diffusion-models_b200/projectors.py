@@ -14,15 +14,25 @@ function of ``seed + 10**4 * model_id`` and is not scaled by 1/sqrt(k).  Differe
 * ``project`` also accepts the *dict / list of per-parameter gradient tensors* that
   ``torch.func.vmap(grad(f))`` returns, so ``vectorize_and_ignore_buffers``
   (``d_trak_grad.py:188-226``) and its extra B*D*4-byte copy can be dropped;
-* ``deferred()`` stages up to 512 (Rademacher) / 1024 (normal) examples (bf16 rows in HBM) and projects them
-  in one pass, which is what makes the tensor cores, not the random-number generation, the bound.
+* ``deferred()`` stages up to 512 (Rademacher) / 1024 (normal) examples (16-bit rows in HBM) and projects them
+  in one pass, which is what makes the tensor cores, not the random-number generation, the bound (DESIGN.md);
+  ``DeferredProjection.accumulate`` sums the K timestep gradients of a batch into an fp32 slab with the 1/K mean
+  folded in (``d_trak_grad.py:764-770``) and stages the batch on the last timestep, and with ``overlap`` the
+  projection pass of one staged batch runs on a side stream while the next batch is being staged.
+
+Numerics that differ from an fp32-input projection and are stated here on purpose: the gradients are rounded to 16
+bits before the tensor-core GEMM -- fp16 with a power-of-two scale per (example, 32768-column group) by default
+(``stage_dtype="f16"``: 11 significant bits, relative feature error ~2e-4), or plain bf16 (``"bf16"``: 8 bits,
+~1.6e-3) -- and the normal-type P is a bf16-rounded Box-Muller matrix.  Accumulation is fp32.
 
 There is no CPU path: a non-CUDA device raises ``ValueError`` exactly like upstream's CudaProjector.
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from enum import Enum
-from typing import Iterable, Mapping, Sequence, Union
+from typing import Mapping, Sequence, Union
 
 import torch
 
@@ -33,6 +43,8 @@ MAX_STAGE_ROWS = 512
 TILE_K = 64
 
 _DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_STAGE_CODES = {"bf16": 0, "f16": 1}          # GADM_STAGE_BF16 / GADM_STAGE_F16G (include/gadm.h)
+_STAGE_TORCH = {"bf16": torch.bfloat16, "f16": torch.float16}
 
 GradsLike = Union[torch.Tensor, Mapping[str, torch.Tensor], Sequence[torch.Tensor]]
 
@@ -68,15 +80,29 @@ def _as_blocks(grads: GradsLike):
     bsz = out[0].shape[0]
     if any(b.shape[0] != bsz for b in out):
         raise ValueError("all gradient blocks must share the batch dimension")
+    if len({b.dtype for b in out}) > 1:  # one launch converts one source dtype
+        out = [b.float() for b in out]
     return out
 
 
+class _Stage:
+    """One staging buffer: 16-bit tile-major gradients [d_pad / 64][m_cap][64] (+ the F16G inverse scales)."""
+
+    def __init__(self, projector: "CudaProjector", rows: int):
+        p = projector
+        self.rows = rows
+        self.data = torch.zeros(p.d_pad // TILE_K, rows, TILE_K, dtype=_STAGE_TORCH[p.stage_dtype], device=p.device)
+        self.inv_scale = (torch.ones(rows, p.scale_groups, dtype=torch.float32, device=p.device)
+                          if p.stage_dtype == "f16" else None)
+        self.done = None  # event of the last projection pass that read this buffer (overlap mode)
+
+
 class CudaProjector:
-    """``trak.projectors.CudaProjector`` signature over ``gadm_project_staged``."""
+    """``trak.projectors.CudaProjector`` signature over ``gadm_stage_rows`` + ``gadm_project_staged``."""
 
     def __init__(self, grad_dim: int, proj_dim: int, seed: int, proj_type: ProjectionType,
                  device, max_batch_size: int = 32, *args, stage_rows: int | None = None, cta_group: int | None = None,
-                 **kwargs) -> None:
+                 stage_dtype: str | None = None, **kwargs) -> None:
         self.grad_dim = int(grad_dim)
         self.proj_dim = int(proj_dim)
         self.seed = int(seed)
@@ -101,6 +127,11 @@ class CudaProjector:
             raise ValueError(f"proj_dim must be a positive multiple of 512 (got {self.proj_dim})")
         if self.grad_dim <= 0:
             raise ValueError("grad_dim must be positive")
+        if stage_dtype is None:
+            stage_dtype = os.environ.get("GADM_STAGE_DTYPE", "f16")
+        if stage_dtype not in _STAGE_CODES:
+            raise ValueError(f"stage_dtype must be 'f16' or 'bf16', got {stage_dtype!r}")
+        self.stage_dtype = stage_dtype
         # kernel variant: 2 = one tcgen05 CTA pair per unit (512 rows per pass); 4 = two pairs per cluster sharing the
         # generated P tiles (1024 rows per pass) -- halves the Box-Muller work that bounds the normal type.
         if cta_group is None:
@@ -108,24 +139,35 @@ class CudaProjector:
         self.cta_group = int(cta_group)
         self.d_pad = -(-self.grad_dim // TILE_K) * TILE_K
         self._handle = _lib.get_handle(device)
+        self.scale_groups = int(self._handle.lib.gadm_stage_scale_count(self.d_pad))
         self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
         max_rows = 256 * self.cta_group
         if stage_rows is None:
-            total = torch.cuda.get_device_properties(device).total_memory
+            # largest pass that leaves a fifth of the free HBM to the caller (C3: D = 274 M -> 256 rows = 140 GB)
+            free, _ = torch.cuda.mem_get_info(device)
             stage_rows = max_rows
-            while stage_rows > 128 and stage_rows * self.d_pad * 2 > 0.45 * total:
+            while stage_rows > 128 and stage_rows * self.d_pad * 2 > 0.8 * free:
                 stage_rows //= 2
         self.stage_rows = int(min(max(int(stage_rows), 1), max_rows))
-        self._stage = None
+        self._stages: list[_Stage] = []
         self._ws = None
+        self._slab = None
+        self._side = None
+        self._owner = None  # the DeferredProjection that has rows pending in the staging buffers
 
     # ------------------------------------------------------------------ buffers
+    def _stage(self, rows: int, index: int = 0) -> _Stage:
+        while len(self._stages) <= index:
+            self._stages.append(None)
+        st = self._stages[index]
+        if st is None or st.rows < rows:
+            self._stages[index] = None
+            st = self._stages[index] = _Stage(self, rows)
+        return st
+
     def _stage_buffer(self, rows: int) -> torch.Tensor:
-        """bf16 staging buffer in the kernel's tile-major layout [d_pad / 64][m_cap][64] (include/gadm.h)."""
-        if self._stage is None or self._stage.shape[1] < rows:
-            self._stage = None
-            self._stage = torch.zeros(self.d_pad // TILE_K, rows, TILE_K, dtype=torch.bfloat16, device=self.device)
-        return self._stage
+        """The first staging buffer's data tensor [d_pad / 64][m_cap][64] (tests and bench fill it directly)."""
+        return self._stage(rows).data
 
     def _group_for(self, rows: int) -> int:
         """cta_group 4 (two CTA pairs sharing the generated P tiles) only pays when both pairs have rows."""
@@ -139,41 +181,75 @@ class CudaProjector:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def _check_free(self, who) -> None:
+        if self._owner is not None and self._owner is not who:
+            raise RuntimeError("a DeferredProjection of this projector still has staged rows that were not projected; "
+                               "call its flush() / result() first (the staging buffers are shared)")
+
     def free_memory(self) -> None:
         """trak AbstractProjector.free_memory."""
-        self._stage = None
+        self._check_free(None)
+        self._stages = []
         self._ws = None
+        self._slab = None
 
     # ------------------------------------------------------------------ kernels
-    def _pack(self, blocks, stage: torch.Tensor, row0: int, scale: float = 1.0) -> int:
-        bsz = blocks[0].shape[0]
+    def _block_table(self, blocks):
         total = sum(b.shape[1] for b in blocks)
         if total != self.grad_dim:
             raise ValueError(f"gradient has {total} entries per example, projector was built for {self.grad_dim}")
-        lib, h, st = self._handle.lib, self._handle.ptr, _lib.stream_ptr(self.device)
-        col = 0
+        bsz = blocks[0].shape[0]
+        live = [b for b in blocks if b.shape[1] > 0]
+        arr = (_lib.Block * len(live))()
+        col, i = 0, 0
         for b in blocks:
             if b.device != self.device:
                 raise ValueError(f"gradients live on {b.device}, projector on {self.device}")
             numel = b.shape[1]
             if numel == 0:
                 continue
-            _lib.check(lib.gadm_pack_block(h, b.data_ptr(), _DTYPES[b.dtype], bsz, numel, b.stride(0) if bsz > 1 else numel,
-                                          stage.data_ptr(), self.d_pad, stage.shape[1], row0, col, float(scale), st))
+            arr[i] = _lib.Block(b.data_ptr(), numel, b.stride(0) if bsz > 1 else numel, col)
             col += numel
+            i += 1
+        return arr, len(live), _DTYPES[blocks[0].dtype], bsz
+
+    def _pack(self, blocks, stage: _Stage, row0: int, scale: float = 1.0) -> int:
+        """Stage a batch (all parameter blocks in one launch) into rows row0.. of `stage`."""
+        arr, n, dtype, bsz = self._block_table(blocks)
+        lib, h = self._handle.lib, self._handle.ptr
+        _lib.check(lib.gadm_stage_rows(h, arr, n, dtype, bsz, float(scale), stage.data.data_ptr(),
+                                       _STAGE_CODES[self.stage_dtype], self.d_pad, stage.rows, row0,
+                                       stage.inv_scale.data_ptr() if stage.inv_scale is not None else None,
+                                       _lib.stream_ptr(self.device)))
         return bsz
 
-    def _project_rows(self, stage: torch.Tensor, rows: int, model_id: int, out: torch.Tensor) -> None:
+    def _accumulate(self, blocks, slab: torch.Tensor, scale: float, accumulate: bool) -> None:
+        arr, n, dtype, bsz = self._block_table(blocks)
+        _lib.check(self._handle.lib.gadm_accumulate_rows(self._handle.ptr, arr, n, dtype, bsz, float(scale),
+                                                        slab.data_ptr(), self.d_pad, slab.shape[0], 0, int(accumulate),
+                                                        _lib.stream_ptr(self.device)))
+
+    def _project_rows(self, stage, rows: int, model_id: int, out: torch.Tensor) -> None:
+        """One projection pass over the first `rows` staged rows, on the current stream."""
+        if isinstance(stage, torch.Tensor):  # the data tensor of buffer 0 (tests / bench fill it directly)
+            stage = next(s for s in self._stages if s is not None and s.data.data_ptr() == stage.data_ptr())
         ws = self._workspace(rows)
         seed64 = (self.seed + SEED_MODEL_ID_STRIDE * int(model_id)) & 0xFFFFFFFFFFFFFFFF
         _lib.check(self._handle.lib.gadm_project_staged(
-            self._handle.ptr, stage.data_ptr(), rows, self.d_pad, stage.shape[1], 0, self.proj_dim, seed64,
-            _PROJ_CODE[self.proj_type], out.data_ptr(), out.stride(0), 0, ws.data_ptr(), ws.numel(),
+            self._handle.ptr, stage.data.data_ptr(), _STAGE_CODES[self.stage_dtype],
+            stage.inv_scale.data_ptr() if stage.inv_scale is not None else None, rows, self.d_pad, stage.rows, 0,
+            self.proj_dim, seed64, _PROJ_CODE[self.proj_type], out.data_ptr(), out.stride(0), 0, ws.data_ptr(), ws.numel(),
             self._group_for(rows), _lib.stream_ptr(self.device)))
 
     # ------------------------------------------------------------------ reference API
     def project(self, grads: GradsLike, model_id: int) -> torch.Tensor:
         """[B, grad_dim] (or per-parameter blocks) -> [B, proj_dim]; returns immediately-usable values."""
+        self._check_free(None)
         blocks = _as_blocks(grads)
         bsz = blocks[0].shape[0]
         in_dtype = blocks[0].dtype
@@ -182,14 +258,16 @@ class CudaProjector:
         with torch.cuda.device(self.device):
             for r0 in range(0, bsz, cap):
                 r1 = min(bsz, r0 + cap)
-                stage = self._stage_buffer(min(cap, max(r1 - r0, min(self.max_batch_size, cap))))
+                stage = self._stage(min(cap, max(r1 - r0, min(self.max_batch_size, cap))))
                 self._pack([b[r0:r1] for b in blocks], stage, 0)
                 self._project_rows(stage, r1 - r0, model_id, out[r0:r1])
         return out if in_dtype == torch.float32 else out.to(in_dtype)
 
-    def deferred(self, model_id: int = 0) -> "DeferredProjection":
-        """Stage examples in HBM and project ``stage_rows`` of them per kernel pass."""
-        return DeferredProjection(self, model_id)
+    def deferred(self, model_id: int = 0, overlap: bool | None = None) -> "DeferredProjection":
+        """Stage examples in HBM and project ``stage_rows`` of them per kernel pass.  ``overlap``: run the passes on a
+        side stream against a second staging buffer so that staging the next batch (and whatever produces it) is
+        not serialised behind the projection; ``None`` = when a second buffer fits in the free HBM."""
+        return DeferredProjection(self, model_id, overlap)
 
     def materialize(self, row0: int, nrows: int, model_id: int = 0) -> torch.Tensor:
         """P[row0:row0+nrows, :] as fp32 -- the kernel's own matrix (test / oracle hook)."""
@@ -205,17 +283,27 @@ class CudaProjector:
 class DeferredProjection:
     """Context manager returned by ``CudaProjector.deferred``.
 
-    ``add(grads, scale)`` appends a batch (tensor or per-parameter blocks; ``scale`` folds e.g. the
-    1/K timestep mean of ``d_trak_grad.py:770``); ``accumulate(grads, scale)`` adds into the rows of
-    the *last added* batch is not supported in bf16 staging -- sum timesteps in fp32 first.
-    ``result()`` returns the [N, proj_dim] fp32 features in insertion order, device resident.
-    """
+    ``add(grads, scale)`` appends a batch (tensor or per-parameter blocks; ``scale`` folds e.g. the 1/K timestep mean
+    of ``d_trak_grad.py:770``).  ``accumulate(grads, scale, last)`` is the featurisation loop's timestep sum
+    (``d_trak_grad.py:757-770``, ``grad_text_to_image_lora.py:804-812``): every call adds ``scale * grads`` of the
+    *current* batch into an fp32 slab, and ``last=True`` stages the summed batch -- no ``[B, D]`` torch temporaries,
+    no ``vectorize_and_ignore_buffers``.  ``result()`` returns the [N, proj_dim] fp32 features in insertion order,
+    device resident (replaces the per-batch ``.cpu()`` of ``d_trak_grad.py:792``)."""
 
-    def __init__(self, projector: CudaProjector, model_id: int):
+    def __init__(self, projector: CudaProjector, model_id: int, overlap: bool | None = None):
         self.p = projector
         self.model_id = model_id
         self.rows = 0
+        self.cur = 0
         self.outputs: list[torch.Tensor] = []
+        self._acc_rows = 0  # batch size of the timestep sum in progress (0: none)
+        if overlap is None:
+            need = projector.stage_rows * projector.d_pad * 2
+            have_second = len(projector._stages) > 1 and projector._stages[1] is not None
+            free, _ = torch.cuda.mem_get_info(projector.device)
+            first = 0 if projector._stages and projector._stages[0] is not None else need
+            overlap = have_second or free > first + need + (16 << 30)
+        self.overlap = bool(overlap)
 
     def __enter__(self):
         return self
@@ -223,36 +311,97 @@ class DeferredProjection:
     def __exit__(self, exc_type, exc, tb):
         if exc_type is None:
             self.flush()
+        else:  # give the buffers back without projecting half-staged work
+            self.rows = self._acc_rows = 0
+            if self.p._owner is self:
+                self.p._owner = None
         return False
 
+    def _claim(self):
+        self.p._check_free(self)
+        self.p._owner = self
+
     def add(self, grads: GradsLike, scale: float = 1.0) -> None:
-        blocks = _as_blocks(grads)
+        if self._acc_rows:
+            raise RuntimeError("add() while a timestep sum is in progress; finish it with accumulate(..., last=True)")
+        self._claim()
+        self._stage_blocks(_as_blocks(grads), scale)
+
+    def _stage_blocks(self, blocks, scale: float) -> None:
         bsz = blocks[0].shape[0]
         cap = self.p.stage_rows
         done = 0
         with torch.cuda.device(self.p.device):
             while done < bsz:
                 take = min(bsz - done, cap - self.rows)
-                stage = self.p._stage_buffer(cap)
+                stage = self.p._stage(cap, self.cur)
                 self.p._pack([b[done:done + take] for b in blocks], stage, self.rows, scale)
                 self.rows += take
                 done += take
                 if self.rows == cap:
                     self.flush()
 
+    def accumulate(self, grads: GradsLike, scale: float = 1.0, last: bool = False) -> None:
+        blocks = _as_blocks(grads)
+        bsz = blocks[0].shape[0]
+        p = self.p
+        self._claim()
+        if self._acc_rows and self._acc_rows != bsz:
+            raise ValueError(f"timestep sum in progress holds {self._acc_rows} examples, got a batch of {bsz}")
+        if p._slab is None or p._slab.shape[0] < bsz:
+            p._slab = None
+            p._slab = torch.empty(bsz, p.d_pad, dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            p._accumulate(blocks, p._slab, scale, accumulate=self._acc_rows > 0)
+        self._acc_rows = bsz
+        if last:
+            self._acc_rows = 0
+            slab = p._slab[:bsz]
+            self._stage_blocks([slab[:, :p.grad_dim]], 1.0)
+
     def flush(self) -> None:
+        if self._acc_rows:
+            raise RuntimeError("flush() while a timestep sum is in progress; finish it with accumulate(..., last=True)")
         if self.rows == 0:
+            if self.p._owner is self:
+                self.p._owner = None
             return
-        out = torch.empty(self.rows, self.p.proj_dim, dtype=torch.float32, device=self.p.device)
-        with torch.cuda.device(self.p.device):
-            self.p._project_rows(self.p._stage_buffer(self.p.stage_rows), self.rows, self.model_id, out)
+        p = self.p
+        stage = p._stage(p.stage_rows, self.cur)
+        out = torch.empty(self.rows, p.proj_dim, dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            if not self.overlap:
+                p._project_rows(stage, self.rows, self.model_id, out)
+            else:
+                main = torch.cuda.current_stream(p.device)
+                side = p._side_stream()
+                staged = torch.cuda.Event()
+                staged.record(main)
+                side.wait_event(staged)
+                with torch.cuda.stream(side):
+                    p._workspace(self.rows)  # allocated (once) under the side stream
+                    p._project_rows(stage, self.rows, self.model_id, out)
+                    stage.done = torch.cuda.Event()
+                    stage.done.record(side)
+                out.record_stream(side)
+                self.cur ^= 1
+                nxt = p._stage(p.stage_rows, self.cur)
+                if nxt.done is not None:  # the pass that last read the other buffer must be over before it is refilled
+                    main.wait_event(nxt.done)
         self.outputs.append(out)
         self.rows = 0
+        p._owner = None
 
     def result(self) -> torch.Tensor:
         self.flush()
+        p = self.p
+        if self.overlap:
+            main = torch.cuda.current_stream(p.device)
+            for st in p._stages:
+                if st is not None and st.done is not None:
+                    main.wait_event(st.done)
         if not self.outputs:
-            return torch.empty(0, self.p.proj_dim, dtype=torch.float32, device=self.p.device)
+            return torch.empty(0, p.proj_dim, dtype=torch.float32, device=p.device)
         return self.outputs[0] if len(self.outputs) == 1 else torch.cat(self.outputs, dim=0)
 
 

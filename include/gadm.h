@@ -8,11 +8,14 @@
  * A handle belongs to one (process, device); it is not thread-safe, distinct handles are.
  *
  * Reference interfaces replaced (paths relative to the reference repository):
- *   gadm_pack_block / gadm_project_staged / gadm_materialize_p
+ *   gadm_stage_rows / gadm_pack_block / gadm_project_staged / gadm_project / gadm_materialize_p
  *       trak.projectors.CudaProjector(...).project(grads, model_id)  -> fast_jl.project_*  (third-party,
  *       requirements.txt:10-11); call sites src/attributions/methods/d_trak_grad.py:504-511,776 and
  *       text_to_image/grad_text_to_image_lora.py:561-568,765,813; vectorize_and_ignore_buffers
- *       (d_trak_grad.py:188-226) is subsumed by per-block packing.
+ *       (d_trak_grad.py:188-226) is subsumed by the block table of gadm_stage_rows.
+ *   gadm_accumulate_rows
+ *       the timestep sum and mean of the featurisation loop: emb += grads, emb / K (d_trak_grad.py:764-770,
+ *       grad_text_to_image_lora.py:808-812).
  *   gadm_gemm_tn / gadm_gram / gadm_cholesky / gadm_tri_inverse / gadm_solve_rows / gadm_score /
  *   gadm_transpose / gadm_row_norms / gadm_col_mean_scaled
  *       text_to_image/traks.py:141-186 (torch.matmul / torch.inverse / norms / mean) and
@@ -42,6 +45,15 @@ typedef struct gadm_ctx* gadm_handle;
 
 enum { GADM_PROJ_NORMAL = 0, GADM_PROJ_RADEMACHER = 1 };
 enum { GADM_DTYPE_F32 = 0, GADM_DTYPE_BF16 = 1, GADM_DTYPE_F16 = 2 };
+/* 16-bit formats of the staged gradients (the A operand of the projection GEMM):
+ *   GADM_STAGE_BF16  bf16(v): 8 significant bits, no scaling.
+ *   GADM_STAGE_F16G  fp16(v * 2^s), one power-of-two scale per (example row, group of GADM_STAGE_GROUP_COLS columns)
+ *                    chosen so that the group's largest magnitude lands in [2^13, 2^14): 11 significant bits and no
+ *                    fp16 range problem.  The inverse scales live in a caller-owned fp32 array
+ *                    inv_scale[m_cap][gadm_stage_scale_count(d_pad)] written by gadm_stage_rows and read by
+ *                    gadm_project_staged (multiplied in, exactly, when accumulation segments are promoted). */
+enum { GADM_STAGE_BF16 = 0, GADM_STAGE_F16G = 1 };
+#define GADM_STAGE_GROUP_COLS 32768
 enum {
   GADM_OK = 0,
   GADM_ERR_INVALID = -1,   /* bad argument (shape, alignment, enum) */
@@ -66,29 +78,62 @@ int gadm_set_watchdog_ns(gadm_handle h, uint64_t ns);
 /* Bytes of scratch gadm_project_staged needs for split-K partial tiles. */
 int64_t gadm_project_workspace_bytes(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_dim, int cta_group);
 
-/* Staging buffer layout (bf16): staged[kb][row][c] with kb = p / 64, c = p % 64, i.e. a contiguous
+/* Staging buffer layout (16-bit elements): staged[kb][row][c] with kb = p / 64, c = p % 64, i.e. a contiguous
  * [d_pad / 64][m_cap][64] array, 128-byte aligned.  p is the position in the flattened gradient, row the example.
- * Tile-major so that the 128-row x 64-column tiles the kernel streams are contiguous in HBM.
- *
- * Convert one gradient block to bf16 inside the staging buffer.
+ * Tile-major so that the 128-row x 64-column tiles the kernel streams are contiguous in HBM. */
+
+/* One parameter block of a batch of per-example gradients (what vmap(grad(f)) returns per parameter):
+ *   ptr                 device pointer to [batch, numel_per_example] elements of `dtype`
+ *   example_stride      elements between consecutive examples
+ *   row_offset          position of the block's first element in the flattened gradient (= row of P) */
+typedef struct {
+  const void* ptr;
+  int64_t numel_per_example;
+  int64_t example_stride;
+  int64_t row_offset;
+} gadm_block;
+
+/* scale groups per staged row = ceil(d_pad / GADM_STAGE_GROUP_COLS) */
+int64_t gadm_stage_scale_count(int64_t d_pad);
+
+/* Stage a batch of examples in ONE launch: rows row0 .. row0 + batch of the staging buffer receive
+ * convert(src * scale) for every column; `blocks` (host array, sorted by row_offset, non-overlapping, at most 1024)
+ * lists the parameter blocks, columns no block covers (gaps, the tail up to d_pad) are written as zeros.
+ * scale = 1/K folds the timestep mean (d_trak_grad.py:770).  inv_scale: see GADM_STAGE_F16G (NULL for bf16). */
+int gadm_stage_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
+                    void* staged, int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale,
+                    void* stream);
+
+/* Timestep accumulator: slab[row0 + b, p] = (accumulate ? slab[row0 + b, p] : 0) + scale * src  for an fp32 slab
+ * [slab_rows][d_pad] (32-byte aligned).  Sum K timesteps with scale = 1/K, then stage the slab rows with
+ * gadm_stage_rows (one fp32 block {slab, d_pad, d_pad, 0}).  Replaces emb += grads / emb / K of d_trak_grad.py:764-770
+ * without the flatten / cat of vectorize_and_ignore_buffers. */
+int gadm_accumulate_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
+                         float* slab, int64_t d_pad, int64_t slab_rows, int64_t row0, int accumulate, void* stream);
+
+/* Convert one gradient block to bf16 inside a GADM_STAGE_BF16 staging buffer (per-block form of gadm_stage_rows).
  *   src: [batch, numel] of `dtype`, consecutive examples `src_stride` elements apart
  *   block lands at rows row0..row0+batch, positions col0..col0+numel of the flattened gradient
- *   the value written is bf16(src * scale)  (scale = 1/K folds the timestep mean, d_trak_grad.py:770) */
+ *   the value written is bf16(src * scale); positions no call writes must have been zeroed by the caller */
 int gadm_pack_block(gadm_handle h, const void* src, int dtype, int64_t batch, int64_t numel, int64_t src_stride,
                     void* staged, int64_t d_pad, int64_t m_cap, int64_t row0, int64_t col0, float scale, void* stream);
 
 /* out[m, :] (+)= G[m, :] * P[p_base : p_base + d_pad, 0:proj_dim]  for the first m_rows rows of the staging buffer
- *   staged: layout above; d_pad % 64 == 0; positions beyond the real gradient length must be zero;
- *           rows >= m_rows may hold anything (they only feed output rows that are never written)
+ *   staged: layout above, format stage_dtype (+ inv_scale for GADM_STAGE_F16G); d_pad % 64 == 0; positions beyond the
+ *           real gradient length must be zero; rows >= m_rows may hold anything (they only feed output rows that are
+ *           never written)
  *   m_rows <= 512 (256 for cta_group 1, 1024 for cta_group 4), m_cap >= m_rows
  *   p_base: canonical index (row of P) of position 0, multiple of 64
  *   proj_dim % 256 == 0; seed64 = seed + 10^4 * model_id (CudaProjector semantics)
  *   out: fp32 [m_rows, proj_dim] with pitch ld_out; accumulate != 0 adds to out (D-chunked projection)
  *   cta_group: 2 (CTA-pair UMMA, default), 1 (single CTA), or 4 = two CTA pairs per cluster that share the
- *              generated P tiles through DSMEM bulk copies (halves the generator work; up to 1024 rows) */
-int gadm_project_staged(gadm_handle h, const void* staged, int64_t m_rows, int64_t d_pad, int64_t m_cap, int64_t p_base,
-                        int64_t proj_dim, uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate,
-                        void* workspace, int64_t workspace_bytes, int cta_group, void* stream);
+ *              generated P tiles through DSMEM bulk copies (halves the generator work; up to 1024 rows)
+ *   Launches in flight on different streams of one device are independent (each takes its own lockstep counter);
+ *   the handle itself is still not thread-safe. */
+int gadm_project_staged(gadm_handle h, const void* staged, int stage_dtype, const float* inv_scale, int64_t m_rows,
+                        int64_t d_pad, int64_t m_cap, int64_t p_base, int64_t proj_dim, uint64_t seed64, int proj_type,
+                        float* out, int64_t ld_out, int accumulate, void* workspace, int64_t workspace_bytes,
+                        int cta_group, void* stream);
 
 /* out[r, j] = P[row0 + r, j] as fp32, r < nrows, j < proj_dim (oracle hook: the kernel's own matrix) */
 int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_dim, uint64_t seed64, int proj_type,
@@ -241,19 +286,12 @@ int gadm_row_mean(gadm_handle h, const double* x, int64_t n, int64_t k, double* 
  * One call per reference function; each is the documented sequence of the calls above on
  * the same stream, with caller-owned workspace.  The Python host layer may call either level. */
 
-/* One gradient block of a batch: `numel_per_example` values per example, consecutive examples `example_stride`
- * elements apart, landing at position `row_offset` of the flattened gradient (d_trak_grad.py:188-226). */
-typedef struct gadm_block {
-  const void* ptr;
-  int64_t numel_per_example;
-  int64_t example_stride;
-  int64_t row_offset;
-} gadm_block;
-/* CudaProjector.project on per-parameter blocks: pack every block (x scale) into `staged` rows 0..batch, then
- * project them.  staged / workspace as for gadm_pack_block / gadm_project_staged. */
+/* CudaProjector.project on per-parameter blocks: stage every block (x scale) into `staged` rows 0..batch
+ * (gadm_stage_rows), then project them (gadm_project_staged); arguments as for those two. */
 int gadm_project(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
-                 void* staged, int64_t d_pad, int64_t m_cap, int64_t proj_dim, uint64_t seed64, int proj_type, float* out,
-                 int64_t ld_out, int accumulate, void* workspace, int64_t workspace_bytes, int cta_group, void* stream);
+                 void* staged, int stage_dtype, float* inv_scale, int64_t d_pad, int64_t m_cap, int64_t proj_dim,
+                 uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate, void* workspace,
+                 int64_t workspace_bytes, int cta_group, void* stream);
 /* G (+)= Phi^T Phi (+ diag_add on the diagonal), lower tiles only (traks.py:149-150).  phi [n, k] pitch ld_phi;
  * phi_t_work: [k, ld_t] scratch with ld_t >= n, ld_t % 4 == 0; g [k, k] pitch ldg. */
 int gadm_gram(gadm_handle h, const float* phi, int64_t n, int64_t k, int64_t ld_phi, float* phi_t_work, int64_t ld_t,

@@ -82,6 +82,47 @@ def round_to_bf16(x: np.ndarray) -> np.ndarray:
     return u.astype(np.uint32).view(np.float32).reshape(x.shape)
 
 
+STAGE_GROUP_COLS = 32768  # GADM_STAGE_GROUP_COLS (include/gadm.h)
+
+
+def round_to_f16_groups(x: np.ndarray, scale: float = 1.0, col0: int = 0) -> np.ndarray:
+    """The GADM_STAGE_F16G staging format (csrc/stage.cuh), returned as float32 values.
+
+    Per (row, group of 32768 columns on the global column grid): amax = max|x| * |scale| (float32), e = floor(log2 amax)
+    clamped to [-100, 100], s = 13 - e (s = 0 for amax == 0 or non-finite); the staged value is
+    float16(float32(x * (scale * 2^s))) (round-to-nearest-even twice) and it stands for staged * 2^-s.
+    ``col0``: global column index of x[:, 0] (a multiple of 32768 keeps the group grid)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    n = x.shape[1]
+    sc = np.float32(scale)
+    first = -(col0 % STAGE_GROUP_COLS)
+    for lo in range(first, n, STAGE_GROUP_COLS):
+        a, b = max(lo, 0), min(lo + STAGE_GROUP_COLS, n)
+        blk = x[:, a:b]
+        with np.errstate(invalid="ignore"):
+            amax = (np.nanmax(np.abs(blk), axis=1) if blk.size else np.zeros(x.shape[0], np.float32)).astype(np.float32)
+        amax = (amax * np.abs(sc)).astype(np.float32)
+        ok = (amax > 0) & np.isfinite(amax)
+        e = np.zeros(x.shape[0], dtype=np.int64)
+        e[ok] = ((amax[ok].view(np.uint32) >> np.uint32(23)) & np.uint32(0xFF)).astype(np.int64) - 127
+        e = np.clip(e, -100, 100)
+        s = np.where(ok, 13 - e, 0)
+        mul = (sc * np.ldexp(np.float32(1.0), s).astype(np.float32)).astype(np.float32)
+        with np.errstate(over="ignore", invalid="ignore"):
+            staged = (blk * mul[:, None]).astype(np.float32).astype(np.float16)
+        out[:, a:b] = np.ldexp(staged.astype(np.float32), -s[:, None]).astype(np.float32)
+    return out
+
+
+def round_staged(x: np.ndarray, stage: str | None = "f16", scale: float = 1.0) -> np.ndarray:
+    """What the projection kernel multiplies by P for gradients x under a staging format ('f16', 'bf16', None)."""
+    if stage == "f16":
+        return round_to_f16_groups(x, scale)
+    xs = (np.asarray(x, dtype=np.float32) * np.float32(scale)).astype(np.float32)
+    return round_to_bf16(xs) if stage == "bf16" else xs
+
+
 def rademacher_matrix(seed64: int, row0: int, nrows: int, k: int) -> np.ndarray:
     """P[row0:row0+nrows, 0:k] as int8 (+1 / -1)."""
     k0, k1 = _key(seed64)

@@ -13,8 +13,10 @@ Two restatements:
   ``cpu_baseline``.  It shares no random stream with the CUDA kernel (neither does
   trak's own CudaProjector), so it is used for throughput and JL statistics only.
 
-* ``project_explicit`` -- the same-matrix parity check: Phi = bf16(G) @ P(seed) in
-  float64 with P from ``oracle.philox`` (bit-exact for Rademacher) or handed in by
+* ``project_explicit`` -- the same-matrix parity check: Phi = staged(G) @ P(seed) in
+  float64, staged() being the kernel's 16-bit input format (``stage="f16"``: fp16 with a
+  power-of-two scale per 32768-column group, the default; ``"bf16"``), with P from
+  ``oracle.philox`` (bit-exact for Rademacher) or handed in by
   the caller (the kernel's own ``gadm_materialize_p`` output for the normal type,
   whose Box-Muller uses MUFU approximations and matches ``oracle.philox`` only to
   one bf16 ulp).  Call-site semantics: ``d_trak_grad.py:776``,
@@ -29,11 +31,9 @@ from . import philox
 
 def project_explicit(grads: np.ndarray, P: np.ndarray | None = None, *, seed: int = 0, model_id: int = 0,
                      proj_type: str = "rademacher", proj_dim: int | None = None, row_offset: int = 0,
-                     round_grads_to_bf16: bool = True, chunk: int = 1 << 15) -> np.ndarray:
+                     stage: str | None = "f16", chunk: int = 1 << 15) -> np.ndarray:
     """fp64 reference of the kernel's contraction: [B, D] x P[row_offset:row_offset+D, :k]."""
-    g = np.asarray(grads, dtype=np.float32)
-    if round_grads_to_bf16:
-        g = philox.round_to_bf16(g)
+    g = philox.round_staged(np.asarray(grads, dtype=np.float32), stage)
     B, D = g.shape
     if P is not None:
         return g.astype(np.float64) @ np.asarray(P, dtype=np.float64)

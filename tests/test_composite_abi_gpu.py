@@ -37,7 +37,8 @@ def test_gadm_project_blocks():
     d_pad = -(-D // 64) * 64
     g = torch.Generator().manual_seed(3)
     parts = [(torch.randn(B, n, generator=g) * 1e-2).to(DEV) for n in sizes]
-    staged = torch.zeros(d_pad // 64, 32, 64, dtype=torch.bfloat16, device=DEV)
+    staged = torch.empty(d_pad // 64, 32, 64, dtype=torch.float16, device=DEV)  # GADM_STAGE_F16G, no pre-zeroing needed
+    inv_scale = torch.empty(32, int(h.lib.gadm_stage_scale_count(d_pad)), device=DEV)
     ws = torch.empty(int(h.lib.gadm_project_workspace_bytes(h.ptr, B, d_pad, k, 2)), dtype=torch.uint8, device=DEV)
     out = torch.empty(B, k, device=DEV)
     blocks = (Block * len(parts))()
@@ -45,8 +46,9 @@ def test_gadm_project_blocks():
     for i, p in enumerate(parts):
         blocks[i] = Block(p.data_ptr(), p.shape[1], p.stride(0), off)
         off += p.shape[1]
-    L.check(h.lib.gadm_project(h.ptr, C.cast(blocks, C.c_void_p), len(parts), 0, B, 0.5, staged.data_ptr(), d_pad, 32, k,
-                               1234, 1, out.data_ptr(), out.stride(0), 0, ws.data_ptr(), ws.numel(), 2, st))
+    L.check(h.lib.gadm_project(h.ptr, C.cast(blocks, C.c_void_p), len(parts), 0, B, 0.5, staged.data_ptr(), 1,
+                               inv_scale.data_ptr(), d_pad, 32, k, 1234, 1, out.data_ptr(), out.stride(0), 0, ws.data_ptr(),
+                               ws.numel(), 2, st))
     torch.cuda.synchronize()
     full = torch.cat(parts, dim=1)
     want = project_explicit((full * 0.5).cpu().numpy(), seed=1234, model_id=0, proj_type="rademacher", proj_dim=k)

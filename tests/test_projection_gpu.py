@@ -1,9 +1,13 @@
 """GPU parity of the JL projection kernel against the CPU oracle (through the C ABI via ctypes).
 
 Tolerances (north_star: "projected features ... within a stated relative tolerance (fp32 accumulate)"):
-* same-matrix parity: |kernel - fp64(bf16(G) @ P)| <= 2e-4 * ||g_row||_2 * max|P|  (fp32 accumulation over D
+* staging parity: the 16-bit staged gradients (fp16 with a power-of-two scale per 32768-column group by default, or
+  bf16) are bit-identical to the oracle's rounding (oracle.philox.round_staged);
+* same-matrix parity: |kernel - fp64(staged(G) @ P)| <= 2e-4 * ||g_row||_2 * max|P|  (fp32 accumulation over D
   products; observed ~1e-6 relative) -- P is the oracle's own matrix for Rademacher (bit-exact) and the
   kernel's materialised matrix for the normal type;
+* effect of the 16-bit staging itself against an fp32-input projection with the same P: relative feature error
+  <= 4e-4 (f16 groups; measured 2.1e-4) / 3e-3 (bf16; measured 1.7e-3) -- test_staging_error_vs_fp32_inputs;
 * kernel normal matrix vs the oracle's float64 Box-Muller: <= 1 bf16 ulp (+1e-4 abs) on every entry and
   identical on > 99% of entries (MUFU sin/cos/lg2/sqrt approximations).
 """
@@ -76,7 +80,7 @@ def test_project_matches_explicit_matrix(cta_group, ptype, B, D, k):
         P = p.materialize(0, D, model_id=1).cpu().numpy()
         want = project_explicit(G, P)
         pmax = float(np.abs(P).max())
-    gn = np.linalg.norm(philox.round_to_bf16(G).astype(np.float64), axis=1, keepdims=True)
+    gn = np.linalg.norm(G.astype(np.float64), axis=1, keepdims=True)
     tol = 2e-4 * gn * pmax + 1e-12
     assert np.all(np.abs(got - want) <= tol), _report(got, want, tol)
     # and the result is a faithful JL sketch of the *unrounded* gradient: ||Pg||/sqrt(k) ~ ||g||
@@ -104,7 +108,7 @@ def test_quad_cluster_variant_matches_explicit_matrix(ptype, B, D, k):
         P = p.materialize(0, D, model_id=0).cpu().numpy()
         want = project_explicit(G, P)
         pmax = float(np.abs(P).max())
-    gn = np.linalg.norm(philox.round_to_bf16(G).astype(np.float64), axis=1, keepdims=True)
+    gn = np.linalg.norm(G.astype(np.float64), axis=1, keepdims=True)
     tol = 2e-4 * gn * pmax + 1e-12
     assert np.all(np.abs(got - want) <= tol), _report(got, want, tol)
     # same features as the pair kernel (different split-K plan -> equal up to fp32 summation order)
@@ -154,6 +158,164 @@ def test_linearity_and_seed_semantics():
         assert not torch.equal(p.project(a, 1), pa)
 
 
+@pytest.mark.parametrize("stage_dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("src_dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_staging_is_bit_identical_to_the_oracle_rounding(stage_dtype, src_dtype):
+    """gadm_stage_rows (one launch for the whole block table) vs oracle.philox.round_staged: every staged 16-bit value
+    times its group's inverse scale equals the oracle's rounding bit for bit -- flat input with an odd row pitch
+    (scalar path), per-parameter blocks of awkward sizes (block-boundary path), rows of very different magnitude,
+    an all-zero group, and the folded 1/K scale."""
+    D, B = 3 * 32768 + 4321, 5
+    g = torch.Generator(device="cpu").manual_seed(7)
+    grads = torch.randn(B, D, generator=g)
+    grads *= torch.tensor([1.0, 1e-6, 3e4, 1e-3, 7.0])[:, None]
+    grads[3, 32768:65536] = 0          # a whole scale group of zeros
+    grads[0, 100] = 900.0              # an outlier sets its group's scale
+    grads = grads.to(src_dtype).to(DEV)
+    p = _proj(D, 512, 3, "rademacher", stage_dtype=stage_dtype, stage_rows=8)
+    ref = grads.float().cpu().numpy()
+    for scale, as_blocks in ((1.0, False), (0.1, True)):
+        st = p._stage(8)
+        st.data.fill_(7.0)             # stale contents must be overwritten, padding columns zeroed
+        if as_blocks:
+            cuts = [0, 3, 4, 1000, 32768 - 1, 32768 + 9, 70000, D]
+            inp = [grads[:, a:b].contiguous() for a, b in zip(cuts[:-1], cuts[1:])]
+        else:
+            inp = grads
+        from gadm_b200.projectors import _as_blocks
+        p._pack(_as_blocks(inp), st, 2, scale)
+        torch.cuda.synchronize()
+        staged = st.data[:, 2:2 + B, :].permute(1, 0, 2).reshape(B, -1).float()
+        assert float(staged[:, D:].abs().max()) == 0.0
+        if st.inv_scale is not None:
+            sc = st.inv_scale[2:2 + B].repeat_interleave(32768, dim=1)[:, :staged.shape[1]]
+            staged = staged * sc
+        want = philox.round_staged(ref, stage_dtype, scale)
+        np.testing.assert_array_equal(staged[:, :D].cpu().numpy(), want)
+        assert float(st.data[:, :2].float().min()) == 7.0 and float(st.data[:, 2 + B:].float().max()) == 7.0
+
+
+def test_timestep_accumulation_matches_fp32_sum():
+    """DeferredProjection.accumulate == the reference loop's fp32 `emb += grads` ... `emb / K` followed by project
+    (d_trak_grad.py:757-776), bit for bit: the slab is summed with separate round-to-nearest multiplies and adds in
+    timestep order, and the staged batch goes through the same kernel."""
+    D, k, B, K = 50_001, 512, 6, 4
+    g = torch.Generator(device="cpu").manual_seed(11)
+    steps = [torch.randn(B, D, generator=g).to(DEV) * (10.0 ** -i) for i in range(K)]
+    cuts = [0, 129, 130, 40_000, D]
+    p = _proj(D, k, 5, "normal", stage_rows=16)
+    with p.deferred(0, overlap=False) as sink:
+        for rep in range(2):  # two batches through the same slab
+            for i, s in enumerate(steps):
+                blocks = {f"w{j}": s[:, a:b] for j, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))}
+                sink.accumulate(blocks if rep else s, scale=1.0 / K, last=(i == K - 1))
+        with pytest.raises(RuntimeError):
+            sink.accumulate(steps[0], 0.25)
+            sink.add(steps[0])
+        sink.accumulate(steps[0], 0.25, last=True)
+    emb = torch.zeros(B, D, device=DEV)
+    for s in steps:
+        emb = emb + s * (1.0 / K)
+    want = p.project(emb, 0)
+    got = sink.result()
+    assert got.shape == (3 * B, k)
+    assert torch.equal(got[:B], want) and torch.equal(got[B:2 * B], want)
+    assert torch.equal(got[2 * B:], p.project(steps[0] * 0.25, 0))
+
+
+def test_overlapped_passes_and_buffer_ownership():
+    """overlap=True: projection passes run on a side stream against two staging buffers; rows come back in insertion
+    order and bit-identical to the serial path.  A second consumer of the shared staging buffers is refused while
+    rows are pending."""
+    D, k, B = 20_000, 512, 100
+    g = torch.Generator(device="cpu").manual_seed(3)
+    grads = torch.randn(B, D, generator=g).to(DEV)
+    p = _proj(D, k, 9, "rademacher", stage_rows=16)
+    with p.deferred(0, overlap=False) as serial:
+        serial.add(grads)
+    with p.deferred(0, overlap=True) as ov:
+        for i in range(0, B, 7):
+            ov.add(grads[i:i + 7])
+    assert torch.equal(ov.result(), serial.result())
+    assert len([s for s in p._stages if s is not None]) == 2
+    pending = p.deferred(0)
+    pending.add(grads[:3])
+    with pytest.raises(RuntimeError):
+        p.project(grads[:2], 0)
+    with pytest.raises(RuntimeError):
+        p.deferred(1).add(grads[:2])
+    with pytest.raises(RuntimeError):
+        p.free_memory()
+    assert torch.equal(pending.result(), serial.result()[:3])
+    assert torch.equal(p.project(grads[:2], 0), serial.result()[:2])
+
+
+@pytest.mark.parametrize("stage_dtype,tol", [("f16", 4e-4), ("bf16", 3e-3)])
+def test_staging_error_vs_fp32_inputs(stage_dtype, tol):
+    """The departure from the reference that the 16-bit staging introduces (the reference hands fp32 gradients to
+    its projector, d_trak_grad.py:776): relative error of the features against fp64 G @ P with UNROUNDED gradients and
+    the same P.  Measured 2.1e-4 (f16 groups) / 1.7e-3 (bf16)."""
+    B, D, k = 16, 40_000, 512
+    g = torch.Generator(device="cpu").manual_seed(5)
+    grads = (torch.randn(B, D, generator=g) * torch.logspace(-4, 0, D)[None, :]).to(DEV)  # 4 decades across parameters
+    p = _proj(D, k, 1, "normal", stage_dtype=stage_dtype)
+    got = p.project(grads, 0).double()
+    want = grads.double() @ p.materialize(0, D).double()
+    rel = ((got - want).norm(dim=1) / want.norm(dim=1)).max().item()
+    assert rel < tol, rel
+    assert rel > tol / 20  # the bound is tight: this is the staging error, not slack
+
+
+@pytest.mark.parametrize("ptype", ["normal", "rademacher"])
+def test_trak_scores_from_kernel_features_agree_with_basic_projector(ptype):
+    """Score-level distributional parity with the reference's own projector (trak BasicProjector, restated in
+    oracle/projector.py): no two trak projectors share P for a seed, so equality is impossible by construction; what
+    must hold is that TRAK scores / contributor rankings computed from the kernel's features agree with those
+    computed from BasicProjector features of the SAME gradients, and with the unprojected influence
+    g_gen^T (G^T G + lam/k I)^-1 g_train that both estimate.
+
+    Synthetic gradients: rank-48 signal (singular values 0.5 .. 0.1) + isotropic noise 0.002, N = 1500 train, T = 16
+    generated, D = 8192, k = 1024, lam = 0.5 (signal eigenvalues of Phi^T Phi >> lam >> noise eigenvalues: the regime
+    in which a JL sketch determines the scores; with noise eigenvalues >= lam the whitening amplifies
+    projection-specific noise and scores from any two projectors decorrelate).  Calibrated on the CPU with the oracle's
+    matrices: Spearman kernel-vs-BasicProjector 0.98, each vs unprojected 0.98 - 0.999.  Stated bounds: >= 0.95."""
+    import gadm_b200 as G
+    from oracle import scorer as oscore
+    from oracle.projector import BasicProjectorOracle
+    from scipy.stats import spearmanr
+
+    N, T, D, k, r = 1500, 16, 8192, 1024, 48
+    rng = np.random.RandomState(0)
+    basis = rng.normal(size=(r, D)).astype(np.float32) / np.sqrt(D)
+    sv = np.geomspace(0.5, 0.1, r).astype(np.float32)
+    zt = rng.normal(size=(N, r)).astype(np.float32) * sv
+    zg = rng.normal(size=(T, r)).astype(np.float32) * sv
+    g_train = zt @ basis + 0.002 * rng.normal(size=(N, D)).astype(np.float32) / np.sqrt(D)
+    g_gen = zg @ basis + 0.002 * rng.normal(size=(T, D)).astype(np.float32) / np.sqrt(D)
+    # product path: kernel features -> device scorer
+    p = _proj(D, k, 42, ptype)
+    with p.deferred(0) as sink:
+        sink.add(torch.from_numpy(g_train).to(DEV))
+    phi_train = sink.result()
+    phi_gen = p.project(torch.from_numpy(g_gen).to(DEV), 0)
+    ours = {n: v.cpu().numpy().astype(np.float64) for n, v in G.trak_scores(phi_train, phi_gen, lam=0.5).items()}
+    # reference path: BasicProjector features -> the reference's torch formulas (traks.py:141-168)
+    bp = BasicProjectorOracle(D, k, 42, ptype)
+    ref = oscore.score_torch(bp.project(torch.from_numpy(g_train), 0).numpy(), bp.project(torch.from_numpy(g_gen), 0).numpy(), 0.5)
+    gt64, gg64 = g_train.astype(np.float64), g_gen.astype(np.float64)
+    exact = (gg64 @ gt64.T @ np.linalg.inv(gt64 @ gt64.T + 0.5 / k * np.eye(N))).mean(axis=0)
+    for name in ("trak", "relative_influence", "renorm_influence", "grad_sim"):
+        rho = spearmanr(ours[name], ref[name]).statistic
+        assert rho >= 0.95, (name, rho)
+    assert spearmanr(ours["trak"], exact).statistic >= 0.95
+    assert spearmanr(ref["trak"], exact).statistic >= 0.95
+    top_ours, top_ref = set(np.argsort(-ours["trak"])[:50]), set(np.argsort(-ref["trak"])[:50])
+    assert len(top_ours & top_ref) >= 35, len(top_ours & top_ref)  # calibrated 44 / 50
+    # JL statistics of the features themselves: same second moments as the reference projector
+    ratio = phi_train.double().norm(dim=1).cpu().numpy() / (np.sqrt(k) * np.linalg.norm(gt64, axis=1))
+    assert abs(ratio.mean() - 1) < 0.01 and ratio.std() < 2.0 / np.sqrt(k)
+
+
 def test_reference_error_behaviour():
     from gadm_b200 import CudaProjector, ProjectionType
 
@@ -179,6 +341,7 @@ def test_full_size_c2_properties():
     * batch-tiling independence at full size (bitwise), JL norm preservation, zero rows stay zero.
     """
     D, k = 35_746_307, 4096
+    torch.cuda.empty_cache()  # the caching allocator may still hold the previous test's staging buffer
     free, _ = torch.cuda.mem_get_info()
     if free < 60 * 2**30:
         pytest.skip("needs ~45 GB of free HBM")
@@ -200,7 +363,10 @@ def test_full_size_c2_properties():
     assert p._handle.watchdog_code() == 0
     seed64 = philox.seed64_of(42, 0)
     P = np.concatenate([philox.rademacher_matrix(seed64, int(q), 1, k) for q in pos]).astype(np.float64)  # [nnz, k]
-    want = philox.round_to_bf16(vals).astype(np.float64) @ P
+    dense_rows = np.zeros((3, D), dtype=np.float32)
+    dense_rows[:, pos] = vals
+    want = philox.round_staged(dense_rows, p.stage_dtype)[:, pos].astype(np.float64) @ P  # the kernel's 16-bit inputs
+    del dense_rows
     got = out[:3].cpu().numpy().astype(np.float64)
     tol = 2e-4 * np.linalg.norm(vals, axis=1, keepdims=True)
     assert np.all(np.abs(got - want) <= tol), np.abs(got - want).max()
@@ -214,35 +380,45 @@ def test_full_size_c2_properties():
     p.free_memory()
 
 
-@pytest.mark.parametrize("ptype,rows,tol", [("normal", 1024, 4e-5), ("rademacher", 512, 4e-6)])
-def test_full_size_c2_fp32_accumulate_accuracy(ptype, rows, tol):
+@pytest.mark.parametrize("ptype,rows,tol,stage_dtype", [("normal", 1024, 4e-5, "f16"), ("rademacher", 512, 4e-6, "f16"),
+                                                        ("rademacher", 512, 4e-6, "bf16")])
+def test_full_size_c2_fp32_accumulate_accuracy(ptype, rows, tol, stage_dtype):
     """BASELINE configs[1] shape, dense rows: relative error of whole feature rows against an fp64 product.
 
     The tensor core adds into its fp32 TMEM accumulator with truncation; left alone over a 15 000-k-block unit
     that shrinks every feature by 1.1e-3 (measured, both types).  The kernel therefore promotes the accumulators
     every 256 / 512 k-blocks with round-to-nearest adds (project.cuh).  Stated tolerance (fp32 accumulate):
     ||kernel - fp64||_2 / ||fp64||_2 <= 4e-5 (normal, measured 1.9e-5) / 4e-6 (Rademacher, measured 1.3e-6) per row,
-    where fp64 = (staged bf16 row, exact) @ P in float64 and P is the kernel's own materialised matrix (pinned to
-    the oracle's Philox matrix by the materialize tests above).  The fp64 checker runs on the GPU (torch.matmul on
-    float64) because the oracle's numpy product over 35.7 M x 4096 does not finish in seconds.
+    where fp64 = (staged 16-bit row x its group scales, exact) @ P in float64 and P is the kernel's own materialised
+    matrix (pinned to the oracle's Philox matrix by the materialize tests above).  The fp64 checker runs on the GPU
+    (torch.matmul on float64) because the oracle's numpy product over 35.7 M x 4096 does not finish in seconds.
+    The f16 cases fill the staging buffer with values around 2^9 and give every (row, group) its own power-of-two
+    inverse scale, so the scale path of the epilogue is exercised at full size.
     """
     D, k = 35_746_307, 4096
+    torch.cuda.empty_cache()  # the caching allocator may still hold the previous test's staging buffer
     free, _ = torch.cuda.mem_get_info()
     if free < (rows * D * 2 + 12 * 2**30):
         pytest.skip("needs the staged buffer + ~12 GB of free HBM")
-    p = _proj(D, k, 42, ptype, stage_rows=rows)
-    stage = p._stage_buffer(rows)
+    p = _proj(D, k, 42, ptype, stage_rows=rows, stage_dtype=stage_dtype)
+    st = p._stage(rows)
+    stage = st.data
     gen = torch.Generator(device=DEV).manual_seed(99)
     nkb = stage.shape[0]
+    amp = 1e-3 if stage_dtype == "bf16" else 512.0
     for k0 in range(0, nkb, 8192):
         k1 = min(nkb, k0 + 8192)
-        blk = (torch.randn(k1 - k0, rows, 64, device=DEV, generator=gen) * 1e-3).to(torch.bfloat16)
+        blk = (torch.randn(k1 - k0, rows, 64, device=DEV, generator=gen) * amp).to(stage.dtype)
         if k1 == nkb and D % 64:
             blk[-1, :, D % 64:] = 0
         stage[k0:k1] = blk
     del blk
+    if st.inv_scale is not None:  # 2^-(17 + (row + group) % 5): effective gradients ~1e-3, a different scale per group
+        r = torch.arange(rows, device=DEV)[:, None]
+        g = torch.arange(p.scale_groups, device=DEV)[None, :]
+        st.inv_scale.copy_(torch.ldexp(torch.ones((), device=DEV), -(17 + (r + g) % 5)))
     out = torch.empty(rows, k, device=DEV)
-    p._project_rows(stage, rows, 0, out)
+    p._project_rows(st, rows, 0, out)
     torch.cuda.synchronize()
     assert p._handle.watchdog_code() == 0
     sel = torch.tensor([0, rows // 2 - 1, rows // 2, rows - 1], device=DEV)  # both accumulators / both CTA pairs
@@ -252,6 +428,9 @@ def test_full_size_c2_fp32_accumulate_accuracy(ptype, rows, tol):
         n = min(D, k1 * 64) - k0 * 64
         P = p.materialize(k0 * 64, n).double()
         g = stage[k0:k1].index_select(1, sel).permute(1, 0, 2).reshape(len(sel), -1)[:, :n].double()
+        if st.inv_scale is not None:  # 1024 k-blocks = two whole scale groups
+            sc = st.inv_scale.index_select(0, sel)[:, k0 // 512:(k1 + 511) // 512].double()
+            g = g * sc.repeat_interleave(512 * 64, dim=1)[:, :n]
         want += g @ P
         del P, g
     got = out.index_select(0, sel).double()

@@ -290,3 +290,94 @@ def test_gemm_triangular_operand_skips_zero_blocks(n):
         assert float((fast.double() - want).abs().max()) < 4e-6 * float(a.double().norm(dim=1).max() * b.double().norm(dim=1).max())
         # the skipped blocks are exact zeros, so the two results agree to accumulation-order rounding
         assert float((fast - full).abs().max()) < 1e-5 * float(full.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-size scorer parity (north_star target: "TRAK scores for CIFAR-10 DDPM (50k train x 1k generated, proj_dim 4096)
+# matching the reference within tolerance").  The fp64 yardstick and the reference's own fp32 formulas
+# (traks.py:149-168 executed literally with torch on the same GPU) are computed in the test with torch / cuSOLVER --
+# checker only, never on the product path.  Stated tolerance: max |ours - fp64| <= 2e-4 * max |fp64| for every variant,
+# and our error is not worse than the error of the reference's fp32 formulas on the same inputs.
+
+def _fp64_variants(train, gen, lam):
+    tp, vp = train.double(), gen.double()
+    K = tp.T @ tp
+    K.diagonal().add_(lam)
+    L = torch.linalg.cholesky(K)
+    del K
+    W = torch.cholesky_solve(tp.T.contiguous(), L)  # K^-1 Phi^T  [k, N]
+    del L
+    S = vp @ W  # [T, N]
+    out = {"trak": S.mean(dim=0), "relative_influence": (S / W.norm(dim=0)).mean(dim=0),
+           "renorm_influence": (S / tp.norm(dim=1)).mean(dim=0)}
+    cos = (vp / vp.norm(dim=1, keepdim=True)) @ (tp / tp.norm(dim=1, keepdim=True)).T
+    out["grad_sim"] = cos.mean(dim=0)
+    out["scores_head"] = S[:64].clone()
+    return out
+
+
+def _reference_fp32_variants(train, gen, lam):
+    """text_to_image/traks.py:141-168, literally, fp32 on the device the reference would use."""
+    grad_sim = torch.matmul(gen, train.T)
+    grad_sim /= torch.matmul(gen.norm(dim=-1, keepdim=True), train.norm(dim=-1, keepdim=True).T)
+    out = {"grad_sim": grad_sim.mean(dim=0)}
+    del grad_sim
+    ihdp = torch.matmul(train.T, train)
+    ihdp += lam * torch.eye(train.shape[1], device=train.device)
+    ihdp = torch.inverse(ihdp)
+    ihdp = torch.matmul(ihdp, train.T)
+    influence = torch.matmul(gen, ihdp)
+    out["trak"] = influence.mean(dim=0)
+    out["relative_influence"] = (influence / ihdp.norm(dim=0)).mean(dim=0)
+    out["renorm_influence"] = (influence / train.norm(dim=-1)).mean(dim=0)
+    return out
+
+
+def _topk_agrees(got, want, k, err):
+    """Top-k contributor set equality; a swap is only tolerated between candidates whose fp64 scores are closer to
+    the k-th score than twice the measured error (a genuine near-tie)."""
+    order = torch.argsort(want, descending=True, stable=True)
+    top_want = set(order[:k].tolist())
+    top_got = set(torch.argsort(got, descending=True, stable=True)[:k].tolist())
+    if top_got == top_want:
+        return True
+    kth = float(want[order[k - 1]])
+    diff = top_got ^ top_want
+    return all(abs(float(want[i]) - kth) <= 2 * err for i in diff)
+
+
+@pytest.mark.parametrize("N,T,k,tag", [(50_000, 1_000, 4096, "C2"), (5_000, 50, 32_768, "C4")])
+def test_full_size_scores_match_fp64_and_beat_reference_fp32(N, T, k, tag):
+    """BASELINE configs[1] (primal k x k system) and configs[3] (N < k: dual N x N system) at full size."""
+    import gadm_b200 as G
+
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~40 GB of free HBM for the fp64 yardstick")
+    gt = torch.Generator(device=DEV).manual_seed(0)
+    gg = torch.Generator(device=DEV).manual_seed(1)
+    train = torch.randn(N, k, device=DEV, generator=gt)  # SURVEY 8(d): Phi ~ randn(N, k), seeds 0 / 1
+    gen = torch.randn(T, k, device=DEV, generator=gg)
+    got, scorer = G.trak_scores(train, gen, lam=0.5, return_scorer=True)
+    torch.cuda.synchronize()
+    scorer.check()
+    assert scorer.dual == (N < k)
+    want = _fp64_variants(train, gen, 0.5)
+    ref = _reference_fp32_variants(train, gen, 0.5)
+    report = {}
+    for name in ("grad_sim", "trak", "relative_influence", "renorm_influence"):
+        w = want[name]
+        scale = float(w.abs().max())
+        ours = float((got[name].double() - w).abs().max()) / scale
+        theirs = float((ref[name].double() - w).abs().max()) / scale
+        report[name] = (ours, theirs)
+        assert ours < 2e-4, (tag, name, ours, theirs)
+        assert ours <= max(theirs, 2e-6), (tag, name, ours, theirs)
+        assert _topk_agrees(got[name].double(), w, 100, ours * scale), (tag, name, ours)
+    # the full [T, N] matrix path (compute_gradient_score.py:126) on a slice of generated images
+    del ref
+    s, _ = G.gradient_scores(train, gen[:64], "trak")
+    sw = want["scores_head"]
+    assert float((s.double() - sw).abs().max()) < 2e-4 * float(sw.abs().max()), tag
+    print(f"{tag} full-size score error (ours, reference fp32) vs fp64: {report}")
