@@ -163,6 +163,8 @@ def main():
                     help="normal is what the reference instantiates (d_trak_grad.py:508)")
     ap.add_argument("--no-extra", action="store_true", help="skip the scoring / aggregation side measurements")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="stage and project serially on one stream")
+    ap.add_argument("--no-producer", action="store_true", help="skip the U-Net vmap(grad) end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -204,58 +206,82 @@ def main():
     peaks = _peaks()
     ptype = ProjectionType(args.proj_type)
     rows = 1024 if args.proj_type == "normal" else STAGE_ROWS  # staged examples per step per GPU
+    chunk = 32  # examples per add(): the gradients of one producer batch, [32, D] fp32 resident in HBM
     proj = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ptype, dev, 32, stage_rows=rows)
     handle = proj._handle
-    stage = proj._stage_buffer(rows)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    nkb = stage.shape[0]  # staging layout [D_pad/64][rows][64] (include/gadm.h)
-    for k0 in range(0, nkb, 8192):  # synthetic per-example gradients, randn * 1e-3, bf16, resident in HBM
-        k1 = min(nkb, k0 + 8192)
-        blk = (torch.randn(k1 - k0, rows, 64, device=dev, generator=gen) * 1e-3).to(torch.bfloat16)
-        if k1 == nkb and GRAD_DIM % 64:
-            blk[-1, :, GRAD_DIM % 64:] = 0
-        stage[k0:k1] = blk
-    del blk
-    out = torch.empty(rows, PROJ_DIM, device=dev)
+    src = torch.randn(chunk, GRAD_DIM, device=dev, generator=gen) * 1e-3  # synthetic per-example gradients
+    overlap = not args.no_overlap
+    if overlap:
+        free, _ = torch.cuda.mem_get_info(dev)
+        overlap = free > 2 * rows * proj.d_pad * 2 + (12 << 30)  # two staging buffers + workspace + the e2e leg's chunks
 
-    # ---------------- device-resident throughput (value) + roofline
+    # ---------------- value: device-resident fp32 gradients through the PUBLIC API (staging inside the timed region)
+    sink = proj.deferred(model_id=0, overlap=overlap, record_events=True)
+
+    def api_step():
+        for _ in range(rows // chunk):
+            sink.add(src)  # one staging launch per batch; the rows-th example triggers the projection pass
+
     for _ in range(args.warmup):
-        proj._project_rows(stage, rows, 0, out)
+        api_step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = handle.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for i in range(args.steps):
-        proj._project_rows(stage, rows, 0, out)
-        ev[i + 1].record()
+    n_warm_passes = len(sink.pass_events)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        api_step()
+    feats = sink.result()  # joins the side stream: every pass of the timed steps has finished
+    t1.record()
     barrier()
     launches = handle.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
-    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = max_over_ranks(t0.elapsed_time(t1))
     ms_per_step = total_ms / args.steps
     value = rows * world / (ms_per_step * 1e-3)
+    pass_ms = [e0.elapsed_time(e1) for (e0, e1, _r) in sink.pass_events[n_warm_passes:]]
+    assert len(pass_ms) == args.steps and feats.shape[0] == rows * (args.steps + args.warmup)
     flops_per_launch = 2.0 * rows * GRAD_DIM * PROJ_DIM
-    kernel_ms = sum(step_ms) / len(step_ms)  # project kernel + its (<0.1 %) split-K reduce, this rank
+    kernel_ms = sum(pass_ms) / len(pass_ms)  # project kernel + its (<0.1 %) split-K reduce, in situ (staging overlapped)
     achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12
     wd = handle.watchdog_code()
     assert wd == 0, f"kernel watchdog fired: {wd:#x}"
+    stage_launches_per_step = rows // chunk
+    del feats, sink
+
+    # ---------------- kernel alone on the rows just staged (no staging in flight): the round-1 `value`, for continuity
+    stage0 = proj._stage(rows, 0)
+    out = torch.empty(rows, PROJ_DIM, device=dev)
+    for _ in range(2):
+        proj._project_rows(stage0, rows, 0, out)
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(3):
+        proj._project_rows(stage0, rows, 0, out)
+    k1.record()
+    barrier()
+    alone_ms = max_over_ranks(k0.elapsed_time(k1)) / 3
+    kernel_only = {"ms_per_pass": alone_ms, "value": rows * world / (alone_ms * 1e-3), "unit": UNIT,
+                   "tflops_per_gpu": flops_per_launch / (alone_ms * 1e-3) / 1e12,
+                   "what": "gadm_project_staged on pre-staged rows, nothing else on the GPU (round-1 headline definition)"}
 
     # the other projection type on the same staged rows (side number; the headline is --proj-type)
     other = "rademacher" if args.proj_type == "normal" else "normal"
     rows_o = min(rows, 1024 if other == "normal" else STAGE_ROWS)
     proj_o = CudaProjector(GRAD_DIM, PROJ_DIM, 42, ProjectionType(other), dev, 32, stage_rows=rows_o)
-    proj_o._stage = proj._stage
+    proj_o._stages = proj._stages
     for _ in range(2):
-        proj_o._project_rows(stage, rows_o, 0, out)
+        proj_o._project_rows(stage0, rows_o, 0, out)
     barrier()
     o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     o0.record()
     for _ in range(3):
-        proj_o._project_rows(stage, rows_o, 0, out)
+        proj_o._project_rows(stage0, rows_o, 0, out)
     o1.record()
     barrier()
     other_ms = max_over_ranks(o0.elapsed_time(o1)) / 3
@@ -264,25 +290,45 @@ def main():
                   "value": rows_o * world / (other_ms * 1e-3), "unit": UNIT,
                   "tflops_per_gpu": flops_o / (other_ms * 1e-3) / 1e12,
                   "frac_of_burst_peak": flops_o / (other_ms * 1e-3) / 1e12 / peaks["bf16_burst"],
-                  "frac_of_sustained_peak": flops_o / (other_ms * 1e-3) / 1e12 / peaks["bf16_sustained"]}
-    proj_o._stage = proj_o._ws = None
+                  "frac_of_sustained_peak": flops_o / (other_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                  "what": "kernel alone on pre-staged rows"}
+    proj_o._stages = []
+    proj_o._ws = None
     del proj_o
+
+    # ---------------- the unmodified reference script: project() per batch of 8 / 16 (d_trak_grad.py:327,776;
+    # grad_text_to_image_lora.py:561-568) -- every call regenerates all of P for a handful of rows
+    unmodified = {}
+    if rank == 0:
+        for bsz in (8, 16):
+            proj.project(src[:bsz], 0)
+            torch.cuda.synchronize()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
+            for _ in range(3):
+                proj.project(src[:bsz], 0)
+            u1.record()
+            torch.cuda.synchronize()
+            ms = u0.elapsed_time(u1) / 3
+            unmodified[f"batch_{bsz}"] = {"ms_per_call": ms, "value": bsz / (ms * 1e-3), "unit": UNIT}
+        unmodified["what"] = ("CudaProjector.project([B, D] fp32 on the device) per call, as the reference scripts call it "
+                              "through shims/trak without deferred(): one GPU")
+    barrier()
 
     # ---------------- end to end: pinned host fp32 gradients -> public API -> features back on the host
     e2e = None
     if not args.no_e2e:
-        chunk = 32
         host = torch.empty(chunk, GRAD_DIM, dtype=torch.float32).pin_memory()
         host.normal_(0, 1e-3)
         host_out = torch.empty(rows, PROJ_DIM, dtype=torch.float32).pin_memory()
-        bufs = [torch.empty(chunk, GRAD_DIM, dtype=torch.float32, device=dev) for _ in range(2)]
+        bufs = [src, torch.empty(chunk, GRAD_DIM, dtype=torch.float32, device=dev)]
         copy_stream = torch.cuda.Stream(device=dev)
         free_ev = [torch.cuda.Event() for _ in range(2)]
         full_ev = [torch.cuda.Event() for _ in range(2)]
         main_stream = torch.cuda.current_stream(dev)
 
         def e2e_step():
-            with proj.deferred(model_id=0) as sink:
+            with proj.deferred(model_id=0, overlap=overlap) as sk:
                 for c in range(rows // chunk):
                     b = c % 2
                     with torch.cuda.stream(copy_stream):
@@ -290,9 +336,9 @@ def main():
                         bufs[b].copy_(host, non_blocking=True)  # H2D of this chunk's gradients
                         full_ev[b].record(copy_stream)
                     main_stream.wait_event(full_ev[b])
-                    sink.add(bufs[b])  # pack -> bf16 staging (projects when 512 rows are staged)
+                    sk.add(bufs[b])  # staged in one launch (projects when the last row of the pass is staged)
                     free_ev[b].record(main_stream)
-            host_out.copy_(sink.result(), non_blocking=True)  # D2H of the step's result
+            host_out.copy_(sk.result(), non_blocking=True)  # D2H of the step's result
             main_stream.synchronize()
 
         for e in free_ev:
@@ -302,7 +348,6 @@ def main():
         for _ in range(n_e2e_warm):
             e2e_step()
         barrier()
-        t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_e2e):
@@ -317,17 +362,24 @@ def main():
                "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
         del bufs, host
     proj.free_memory()
-    del stage
+    del stage0, src
     torch.cuda.empty_cache()
 
-    # ---------------- side measurements: full TRAK scoring at C2 dims, aggregation at config 5
+    # ---------------- side measurements: full TRAK scoring at C2 dims, aggregation at config 5, the real producer
     extra = {}
     if not args.no_extra:
         try:
             extra = side_measurements(dev, rank, world)
         except Exception as e:  # never lose the headline line
             extra = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1 and not args.no_producer:
+            try:
+                extra["e2e_producer"] = producer_leg(dev, args.proj_type)
+            except Exception as e:
+                extra["e2e_producer"] = {"error": f"{type(e).__name__}: {e}"}
     extra["projection_other_type"] = other_line
+    extra["kernel_only"] = kernel_only
+    extra["unmodified_script"] = unmodified
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,24 +395,87 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "f16 staged gradients x bf16 P, fp32 accumulate" if proj.stage_dtype == "f16" else "bf16",
+            "data": "synthetic",
             "config": {"workload": "CIFAR-10 DDPM TRAK featurisation: JL projection of per-example U-Net gradients "
-                                   f"(BASELINE configs[1]), {rows} staged examples per step per GPU",
+                                   f"(BASELINE configs[1]), {rows} examples per step per GPU through "
+                                   "CudaProjector.deferred().add(fp32 [32, D] on the device) -> result()",
                        "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": args.proj_type,
                        "rows_per_step_per_gpu": rows, "sharding": f"examples x{world}",
+                       "staging": f"{proj.stage_dtype} staging inside the timed region"
+                                  + (", overlapped with the previous pass (second staging buffer, side stream)" if overlap else ", serial"),
                        "l2": f"staged input ({rows * GRAD_DIM * 2 / 1e9:.1f} GB) and split-K partials exceed the 126 MB L2"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                          "peak_kind": f"bf16_tflops_sustained of measured ({peaks['source']}); timed inside a multi-step loop",
                          "frac_of_burst_peak": achieved / peaks["bf16_burst"], "flops_per_launch": flops_per_launch,
+                         "kernel_ms": kernel_ms,
+                         "timing": "CUDA events around every pass on the stream it is launched on, staging of the next "
+                                   "pass running concurrently" if overlap else "CUDA events around every pass",
                          "kernel": "gadm::proj::project_quad_kernel<4, 4>" if args.proj_type == "normal"
                          else "gadm::proj::project_kernel<2,2>"},
-            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "tflops": achieved * world, "extra": extra,
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "gpu_launches_per_step": {"stage_groups_kernel": stage_launches_per_step, "project": 1, "project_reduce": 1},
+            "clocks": clocks, "tflops": achieved * world, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def producer_leg(dev, proj_type):
+    """SURVEY 8(f)-1, the real end to end: the reference's DDPM-CIFAR U-Net (35 746 307 parameters, random init)
+    under vmap(grad) for 10 timesteps per example -> DeferredProjection.accumulate -> projection -> host.
+    Reference loop: d_trak_grad.py:718-792.  Reports grads/s and how the wall time splits."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from ddpm_unet import DDPMCifarUNet, DDPMScheduler, count_parameters
+    from featurize_and_score import featurize
+
+    from gadm_b200 import CudaProjector, ProjectionType
+
+    torch.manual_seed(0)
+    model = DDPMCifarUNet().to(dev).eval()
+    n_params = count_parameters(model)
+    assert n_params == GRAD_DIM
+    sched = DDPMScheduler(device=dev)
+    K, batch = 10, 16
+    g = torch.Generator(device=dev).manual_seed(1)
+    images = torch.rand(1024, 3, 32, 32, device=dev, generator=g) * 2 - 1
+    # producer alone on two batches: sizes the sample so that the leg stays near 20 s
+    featurize(model, images[:batch], None, sched, K, 42, "loss", batch, project=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    featurize(model, images[:2 * batch], None, sched, K, 42, "loss", batch, project=False)
+    torch.cuda.synchronize()
+    prod_s_per_example = (time.perf_counter() - t0) / (2 * batch)
+    n = int(min(1024, max(64, (18.0 / prod_s_per_example) // batch * batch)))
+    proj = CudaProjector(n_params, PROJ_DIM, 42, ProjectionType(proj_type), dev, batch, stage_rows=min(1024, n))
+    host_out = torch.empty(n, PROJ_DIM, dtype=torch.float32).pin_memory()
+    sink = proj.deferred(0, record_events=True)
+    featurize(model, images[:batch], proj, sched, K, 42, "loss", batch, sink=sink)  # warm-up: allocations, autotune
+    sink.result()
+    torch.cuda.synchronize()
+    sink = proj.deferred(0, record_events=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = proj._handle.launch_count()
+    e0.record()
+    featurize(model, images[:n], proj, sched, K, 42, "loss", batch, sink=sink)
+    host_out.copy_(sink.result(), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    pass_ms = sum(a.elapsed_time(b) for (a, b, _r) in sink.pass_events)
+    proj.free_memory()
+    return {"value": n / (total_ms * 1e-3), "unit": UNIT, "examples": n, "timesteps": K, "batch": batch,
+            "total_ms": total_ms, "producer_alone_ms": prod_s_per_example * n * 1e3, "projection_pass_ms": pass_ms,
+            "projection_share_of_wall": pass_ms / total_ms,
+            "staging_and_timestep_sum_share_of_wall": max(0.0, 1.0 - pass_ms / total_ms - prod_s_per_example * n * 1e3 / total_ms),
+            "gadm_launches": int(proj._handle.launch_count() - l0), "finite": bool(torch.isfinite(host_out).all()),
+            "d2h_bytes": n * PROJ_DIM * 4,
+            "what": "DDPMCifarUNet vmap(grad) x 10 timesteps -> DeferredProjection.accumulate(dict of per-parameter "
+                    "grads, 1/K) -> staged on the last timestep -> projection passes -> features on the host"}
 
 
 def side_measurements(dev, rank, world):
@@ -392,10 +507,40 @@ def side_measurements(dev, rank, world):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    gram_flops = 2.0 * N_TRAIN * PROJ_DIM * PROJ_DIM
     out["trak_score"] = {"ms": ms, "n_train": N_TRAIN, "n_gen": N_GEN, "proj_dim": PROJ_DIM, "lam": 0.5,
-                         "what": "Gram (+NCCL all-reduce) -> Cholesky -> solve -> score GEMM -> mean (+all-gather)",
-                         "finite": bool(torch.isfinite(res["trak"]).all())}
-    del train, gen, res
+                         "what": "Gram (+NCCL all-reduce) -> Cholesky -> triangular inverse -> mean-row solve -> matvec "
+                                 "over the training features (+all-gather), incl. the factorisation check (one D2H)",
+                         "gram_flops": gram_flops, "finite": bool(torch.isfinite(res["trak"]).all())}
+    # parity of the sharded path (all-reduce of the Gram, all-gather of the score slices) against the unsharded
+    # computation on rank 0, and of both against an fp64 product for a sample of training examples
+    if world > 1:
+        parts = [torch.empty_like(train) for _ in range(world)]
+        dist.all_gather(parts, train)
+        train_all = torch.cat(parts, dim=0)
+        del parts
+    else:
+        train_all = train
+    if rank == 0:
+        single = G.trak_scores(train_all, gen, lam=0.5, variants=("trak",), group=G.LOCAL)["trak"]
+        scale = float(single.abs().max())
+        k_top = 100
+        top_s = set(torch.argsort(single, descending=True, stable=True)[:k_top].tolist())
+        top_d = set(torch.argsort(res["trak"], descending=True, stable=True)[:k_top].tolist())
+        # fp64 spot check: s_n = mean(gen) K^-1 phi_n for 64 examples, K^-1 applied by fp64 Cholesky (torch, checker only)
+        tp = train_all.double()
+        K = tp.T @ tp
+        K.diagonal().add_(0.5)
+        zbar = torch.cholesky_solve(gen.double().mean(dim=0)[:, None], torch.linalg.cholesky(K))[:, 0]
+        idx = torch.arange(0, N_TRAIN, N_TRAIN // 64, device=dev)
+        want = tp[idx] @ zbar
+        out["trak_score"].update({
+            "rel_err_vs_single_gpu": float((res["trak"] - single).abs().max()) / scale,
+            "topk_equal": top_s == top_d, "topk": k_top, "topk_overlap": len(top_s & top_d),
+            "rel_err_vs_fp64_sample": float((res["trak"][idx].double() - want).abs().max()) / float(want.abs().max()),
+            "single_gpu_rel_err_vs_fp64_sample": float((single[idx].double() - want).abs().max()) / float(want.abs().max())})
+        del tp, K, single
+    del train, gen, res, train_all
     torch.cuda.empty_cache()
     if rank == 0:
         n, d, K, m = 1000, 100, 1000, 100

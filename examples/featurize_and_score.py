@@ -2,7 +2,8 @@
 
 Mirrors the hot loop of src/attributions/methods/d_trak_grad.py:700-794 with the B200 path dropped in:
   * per-example gradients: torch.func.vmap(grad(compute_f)) exactly as the reference (PyTorch, by design);
-  * timestep mean folded into the projector's staging (`scale=1/K`, d_trak_grad.py:764-770);
+  * timestep sum and mean inside the projector (`DeferredProjection.accumulate(g, scale=1/K, last=...)`: an fp32 slab
+    summed by one kernel per timestep, staged on the last one; d_trak_grad.py:764-770);
   * the per-parameter gradient dict goes straight to `CudaProjector` (no vectorize_and_ignore_buffers copy);
   * features stay on the device; `trak_scores` (Gram -> Cholesky -> solve -> score GEMM) replaces traks.py:141-186.
 
@@ -27,8 +28,10 @@ from ddpm_unet import DDPMCifarUNet, DDPMScheduler, count_parameters
 from gadm_b200 import CudaProjector, ProjectionType, trak_scores
 
 
-def featurize(model, images, projector, scheduler, k_partition: int, opt_seed: int, behavior: str, batch: int):
-    """[N, 3, 32, 32] images -> [N, proj_dim] features (device resident)."""
+def featurize(model, images, projector, scheduler, k_partition: int, opt_seed: int, behavior: str, batch: int,
+              sink=None, project: bool = True):
+    """[N, 3, 32, 32] images -> [N, proj_dim] features (device resident).  ``project=False`` runs the gradient
+    producer alone (bench.py uses it to split the wall time)."""
     params = {k: v.detach() for k, v in model.named_parameters() if v.requires_grad}
     buffers = {k: v.detach() for k, v in model.named_buffers()}
 
@@ -39,20 +42,21 @@ def featurize(model, images, projector, scheduler, k_partition: int, opt_seed: i
         return F.mse_loss(pred.float(), torch.zeros_like(targets).unsqueeze(0).float(), reduction="none").mean()
 
     sample_grad = vmap(grad(compute_f), in_dims=(None, None, 0, 0, 0))
-    selected_timesteps = range(0, 1000, 1000 // k_partition)  # t_strategy == "uniform" (d_trak_grad.py:718-719)
-    sink = projector.deferred(model_id=0)
+    selected_timesteps = list(range(0, 1000, 1000 // k_partition))  # t_strategy == "uniform" (d_trak_grad.py:718-719)
+    own_sink = sink is None
+    if own_sink and project:
+        sink = projector.deferred(model_id=0)
     for i in range(0, images.shape[0], batch):
         image = images[i:i + batch]
-        emb = None
-        for t in selected_timesteps:
+        for j, t in enumerate(selected_timesteps):
             timesteps = torch.full((image.shape[0],), t, device=image.device, dtype=torch.long)
             torch.manual_seed(opt_seed * 1000 + t)  # seed_everything(args.opt_seed * 1000 + t) (d_trak_grad.py:727)
             noise = torch.randn_like(image)
             noisy = scheduler.add_noise(image, noise, timesteps)
             g = sample_grad(params, buffers, noisy, timesteps, noise)
-            emb = g if emb is None else {k: emb[k] + g[k] for k in g}
-        sink.add(emb, scale=1.0 / k_partition)
-    return sink.result()
+            if project:  # emb += g; emb / K on the last timestep; stage (d_trak_grad.py:764-770)
+                sink.accumulate(g, scale=1.0 / k_partition, last=(j == len(selected_timesteps) - 1))
+    return sink.result() if (project and own_sink) else None
 
 
 def main():

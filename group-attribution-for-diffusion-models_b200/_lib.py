@@ -44,6 +44,8 @@ _SIGNATURES = {
     "gadm_tri_inverse": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "gadm_solve_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "gadm_row_norms": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp]),
+    "gadm_matvec_rows": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "gadm_diag_minmax": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gadm_col_mean_scaled": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "gadm_scale_rows_cols": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "gadm_pack_masks": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),

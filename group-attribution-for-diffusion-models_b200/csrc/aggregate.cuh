@@ -426,40 +426,81 @@ __global__ void lds_spearman_kernel(const double* __restrict__ pred, const doubl
   if (lane == 0) rho[job] = (sab / sqrt(saa)) / sqrt(sbb);  // corrcoef's two-step normalisation; 0/0 -> NaN
 }
 
-// lds[e] = mean_k(rho[e, k]) * 100  (sequential, fixed order)
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h, pairwise_sum_@TYPE@), restated over a stream of
+// values consumed in order: fewer than 8 -> running sum from -0; up to 128 -> eight strided accumulators combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus the remainder in order; more -> split at n/2 rounded down to a multiple of
+// 8 and recurse.  np.sum / np.mean over a contiguous axis are 0 + this (pinned against numpy for every n <= 300 and
+// a set of larger sizes by tests/test_oracle_golden.py).  The reference ranks contributors by
+// np.argsort(-x.mean(-1)) and sums group attributions with .sum() (traks.py:199-218, shapley_lds.py:294): the last
+// ulp of these sums decides near-ties, so the order is reproduced exactly instead of "some fixed order".
+template <typename T, typename Next>
+__device__ T numpy_pairwise_sum(Next& next, int64_t n) {
+  if (n < 8) {
+    T res = static_cast<T>(-0.0);
+    for (int64_t i = 0; i < n; ++i) res = res + next();
+    return res;
+  }
+  if (n <= 128) {
+    T r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = next();
+    int64_t i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = r[j] + next();
+    }
+    T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res = res + next();
+    return res;
+  }
+  int64_t n2 = n / 2;
+  n2 -= n2 % 8;
+  const T left = numpy_pairwise_sum<T>(next, n2);
+  return left + numpy_pairwise_sum<T>(next, n - n2);
+}
+
+// lds[e] = mean_k(rho[e, k] * 100) = np.mean of the per-behaviour list (shapley_lds.py:147, lds.py:167)
 __global__ void lds_mean_kernel(const double* __restrict__ rho, int64_t R, int64_t K, double* __restrict__ out) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= R) return;
-  double s = 0.0;
-  for (int64_t k = 0; k < K; ++k) s += rho[e * K + k] * 100.0;
-  out[e] = s / static_cast<double>(K);
+  const double* p = rho + e * K;
+  auto next = [&]() { return __dmul_rn(*p++, 100.0); };  // rounded product, then summed (no FMA contraction)
+  out[e] = (0.0 + numpy_pairwise_sum<double>(next, K)) / static_cast<double>(K);
 }
 
 // ------------------------------------------------------------------ group reductions and ranks
-// out[g] = sum / mean / max over {values[i] : group[i] == g}, accumulated in fp64 in index order
-// (traks.py:188-204; attribution_utils.py:15-48).  One warp per group, lanes take strided slices and
-// are combined in a fixed tree => deterministic.
+// out[g] = sum / mean / max over {values[i] : group[i] == g} exactly as the reference computes them
+// (traks.py:188-204 `attrs[group_indices].sum()` / `.mean()` / `.max()`; attribution_utils.py:15-48): members in index
+// order, numpy's pairwise summation IN THE VALUES' OWN PRECISION (the reference's attrs are float32 arrays, so its
+// group sums are float32 sums widened afterwards), mean = sum / count in that precision.  One thread per group:
+// count the members, then stream them through numpy_pairwise_sum (N * G reads from L2; N <= 5 * 10^4, G <= 10^3).
 template <typename T>
 __global__ void group_reduce_kernel(const T* __restrict__ values, const int32_t* __restrict__ group, int64_t N,
                                     int64_t G, int mode, double* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t g = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (g >= G) return;
-  double s = 0.0, mx = -INFINITY;
   int64_t cnt = 0;
-  for (int64_t i = lane; i < N; i += 32) {
+  T mx = static_cast<T>(-INFINITY);
+  bool any_nan = false;
+  for (int64_t i = 0; i < N; ++i) {
     if (group[i] == g) {
-      const double v = static_cast<double>(values[i]);
-      s += v; mx = fmax(mx, v); ++cnt;
+      const T v = values[i];
+      ++cnt;
+      any_nan |= (v != v);
+      mx = v > mx ? v : mx;
     }
   }
-  s = warp_sum(s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (mode == 2) {
+    out[g] = any_nan ? static_cast<double>(NAN) : static_cast<double>(mx);  // np.max propagates NaN
+    return;
   }
-  if (lane == 0) out[g] = (mode == 0) ? s : (mode == 1 ? s / static_cast<double>(cnt) : mx);
+  int64_t cursor = 0;
+  auto next = [&]() {
+    while (group[cursor] != g) ++cursor;
+    return values[cursor++];
+  };
+  const T sum = static_cast<T>(0) + numpy_pairwise_sum<T>(next, cnt);
+  out[g] = static_cast<double>(mode == 0 ? sum : sum / static_cast<T>(cnt));  // empty group: 0 / (0/0 = NaN) like numpy
 }
 
 // rank[pos] = i where pos = #{j : x_j > x_i} + #{j < i : x_j == x_i}  == np.argsort(-x, kind="stable")
@@ -485,9 +526,9 @@ __global__ void stable_rank_desc_kernel(const double* __restrict__ x, int64_t n,
 __global__ void row_mean_kernel(const double* __restrict__ x, int64_t n, int64_t K, double* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double s = 0.0;
-  for (int64_t k = 0; k < K; ++k) s += x[i * K + k];
-  out[i] = s / static_cast<double>(K);
+  const double* p = x + i * K;
+  auto next = [&]() { return *p++; };
+  out[i] = (0.0 + numpy_pairwise_sum<double>(next, K)) / static_cast<double>(K);  // == np.mean(x, axis=-1)
 }
 
 }  // namespace agg

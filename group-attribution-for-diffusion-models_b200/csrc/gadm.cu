@@ -845,6 +845,24 @@ int gadm_row_norms(gadm_handle h, const float* x, int64_t rows, int64_t cols, in
   return GADM_OK;
 }
 
+int gadm_matvec_rows(gadm_handle h, const float* x, int64_t rows, int64_t cols, int64_t ld, const float* v,
+                     const float* col_scale, float* out, void* stream) {
+  GADM_REQUIRE(h && x && v && out && rows > 0 && cols > 0 && ld >= cols, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::gemm::matvec_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, rows, cols, ld, v, col_scale,
+                                                                                           out);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
+int gadm_diag_minmax(gadm_handle h, const float* l, int64_t ld, int64_t k, float* out2, void* stream) {
+  GADM_REQUIRE(h && l && out2 && k > 0 && ld >= k, "bad argument");
+  DeviceGuard guard(h->device);
+  gadm::gemm::diag_minmax_kernel<<<1, 1024, 0, as_stream(stream)>>>(l, ld, k, out2);
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
 int gadm_col_mean_scaled(gadm_handle h, const float* s, int64_t t, int64_t n, int64_t ld, const float* row_scale,
                          const float* col_scale, float* out, void* stream) {
   GADM_REQUIRE(h && s && out && t > 0 && n > 0 && ld >= n, "bad argument");
@@ -1106,12 +1124,12 @@ int gadm_group_reduce(gadm_handle h, const void* values, int dtype, const int32_
                       int mode, double* out, void* stream) {
   GADM_REQUIRE(h && values && group && out && n > 0 && n_groups > 0 && mode >= 0 && mode <= 2, "bad argument");
   DeviceGuard guard(h->device);
-  const unsigned blocks = (unsigned)((n_groups + 3) / 4);
+  const unsigned blocks = (unsigned)((n_groups + 31) / 32);
   if (dtype == GADM_DTYPE_F32)
-    gadm::agg::group_reduce_kernel<float><<<blocks, 128, 0, as_stream(stream)>>>(
+    gadm::agg::group_reduce_kernel<float><<<blocks, 32, 0, as_stream(stream)>>>(
         reinterpret_cast<const float*>(values), group, n, n_groups, mode, out);
   else if (dtype == GADM_DTYPE_F64)
-    gadm::agg::group_reduce_kernel<double><<<blocks, 128, 0, as_stream(stream)>>>(
+    gadm::agg::group_reduce_kernel<double><<<blocks, 32, 0, as_stream(stream)>>>(
         reinterpret_cast<const double*>(values), group, n, n_groups, mode, out);
   else
     return fail(GADM_ERR_INVALID, "group_reduce supports f32 / f64 values, got dtype %d", dtype);

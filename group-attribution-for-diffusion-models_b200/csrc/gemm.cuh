@@ -668,5 +668,63 @@ __global__ void scale_rows_cols_kernel(float* __restrict__ S, int64_t T, int64_t
   S[t * ld + n] = v;
 }
 
+// out[n] = col_scale[n] * sum_j x[n, j] * v[j]: the mean-over-generated-images forms of traks.py:157,162-168 are
+// linear in the generated features, so mean_t(gen_t K^-1 phi_n) = (mean_t gen_t) K^-1 phi_n needs one row of
+// K^-1-solved features and this matrix-vector product instead of the [T, N] score GEMM.  HBM-bound (N * k * 4 bytes);
+// one warp per row, float4 loads, fp64 accumulation in a fixed order.
+__global__ void matvec_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                                   const float* __restrict__ v, const float* __restrict__ col_scale,
+                                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* xr = x + r * ld;
+  double s = 0.0;
+  if ((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+    const int64_t c4 = cols >> 2;
+    for (int64_t c = lane; c < c4; c += 32) {
+      const float4 a = reinterpret_cast<const float4*>(xr)[c];
+      const float4 b = reinterpret_cast<const float4*>(v)[c];
+      s += static_cast<double>(a.x) * b.x + static_cast<double>(a.y) * b.y + static_cast<double>(a.z) * b.z +
+           static_cast<double>(a.w) * b.w;
+    }
+    for (int64_t c = (c4 << 2) + lane; c < cols; c += 32) s += static_cast<double>(xr[c]) * v[c];
+  } else {
+    for (int64_t c = lane; c < cols; c += 32) s += static_cast<double>(xr[c]) * v[c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = static_cast<float>(col_scale ? s * col_scale[r] : s);
+}
+
+// out[0] = min_i L[i, i], out[1] = max_i L[i, i] of a Cholesky factor: (max / min)^2 is a lower bound of cond(K) and
+// tells the host whether an fp32 factorisation can be trusted at all (one CTA; k reads).
+__global__ void diag_minmax_kernel(const float* __restrict__ L, int64_t ld, int64_t k, float* __restrict__ out) {
+  __shared__ float smin[32], smax[32];
+  float lo = __int_as_float(0x7f800000), hi = 0.f;
+  for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+    const float d = L[i * ld + i];
+    lo = fminf(lo, d);
+    hi = fmaxf(hi, d);
+    if (!(d == d)) lo = d;  // NaN poisons the minimum
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = (l2 != l2 || lo != lo) ? __int_as_float(0x7fc00000) : fminf(lo, l2);
+    hi = fmaxf(hi, h2);
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (unsigned w = 1; w < (blockDim.x >> 5); ++w) {
+      lo = (smin[w] != smin[w] || lo != lo) ? __int_as_float(0x7fc00000) : fminf(lo, smin[w]);
+      hi = fmaxf(hi, smax[w]);
+    }
+    out[0] = lo;
+    out[1] = hi;
+  }
+}
+
 }  // namespace gemm
 }  // namespace gadm

@@ -263,11 +263,12 @@ class CudaProjector:
                 self._project_rows(stage, r1 - r0, model_id, out[r0:r1])
         return out if in_dtype == torch.float32 else out.to(in_dtype)
 
-    def deferred(self, model_id: int = 0, overlap: bool | None = None) -> "DeferredProjection":
+    def deferred(self, model_id: int = 0, overlap: bool | None = None, record_events: bool = False) -> "DeferredProjection":
         """Stage examples in HBM and project ``stage_rows`` of them per kernel pass.  ``overlap``: run the passes on a
         side stream against a second staging buffer so that staging the next batch (and whatever produces it) is
-        not serialised behind the projection; ``None`` = when a second buffer fits in the free HBM."""
-        return DeferredProjection(self, model_id, overlap)
+        not serialised behind the projection; ``None`` = when a second buffer fits in the free HBM.
+        ``record_events``: keep a (start, end) CUDA event pair per pass in ``.pass_events`` (bench.py's roofline)."""
+        return DeferredProjection(self, model_id, overlap, record_events)
 
     def materialize(self, row0: int, nrows: int, model_id: int = 0) -> torch.Tensor:
         """P[row0:row0+nrows, :] as fp32 -- the kernel's own matrix (test / oracle hook)."""
@@ -290,8 +291,9 @@ class DeferredProjection:
     no ``vectorize_and_ignore_buffers``.  ``result()`` returns the [N, proj_dim] fp32 features in insertion order,
     device resident (replaces the per-batch ``.cpu()`` of ``d_trak_grad.py:792``)."""
 
-    def __init__(self, projector: CudaProjector, model_id: int, overlap: bool | None = None):
+    def __init__(self, projector: CudaProjector, model_id: int, overlap: bool | None = None, record_events: bool = False):
         self.p = projector
+        self.pass_events = [] if record_events else None
         self.model_id = model_id
         self.rows = 0
         self.cur = 0
@@ -371,7 +373,7 @@ class DeferredProjection:
         out = torch.empty(self.rows, p.proj_dim, dtype=torch.float32, device=p.device)
         with torch.cuda.device(p.device):
             if not self.overlap:
-                p._project_rows(stage, self.rows, self.model_id, out)
+                self._timed_pass(stage, out)
             else:
                 main = torch.cuda.current_stream(p.device)
                 side = p._side_stream()
@@ -380,7 +382,7 @@ class DeferredProjection:
                 side.wait_event(staged)
                 with torch.cuda.stream(side):
                     p._workspace(self.rows)  # allocated (once) under the side stream
-                    p._project_rows(stage, self.rows, self.model_id, out)
+                    self._timed_pass(stage, out)
                     stage.done = torch.cuda.Event()
                     stage.done.record(side)
                 out.record_stream(side)
@@ -391,6 +393,16 @@ class DeferredProjection:
         self.outputs.append(out)
         self.rows = 0
         p._owner = None
+
+    def _timed_pass(self, stage, out) -> None:
+        if self.pass_events is None:
+            self.p._project_rows(stage, self.rows, self.model_id, out)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()  # on the stream the kernel is launched on
+        self.p._project_rows(stage, self.rows, self.model_id, out)
+        e1.record()
+        self.pass_events.append((e0, e1, self.rows))
 
     def result(self) -> torch.Tensor:
         self.flush()

@@ -126,10 +126,40 @@ def scale_rows_cols_(s: torch.Tensor, row_scale: torch.Tensor | None = None, col
     return s
 
 
-def _dist():
+LOCAL = "local"  # pass as ``group`` to score this process's rows alone even when torch.distributed is initialised
+
+
+def _dist(group=None):
     import torch.distributed as dist
 
+    if group is LOCAL:
+        return None
     return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def _grp(group):
+    return None if group is LOCAL else group
+
+
+# (max pivot / min pivot)^2 of the Cholesky factor is a lower bound of cond(K).  fp32 resolves 2^-24: beyond ~1e7 the
+# factor of an fp32 matrix carries no correct digits in the small-eigenvalue directions, so results are refused
+# instead of returned (the reference inverts in fp64 on its numpy path, compute_gradient_score.py:108-110).
+MAX_FP32_PIVOT_COND = 1.0e7
+
+
+def matvec_rows(x: torch.Tensor, v: torch.Tensor, col_scale: torch.Tensor | None = None) -> torch.Tensor:
+    """out[n] = col_scale[n] * <x[n, :], v>  (HBM-bound GEMV, fp64 accumulation)."""
+    x = _check_cuda_f32(x, "x")
+    v = v.reshape(-1).contiguous().float()
+    if v.numel() != x.shape[1]:
+        raise ValueError(f"vector has {v.numel()} entries, rows have {x.shape[1]}")
+    out = torch.empty(x.shape[0], dtype=_f32, device=x.device)
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        _lib.check(h.lib.gadm_matvec_rows(h.ptr, x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), v.data_ptr(),
+                                         col_scale.data_ptr() if col_scale is not None else None, out.data_ptr(),
+                                         _lib.stream_ptr(x.device)))
+    return out
 
 
 class TrakScorer:
@@ -159,7 +189,7 @@ class TrakScorer:
     def fit(self, train_phi: torch.Tensor, dual: bool | None = None) -> "TrakScorer":
         """train_phi: this rank's [N_local, k] features.  traks.py:149-151 / compute_gradient_score.py:108-110."""
         phi = _check_cuda_f32(train_phi, "train_phi")
-        dist = _dist()
+        dist = _dist(self.group)
         world = dist.get_world_size(self.group) if dist else 1
         n_local = phi.shape[0]
         if world > 1:
@@ -172,14 +202,15 @@ class TrakScorer:
         n_total = sum(lens)
         self.dual = (n_total < phi.shape[1]) if dual is None else bool(dual)
         if self.dual:
-            self.phi_all = _check_cuda_f32(allgather_cat(phi, dim=0, group=self.group), "train_phi")
+            self.phi_all = _check_cuda_f32(phi if dist is None else allgather_cat(phi, dim=0, group=self.group), "train_phi")
             lo = sum(lens[:rank])
             self.local = (lo, lo + n_local)
             gram = gemm_tn(self.phi_all, self.phi_all, lower_only=True, diag_add=self.lam)  # A = Phi Phi^T + lam I
             return self.factor_(gram)
         phi_t = transpose(phi)  # [k, N]: contraction over examples becomes K-major
         gram = gemm_tn(phi_t, phi_t, lower_only=True, diag_add=self.lam / world)
-        allreduce_sum_(gram, self.group)  # one NCCL all-reduce over NVLink (sum of per-rank Grams)
+        if dist is not None:
+            allreduce_sum_(gram, self.group)  # one NCCL all-reduce over NVLink (sum of per-rank Grams)
         return self.factor_(gram)
 
     def partial_fit(self, phi_rows: torch.Tensor) -> "TrakScorer":
@@ -199,7 +230,8 @@ class TrakScorer:
         if getattr(self, "_gram_acc", None) is None:
             raise RuntimeError("finalize() before any partial_fit()")
         gram, self._gram_acc = self._gram_acc, None
-        allreduce_sum_(gram, self.group)
+        if _dist(self.group) is not None:
+            allreduce_sum_(gram, self.group)
         gram.diagonal().add_(self.lam)
         self.dual = False
         return self.factor_(gram)
@@ -218,8 +250,12 @@ class TrakScorer:
         with torch.cuda.device(gram.device):
             _lib.check(h.lib.gadm_cholesky(h.ptr, gram.data_ptr(), gram.stride(0), self.k, self.blocks.data_ptr(), nbytes,
                                           C.cast(self.info.data_ptr(), C.POINTER(C.c_int)), _lib.stream_ptr(gram.device)))
+            self.pivots = torch.empty(2, dtype=_f32, device=gram.device)
+            _lib.check(h.lib.gadm_diag_minmax(h.ptr, gram.data_ptr(), gram.stride(0), self.k, self.pivots.data_ptr(),
+                                             _lib.stream_ptr(gram.device)))
         self.L = gram
         self.U = None
+        self._checked = False
         return self
 
     def _tri_inverse_(self) -> "TrakScorer":
@@ -236,11 +272,23 @@ class TrakScorer:
                                               ws.data_ptr(), ws.numel(), _lib.stream_ptr(gram.device)))
         return self
 
-    def check(self) -> None:
-        """Host sync: raise if the factorisation met a non-positive pivot."""
+    def check(self, max_cond: float = MAX_FP32_PIVOT_COND) -> None:
+        """Host sync (one small D2H, cached): raise if the factorisation met a non-positive / NaN pivot (the kernel
+        substitutes 1 and carries on, so everything downstream would be finite garbage) or if the pivot range shows
+        that fp32 cannot resolve the matrix."""
+        if getattr(self, "_checked", False):
+            return
         bad = int(self.info.item())
         if bad:
-            raise _lib.GadmError(f"Gram matrix is not positive definite (pivot {bad - 1})")
+            raise _lib.GadmError(f"Gram matrix + lam*I is not positive definite in fp32 (pivot {bad - 1}): features "
+                                 "contain NaN / Inf or the system is too ill-conditioned for the fp32 factorisation")
+        lo, hi = (float(x) for x in self.pivots.tolist())
+        if not (lo > 0.0) or not (hi < float("inf")):
+            raise _lib.GadmError(f"Cholesky factor has a non-finite or non-positive pivot range [{lo}, {hi}]")
+        if (hi / lo) ** 2 > max_cond:
+            raise _lib.GadmError(f"system is too ill-conditioned for fp32 (pivot-ratio bound cond >= {(hi / lo) ** 2:.3g} > "
+                                 f"{max_cond:.3g}); rescale the features or increase lam")
+        self._checked = True
 
     def _solve(self, rows: torch.Tensor, inplace: bool = False) -> torch.Tensor:
         """rows [m, self.k] -> rows @ (factored matrix)^-1 = (rows L^-T) L^-1: two GEMMs against the explicit
@@ -300,39 +348,63 @@ TRAK_VARIANTS = ("grad_sim", "trak", "relative_influence", "renorm_influence")
 
 def trak_scores(train_phi: torch.Tensor, gen_phi: torch.Tensor, lam: float = 5e-1,
                 variants: Sequence[str] = TRAK_VARIANTS, journey_phi: torch.Tensor | None = None,
-                group=None, gather: bool = True, return_scorer: bool = False, dual: bool | None = None):
+                group=None, gather: bool = True, return_scorer: bool = False, dual: bool | None = None,
+                check: bool = True):
     """Per-training-example attribution vectors of text_to_image/traks.py:139-173 (mean over generated images).
 
     Returns dict name -> fp32 tensor [N] (all ranks' examples when ``gather`` and torch.distributed is up).
     ``journey_trak`` is added when ``journey_phi`` is given.  D-TRAK (traks.py:176-186) is the same call on the
-    mean-squared-l2-norm features."""
+    mean-squared-l2-norm features.
+
+    Every variant is a mean over generated images of something linear in the generated features, so the mean is
+    taken FIRST: ``mean_t(gen_t) K^-1 Phi^T`` is one solved row and a matrix-vector product over the training
+    features instead of the reference's [T, N] GEMM followed by ``.mean(dim=0)`` (traks.py:156-157); the [T, N]
+    matrix itself is still available from ``gradient_scores`` / ``TrakScorer.score_matrix``.  ``check`` raises (one
+    small host sync) when the factorisation failed or is beyond fp32 instead of returning finite garbage."""
     train = _check_cuda_f32(train_phi, "train_phi")
     gen = _check_cuda_f32(gen_phi, "gen_phi")
     out = {}
     inv_train_norm = None
     if "grad_sim" in variants or "renorm_influence" in variants:
         inv_train_norm = row_norms(train, reciprocal=True)
-    if "grad_sim" in variants:  # traks.py:141-146
-        cos = gemm_tn(gen, train)
-        out["grad_sim"] = col_mean_scaled(cos, row_norms(gen, reciprocal=True), inv_train_norm)
-        del cos
+    if "grad_sim" in variants:  # traks.py:141-146: mean_t cos(gen_t, phi_n) = <mean_t gen_t / |gen_t|, phi_n> / |phi_n|
+        out["grad_sim"] = matvec_rows(train, col_mean_scaled(gen, row_norms(gen, reciprocal=True)), inv_train_norm)
     scorer = None
     if any(v in variants for v in ("trak", "relative_influence", "renorm_influence")) or journey_phi is not None:
         scorer = TrakScorer(lam, group).fit(train, dual=dual)  # dual=None: N x N system when N_total < k
-        s = scorer.score_matrix(gen, train)  # [T, N]
-        if "trak" in variants:
-            out["trak"] = col_mean_scaled(s)  # traks.py:156-157
-        if "relative_influence" in variants:  # traks.py:161-164: / ||K^-1 phi_n||
-            out["relative_influence"] = col_mean_scaled(s, None, scorer.train_weight_norms(train))
-        if "renorm_influence" in variants:  # traks.py:166-168: / ||phi_n||
-            out["renorm_influence"] = col_mean_scaled(s, None, inv_train_norm)
-        del s
+
+        def mean_scores(rows_phi):
+            """mean_t (rows_t K^-1 phi_n) for this rank's examples, unscaled."""
+            bar = col_mean_scaled(rows_phi)  # [k]
+            if scorer.dual:
+                y = matvec_rows(scorer.phi_all, bar)  # (mean gen) Phi^T   [N_total]
+                z = scorer._solve(y[None, :])[0]      # ... A^-1
+                return z[scorer.local[0]:scorer.local[1]].contiguous()
+            return matvec_rows(train, scorer._solve(bar[None, :])[0])
+
+        need = [v for v in ("trak", "relative_influence", "renorm_influence") if v in variants]
+        if need:
+            m = mean_scores(gen)
+            if "trak" in variants:
+                out["trak"] = m  # traks.py:156-157
+            if "relative_influence" in variants:  # traks.py:161-164: / ||K^-1 phi_n||
+                out["relative_influence"] = _scaled(m, scorer.train_weight_norms(train))
+            if "renorm_influence" in variants:  # traks.py:166-168: / ||phi_n||
+                out["renorm_influence"] = _scaled(m, inv_train_norm)
         if journey_phi is not None:  # traks.py:171-173
-            out["journey_trak"] = col_mean_scaled(scorer.score_matrix(_check_cuda_f32(journey_phi, "journey_phi"), train))
-    if gather:
+            out["journey_trak"] = mean_scores(_check_cuda_f32(journey_phi, "journey_phi"))
+        if check:
+            scorer.check()
+    if gather and _dist(group) is not None:
         for name, v in list(out.items()):
             out[name] = allgather_cat(v, dim=0, group=group)  # one all-gather of the per-example score slices
     return (out, scorer) if return_scorer else out
+
+
+def _scaled(v: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """v[n] * scale[n] through the row/column scaling kernel (keeps elementwise torch math off the product path)."""
+    out = v.clone().reshape(1, -1)
+    return scale_rows_cols_(out, None, scale)[0]
 
 
 def group_and_rank(sample_output_dict: dict, group_ids, num_groups: int):
@@ -363,8 +435,12 @@ def aggregate_by_class(scores, labels, by: str = "mean", compat_max_over_all_row
     lut = {v: i for i, v in enumerate(uniq)}
     gid = np.array([lut[v] for v in labels.tolist()], dtype=np.int32)
     rows = []
+    counts = np.bincount(gid, minlength=len(uniq))
     for r in range(scores.shape[0]):
-        rows.append(group_reduce(scores[r].contiguous(), gid, len(uniq), "mean" if by == "mean" else "max"))
+        if by == "mean":  # np.divide(scores[:, mask].sum(axis=1), np.sum(mask)): sum in the scores' dtype, division in fp64
+            rows.append(group_reduce(scores[r].contiguous(), gid, len(uniq), "sum") / counts)
+        else:
+            rows.append(group_reduce(scores[r].contiguous(), gid, len(uniq), "max"))
     result = np.stack(rows)
     if by == "max" and compat_max_over_all_rows:
         result[:] = result.max(axis=0, keepdims=True)
@@ -372,8 +448,9 @@ def aggregate_by_class(scores, labels, by: str = "mean", compat_max_over_all_row
 
 
 def gradient_scores(train_phi: torch.Tensor, val_phi: torch.Tensor, gradient_type: str = "trak", lam: float = 5e-1,
-                    kernel_inverse: torch.Tensor | None = None):
-    """Score matrix [T, N] of compute_gradient_score.py:108-126 for one gradient_type; returns (scores, scorer)."""
+                    kernel_inverse: torch.Tensor | None = None, check: bool = True):
+    """Score matrix [T, N] of compute_gradient_score.py:108-126 for one gradient_type; returns (scores, scorer).
+    ``check``: raise instead of returning finite garbage when the factorisation failed (TrakScorer.check)."""
     train = _check_cuda_f32(train_phi, "train_phi")
     val = _check_cuda_f32(val_phi, "val_phi")
     if gradient_type == "vanilla_gradient":  # :114-117
@@ -406,6 +483,8 @@ def gradient_scores(train_phi: torch.Tensor, val_phi: torch.Tensor, gradient_typ
         s = gemm_tn(val, w) if w is not None else scorer.score_matrix(val, train)
     if col is not None:
         scale_rows_cols_(s, None, col)
+    if check and scorer is not None:
+        scorer.check()
     return s, scorer
 
 
@@ -482,6 +561,7 @@ def compute_gradient_scores(args, retraining: bool = False, training_seeds: Iter
             # the reference builds and caches the kernel before it looks at gradient_type (:102-111)
             if scorer is None:
                 scorer = TrakScorer(5e-1).fit(train)
+            scorer.check()  # never cache the inverse of a factorisation that failed or is beyond fp32
             np.save(kernel_path, scorer.kernel_inverse().double().cpu().numpy())
     is_local = args.model_behavior_key in ["ssim", "nrmse", "diffusion_loss"]
     if getattr(args, "by_class", False):

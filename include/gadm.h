@@ -181,6 +181,14 @@ int gadm_tri_inverse(gadm_handle h, const float* l, int64_t ldl, const void* blo
  * gadm_cholesky, u: its transpose (gadm_transpose), blocks: the same workspace. */
 int gadm_solve_rows(gadm_handle h, const float* l, int64_t ldl, const float* u, int64_t ldu, const void* blocks,
                     int64_t k, float* y, int64_t ldy, int64_t m, void* stream);
+/* out[r] = col_scale[r] * sum_j x[r, j] * v[j]  (col_scale may be NULL).  The mean over generated images of
+ * traks.py:157,162-168 is linear in the generated features: mean_t(gen_t K^-1 phi_n) = (mean_t gen_t) K^-1 phi_n,
+ * i.e. one solved row and this product instead of the [T, N] score GEMM. */
+int gadm_matvec_rows(gadm_handle h, const float* x, int64_t rows, int64_t cols, int64_t ld, const float* v,
+                     const float* col_scale, float* out, void* stream);
+/* out2[0] = min_i L[i, i], out2[1] = max_i L[i, i] of the factor left by gadm_cholesky ((max / min)^2 bounds cond(K)
+ * from below: the host refuses fp32 results when it exceeds what fp32 can resolve; NaN pivots give NaN) */
+int gadm_diag_minmax(gadm_handle h, const float* l, int64_t ld, int64_t k, float* out2, void* stream);
 /* out[r] = ||x[r, :]||_2, or 1 / that when reciprocal != 0 (traks.py:143,162,166) */
 int gadm_row_norms(gadm_handle h, const float* x, int64_t rows, int64_t cols, int64_t ld, int reciprocal, float* out,
                    void* stream);

@@ -269,3 +269,42 @@ def test_bca_bootstrap_ci_end_to_end():
         assert abs(a.standard_error - b.standard_error) < tol
     assert ours.bootstrap_distribution.shape == (100,)
     assert ours.confidence_interval.low < ours.confidence_interval.high
+
+
+def test_rank_hygiene_numpy_summation_order_on_near_ties():
+    """np.argsort(-x.mean(axis=-1), kind="stable") (shapley_lds.py:294, traks.py:218) on rows engineered so that the
+    ORDER of the fp64 summation decides the ranking: pairs of rows hold the same multiset of values in different
+    positions (their exact sums are equal; their numpy-order sums differ in the last ulp or not at all) plus exact
+    ties.  The device means must equal numpy's bit for bit, hence the ranks."""
+    import gadm_b200 as G
+
+    rng = np.random.RandomState(7)
+    for K in (1, 5, 8, 37, 128, 129, 1000):
+        base = rng.normal(size=(40, K)) * rng.choice([1.0, 1e8, 1e-8], size=(40, K))
+        rows = [base]
+        for rep in range(3):  # permuted copies: near-ties by construction
+            rows.append(np.stack([r[rng.permutation(K)] for r in base]))
+        rows.append(base[:5].copy())  # exact ties -> lower index first
+        x = np.concatenate(rows)
+        want_mean = x.mean(axis=-1)
+        np.testing.assert_array_equal(G.stable_rank(x), np.argsort(-want_mean, kind="stable"))
+    # group sums in the values' own precision and numpy order (traks.py:188-204 on float32 attrs)
+    attrs = (rng.normal(size=5000) * rng.choice([1.0, 1e4], size=5000)).astype(np.float32)
+    groups = rng.randint(0, 258, size=5000)
+    groups[groups == 17] = 16  # an empty group
+    got_sum = G.group_reduce(attrs, groups, 258, "sum")
+    got_mean = G.group_reduce(attrs, groups, 258, "mean")
+    got_max = G.group_reduce(attrs, groups, 258, "max")
+    for g in range(258):
+        idx = np.where(groups == g)[0]
+        if len(idx) == 0:
+            assert got_sum[g] == 0.0 and np.isnan(got_mean[g])
+            continue
+        assert got_sum[g] == np.float64(attrs[idx].sum()), g
+        assert got_mean[g] == np.float64(attrs[idx].mean()), g
+        assert got_max[g] == np.float64(attrs[idx].max()), g
+    # and for float64 attrs
+    a64 = attrs.astype(np.float64) * 1.000000001
+    got = G.group_reduce(a64, groups, 258, "sum")
+    for g in (0, 1, 100, 257):
+        assert got[g] == a64[np.where(groups == g)[0]].sum()

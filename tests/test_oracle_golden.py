@@ -105,3 +105,23 @@ def test_shapley_properties():
     np.testing.assert_allclose(phi, w, atol=1e-8)  # linear game -> exact recovery
     Xu = oagg.uniform_masks(d, list(range(n)))
     np.testing.assert_allclose(oagg.data_banzhaf(Xu, (Xu - 0.5) @ w), w, atol=1e-8)  # no intercept in the model
+
+
+def test_numpy_pairwise_sum_restatement_is_numpys_order():
+    """The summation order csrc/aggregate.cuh reproduces (rank hygiene: np.argsort(-x.mean(-1)) near-ties) is numpy's
+    own: 0 + pairwise_sum, for every n up to 300 and sizes around numpy's buffer / block limits, fp32 and fp64."""
+    import warnings
+
+    from oracle.aggregation import numpy_pairwise_sum
+
+    rng = np.random.RandomState(0)
+    for dtype in (np.float32, np.float64):
+        for n in list(range(1, 300)) + [1000, 1001, 4096, 8191, 8192, 8193, 20000]:
+            a = (rng.normal(size=n) * rng.choice([1, 1e3, 1e-3], size=n)).astype(dtype)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                assert dtype(dtype(0) + numpy_pairwise_sum(a, dtype)) == a.sum(), (dtype, n)
+    x = rng.normal(size=(40, 53))
+    want = x.mean(axis=-1)
+    got = np.array([(0.0 + numpy_pairwise_sum(r)) / 53 for r in x])
+    np.testing.assert_array_equal(got, want)

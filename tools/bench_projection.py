@@ -1,4 +1,4 @@
-"""Kernel-only timing of the projection at a named shape (CUDA events, staged bf16 input resident)."""
+"""Kernel-only timing of the projection at a named shape (CUDA events, staged 16-bit input resident)."""
 import argparse
 import json
 import sys, os
@@ -16,34 +16,41 @@ def main():
     ap.add_argument("--type", default="rademacher")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--cta-group", type=int, default=0, help="0 = projector default (4 for normal, 2 for rademacher)")
+    ap.add_argument("--stage-dtype", default=None, help="f16 (default) or bf16")
     ap.add_argument("--check", type=int, default=0,
                     help="rows to compare with an fp64 product against the kernel's own materialised P (full D)")
     a = ap.parse_args()
     dev = "cuda:0"
     if a.M == 0:
         a.M = 1024 if (a.type == "normal" and a.cta_group in (0, 4)) else 512
-    p = CudaProjector(a.D, a.k, 42, ProjectionType(a.type), dev, 32, stage_rows=a.M, cta_group=a.cta_group or None)
+    p = CudaProjector(a.D, a.k, 42, ProjectionType(a.type), dev, 32, stage_rows=a.M, cta_group=a.cta_group or None,
+                      stage_dtype=a.stage_dtype)
     a.cta_group = p._group_for(a.M)
-    stage = p._stage_buffer(a.M)  # tile-major [nkb, M, 64]
+    st = p._stage(a.M)
+    stage = st.data  # tile-major [nkb, M, 64]
+    f16 = st.inv_scale is not None
+    amp, inv = (512.0, 2.0 ** -19) if f16 else (1e-3, 1.0)  # f16 groups: values ~2^9 in the buffer, scale 2^-19 -> ~1e-3
+    if f16:
+        st.inv_scale.fill_(inv)
     g = torch.Generator(device=dev).manual_seed(1234)
     nkb = stage.shape[0]
     sq = torch.zeros(a.M, device=dev, dtype=torch.float64)
     for k0 in range(0, nkb, 8192):  # fill the staged buffer in slabs (bf16 randn * 1e-3)
         k1 = min(nkb, k0 + 8192)
-        blk = (torch.randn(k1 - k0, a.M, 64, device=dev, generator=g) * 1e-3).to(torch.bfloat16)
+        blk = (torch.randn(k1 - k0, a.M, 64, device=dev, generator=g) * amp).to(stage.dtype)
         if k1 == nkb and a.D % 64:
             blk[-1, :, a.D % 64:] = 0  # positions beyond the gradient length stay zero
         stage[k0:k1] = blk
-        sq += blk.double().pow(2).sum(dim=(0, 2))
+        sq += (blk.double() * inv).pow(2).sum(dim=(0, 2))
     gnorm = sq.sqrt().mean()
     out = torch.empty(a.M, a.k, device=dev)
-    p._project_rows(stage, a.M, 0, out)
+    p._project_rows(st, a.M, 0, out)
     torch.cuda.synchronize()
     ts = []
     for _ in range(a.iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        p._project_rows(stage, a.M, 0, out)
+        p._project_rows(st, a.M, 0, out)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -59,7 +66,7 @@ def main():
             k1 = min(nkb, k0 + step_kb)
             n = min(a.D, k1 * 64) - k0 * 64
             P = p.materialize(k0 * 64, n).double()
-            g = stage[k0:k1].index_select(1, rows_sel).permute(1, 0, 2).reshape(R, -1)[:, :n].double()
+            g = stage[k0:k1].index_select(1, rows_sel).permute(1, 0, 2).reshape(R, -1)[:, :n].double() * inv
             want += g @ P
             del P, g
         got = out.index_select(0, rows_sel).double()
@@ -68,7 +75,7 @@ def main():
         chk = {"rel_err_rows": [float(x) for x in rel], "scale_err_rows": [float(x) for x in shrink],
                "max_abs_over_rownorm": float(((got - want).abs().max(dim=1).values / want.norm(dim=1) * a.k ** 0.5).max())}
     flops = 2.0 * a.M * a.D * a.k
-    print(json.dumps({"D": a.D, "k": a.k, "M": a.M, "type": a.type, "cta_group": a.cta_group, "ms": ts,
+    print(json.dumps({"D": a.D, "k": a.k, "M": a.M, "type": a.type, "cta_group": a.cta_group, "stage_dtype": p.stage_dtype, "ms": ts,
                       "tflops": flops / ms / 1e9, "frac_of_1590": flops / ms / 1e9 / 1590.4,
                       "gen_elems_per_s": a.D * a.k / ms * 1e3, "watchdog": p._handle.watchdog_code(),
                       "norm_ratio": float(out.double().norm(dim=1).mean() / (gnorm * a.k ** 0.5)),
