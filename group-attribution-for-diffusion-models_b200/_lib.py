@@ -32,7 +32,7 @@ _SIGNATURES = {
                                        c_vp]),
     "gadm_project_staged": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp,
                                       c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp]),
-    "gadm_materialize_p": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, c_vp, c_vp]),
+    "gadm_materialize_p": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, C.c_int, C.c_int, c_vp, c_vp]),
     "gadm_gemm_tn": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_float, C.c_float,
                                C.c_float, C.c_int, c_vp]),
     "gadm_gemm_tn_batched": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64,

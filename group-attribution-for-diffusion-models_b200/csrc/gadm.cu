@@ -521,7 +521,9 @@ int gadm_project_staged(gadm_handle h, const void* staged, int stage_dtype, cons
   // k-blocks per TMEM accumulation segment (see project.cuh).  Measured at the C2 shape (fp64 reference, full D):
   // normal 256 -> 1.9e-5 relative error (unsegmented 1.3e-3), Rademacher 512 -> 1.3e-6; each costs ~2 % throughput.
   // GADM_PROJ_SEG_KB overrides for tuning.
-  a.seg_kb = (proj_type == gadm::kProjRademacher) ? 512u : 256u;
+  // fp16 inputs carry 11 significant bits, so each truncating TMEM add loses more than with bf16 inputs: Rademacher at
+  // 512-k-block segments measured 7.8e-6 with F16G staging (1.3e-6 with bf16) -> 256 for both types there.
+  a.seg_kb = (proj_type == gadm::kProjRademacher && stage_dtype == GADM_STAGE_BF16) ? 512u : 256u;
   if (const char* e = getenv("GADM_PROJ_SEG_KB")) { const long v = atol(e); if (v >= 1) a.seg_kb = (uint32_t)v; }
   a.m_rows = (uint32_t)m_rows;
   a.a_fmt = (stage_dtype == GADM_STAGE_F16G) ? gadm::UMMA_FMT_F16 : gadm::UMMA_FMT_BF16;
@@ -562,7 +564,7 @@ int gadm_project_staged(gadm_handle h, const void* staged, int stage_dtype, cons
 }
 
 int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_dim, uint64_t seed64, int proj_type,
-                       float* out, void* stream) {
+                       int stage_dtype, float* out, void* stream) {
   GADM_REQUIRE(h && out, "null argument");
   GADM_REQUIRE(row0 >= 0 && nrows > 0 && proj_dim > 0, "bad shape");
   GADM_REQUIRE(proj_type == GADM_PROJ_NORMAL || proj_type == GADM_PROJ_RADEMACHER, "unknown proj_type %d", proj_type);
@@ -570,7 +572,8 @@ int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_
   const int64_t total = nrows * proj_dim;
   const int threads = 256;
   gadm::proj::materialize_p_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
-      out, row0, nrows, proj_dim, (uint32_t)(seed64 & 0xFFFFFFFFull), (uint32_t)(seed64 >> 32), proj_type);
+      out, row0, nrows, proj_dim, (uint32_t)(seed64 & 0xFFFFFFFFull), (uint32_t)(seed64 >> 32), proj_type,
+      stage_dtype == GADM_STAGE_F16G ? 1 : 0);
   GADM_CUDA(cudaGetLastError());
   h->launches++;
   return GADM_OK;

@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gadm {
 
@@ -40,19 +41,26 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ uint4 rademacher_call(uint32_t p_div32, uint32_t j_div4, uint32_t k0, uint32_t k1) {
   return philox4x32_10(p_div32, j_div4, 0u, kTagRademacher, k0, k1);
 }
-// 8 sign bits -> 8 bf16 (+1 / -1) packed in a 16-byte chunk; bit e -> element e (bit set = -1)
-__device__ __forceinline__ uint4 rademacher_expand8(uint32_t byte) {
+// P is written in the 16-bit format of the staged gradients (tcgen05 kind::f16 takes f16 x f16 or bf16 x bf16; a
+// mixed pair faults on sm_100a): +-1 is exact in both, the normal type is Box-Muller rounded to that format.
+constexpr uint32_t kOnesBf16 = 0x3F803F80u;  // two bf16 1.0
+constexpr uint32_t kOnesF16 = 0x3C003C00u;   // two fp16 1.0
+
+// 8 sign bits -> 8 16-bit (+1 / -1) values packed in a 16-byte chunk; bit e -> element e (bit set = -1).
+// `ones` = kOnesBf16 or kOnesF16.
+__device__ __forceinline__ uint4 rademacher_expand8(uint32_t byte, uint32_t ones) {
   // (byte >> 2q) * (2^15 + 2^30): bit 2q -> bit 15, bit 2q+1 -> bit 31 (byte < 2^8 so the copies never overlap)
   uint4 o;
-  o.x = ((byte * 0x40008000u) & 0x80008000u) | 0x3F803F80u;
-  o.y = ((byte * 0x10002000u) & 0x80008000u) | 0x3F803F80u;
-  o.z = ((byte * 0x04000800u) & 0x80008000u) | 0x3F803F80u;
-  o.w = ((byte * 0x01000200u) & 0x80008000u) | 0x3F803F80u;
+  o.x = ((byte * 0x40008000u) & 0x80008000u) | ones;
+  o.y = ((byte * 0x10002000u) & 0x80008000u) | ones;
+  o.z = ((byte * 0x04000800u) & 0x80008000u) | ones;
+  o.w = ((byte * 0x01000200u) & 0x80008000u) | ones;
   return o;
 }
 
-// ---- Normal: one call covers 8 consecutive p for one j -> one 16-byte chunk of bf16.
-__device__ __forceinline__ uint32_t box_muller_pair_bf16(uint32_t x) {
+// ---- Normal: one call covers 8 consecutive p for one j -> one 16-byte chunk of bf16 (kF16 = false) or fp16.
+template <bool kF16>
+__device__ __forceinline__ uint32_t box_muller_pair(uint32_t x) {
   // lo16 -> u1 = (lo + 0.5) / 2^16 (exact), hi16 -> turn = (hi + 0.5) / 2^16 (exact)
   const float flo = __uint_as_float(0x4B000000u | (x & 0xFFFFu));         // 2^23 + lo
   const float fhi = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7632));  // 2^23 + hi
@@ -66,13 +74,19 @@ __device__ __forceinline__ uint32_t box_muller_pair_bf16(uint32_t x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(-1.3862943611198906f, l2)));  // sqrt(-2 ln u1)
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(theta));
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(theta));
-  const __nv_bfloat162 v = __floats2bfloat162_rn(__fmul_rn(r, c), __fmul_rn(r, s));  // .x (low) = even p
-  return *reinterpret_cast<const uint32_t*>(&v);
+  if constexpr (kF16) {
+    const __half2 v = __floats2half2_rn(__fmul_rn(r, c), __fmul_rn(r, s));  // .x (low) = even p
+    return *reinterpret_cast<const uint32_t*>(&v);
+  } else {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(__fmul_rn(r, c), __fmul_rn(r, s));
+    return *reinterpret_cast<const uint32_t*>(&v);
+  }
 }
+template <bool kF16>
 __device__ __forceinline__ uint4 normal_chunk(uint32_t p_div8, uint32_t j, uint32_t k0, uint32_t k1) {
   const uint4 w = philox4x32_10(p_div8, j, 0u, kTagNormal, k0, k1);
-  return make_uint4(box_muller_pair_bf16(w.x), box_muller_pair_bf16(w.y), box_muller_pair_bf16(w.z),
-                    box_muller_pair_bf16(w.w));
+  return make_uint4(box_muller_pair<kF16>(w.x), box_muller_pair<kF16>(w.y), box_muller_pair<kF16>(w.z),
+                    box_muller_pair<kF16>(w.w));
 }
 
 }  // namespace gadm

@@ -47,6 +47,15 @@ constexpr int kTmemCols = 512;
 constexpr int kGenBackoffNs = GADM_GEN_BACKOFF_NS;  // poll interval of generator warps waiting for their slot (mbar_wait)
 constexpr int kEpiBackoffNs = GADM_EPI_BACKOFF_NS;  // ... of epilogue warps waiting for the end of a segment
 
+// Register budget of the projection kernels: by default whatever fits one CTA per SM (__launch_bounds__); a build with
+// -DGADM_PROJ_MAXNREG=N caps it instead, which leaves more of the register file to kernels that run beside the
+// persistent projection (staging of the next pass).
+#ifdef GADM_PROJ_MAXNREG
+#define GADM_PROJ_BOUNDS __maxnreg__(GADM_PROJ_MAXNREG)
+#else
+#define GADM_PROJ_BOUNDS __launch_bounds__(Roles<kWarpsPerGroup>::kThreads, 1)
+#endif
+
 // Warp roles.  Generator warps come FIRST and the single-thread TMA / MMA roles LAST: the SM sub-partition
 // arbiter favours the highest warp id among eligible warps, and a late MMA / TMA issue stalls the whole
 // pipeline while a late generator instruction does not.
@@ -95,7 +104,7 @@ struct Args {
   uint32_t sync_every;    // k-blocks between lockstep points
   uint32_t seg_kb;        // k-blocks accumulated in TMEM before the accumulators are promoted into the partial tile
   uint32_t m_rows;        // staged rows in use (rows beyond it are never scaled nor reduced)
-  uint32_t a_fmt;         // UMMA format of the staged gradients: UMMA_FMT_BF16 or UMMA_FMT_F16 (P is always bf16)
+  uint32_t a_fmt;         // UMMA format of the staged gradients AND of the generated P: UMMA_FMT_BF16 or UMMA_FMT_F16
   const float* inv_scale; // F16G staging: [m_cap][scale_groups] inverse power-of-two scales (nullptr: unscaled)
   uint32_t scale_groups;  // scale groups per row = ceil(nkb_total / group_kb)
   uint32_t group_kb;      // k-blocks per scale group (multiple of seg_kb)
@@ -226,7 +235,7 @@ __device__ __forceinline__ void grid_lockstep(uint32_t* counter, uint32_t target
 //   smem_b: stage base (1024-aligned); p_div32: canonical p of stage column 0, / 32; j0: first Phi column
 template <int kBRows, int kGroupThreads>
 __device__ __forceinline__ void gen_rademacher_stage(uint32_t smem_b, uint32_t p_div32, uint32_t j0, uint32_t k0,
-                                                     uint32_t k1, int tig, int lane) {
+                                                     uint32_t k1, int tig, int lane, uint32_t ones) {
   constexpr int kJGroups = kBRows / 4;
   constexpr int kCalls = kJGroups * 2;
   const int rot = (lane >> 1) & 3;
@@ -248,14 +257,14 @@ __device__ __forceinline__ void gen_rademacher_stage(uint32_t smem_b, uint32_t p
       for (int cc = 0; cc < 4; ++cc) {
         const uint32_t byte = (words[i] >> (8 * cc)) & 0xFFu;
         const uint32_t chunk = 4 * pg + cc;
-        st_shared_v4(row_addr + ((chunk ^ sw) << 4), rademacher_expand8(byte));
+        st_shared_v4(row_addr + ((chunk ^ sw) << 4), rademacher_expand8(byte, ones));
       }
     }
   }
 }
 
 // Fill one B stage with bf16 N(0,1) values.  p_div8: canonical p of stage column 0, / 8.
-template <int kBRows, int kGroupThreads>
+template <int kBRows, int kGroupThreads, bool kF16>
 __device__ __forceinline__ void gen_normal_stage(uint32_t smem_b, uint32_t p_div8, uint32_t j0, uint32_t k0,
                                                  uint32_t k1, int tig) {
   constexpr int kCalls = kBRows * 8;
@@ -263,13 +272,13 @@ __device__ __forceinline__ void gen_normal_stage(uint32_t smem_b, uint32_t p_div
   for (int e = tig; e < kCalls; e += kGroupThreads) {
     const int row = e % kBRows;
     const int c = e / kBRows;
-    const uint4 v = normal_chunk(p_div8 + c, j0 + row, k0, k1);
+    const uint4 v = normal_chunk<kF16>(p_div8 + c, j0 + row, k0, k1);
     st_shared_v4(smem_b + row * 128 + ((c ^ (row & 7)) << 4), v);
   }
 }
 
 template <int kCtaGroup, int kWarpsPerGroup>
-__global__ void __launch_bounds__(Roles<kWarpsPerGroup>::kThreads, 1)
+__global__ void GADM_PROJ_BOUNDS
 project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   using C = Cfg<kCtaGroup>;
   using R = Roles<kWarpsPerGroup>;
@@ -343,7 +352,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   } else if (warp == R::kMmaWarp) {
     // ===================== MMA issuer (leader CTA, one thread)
     if (rank == 0 && lane == 0) {
-      const uint32_t idesc = umma_idesc_ab(a.a_fmt, UMMA_FMT_BF16, kAccRows * kCtaGroup, kTileN);
+      const uint32_t idesc = umma_idesc(a.a_fmt, kAccRows * kCtaGroup, kTileN);
       uint32_t it = 0, seg_iter = 0;
       for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
         const uint32_t split = u / a.n_tiles;
@@ -420,9 +429,12 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
         if (a.debug & 1u) {
           // ablation: publish the slot without generating
         } else if (a.proj_type == kProjRademacher)
-          gen_rademacher_stage<C::kBRows, R::kGroupThreads>(smem_b(s), p_div64 * 2u, j0, a.key0, a.key1, tig, lane);
+          gen_rademacher_stage<C::kBRows, R::kGroupThreads>(smem_b(s), p_div64 * 2u, j0, a.key0, a.key1, tig, lane,
+                                                            a.a_fmt == UMMA_FMT_F16 ? kOnesF16 : kOnesBf16);
+        else if (a.a_fmt == UMMA_FMT_F16)
+          gen_normal_stage<C::kBRows, R::kGroupThreads, true>(smem_b(s), p_div64 * 8u, j0, a.key0, a.key1, tig);
         else
-          gen_normal_stage<C::kBRows, R::kGroupThreads>(smem_b(s), p_div64 * 8u, j0, a.key0, a.key1, tig);
+          gen_normal_stage<C::kBRows, R::kGroupThreads, false>(smem_b(s), p_div64 * 8u, j0, a.key0, a.key1, tig);
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the UMMA (async proxy) reads
         __syncwarp();
         if (lane == 0) {
@@ -462,7 +474,7 @@ __global__ void project_reduce_kernel(const float* __restrict__ partial, float* 
 // Oracle hook: P[row0 + r, j] for r < nrows, j < k as fp32, using the very device functions the
 // projection kernel uses (so a host-side G @ P reproduces the kernel up to summation order).
 __global__ void materialize_p_kernel(float* __restrict__ out, int64_t row0, int64_t nrows, int64_t k, uint32_t key0,
-                                     uint32_t key1, int proj_type) {
+                                     uint32_t key1, int proj_type, int f16) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= nrows * k) return;
   const int64_t r = idx / k, j = idx % k;
@@ -473,15 +485,16 @@ __global__ void materialize_p_kernel(float* __restrict__ out, int64_t row0, int6
     const uint32_t words[4] = {w.x, w.y, w.z, w.w};
     const uint32_t word = words[j & 3];
     const uint32_t byte = (word >> (8 * ((p & 31) >> 3))) & 0xFFu;
-    const uint4 e = rademacher_expand8(byte);
+    const uint4 e = rademacher_expand8(byte, f16 ? kOnesF16 : kOnesBf16);
     const uint32_t pk[4] = {e.x, e.y, e.z, e.w};
     const uint32_t h = (pk[(p & 7) >> 1] >> (16 * (p & 1))) & 0xFFFFu;
-    v = __uint_as_float(h << 16);
+    v = f16 ? __half2float(__ushort_as_half(static_cast<unsigned short>(h))) : __uint_as_float(h << 16);
   } else {
-    const uint4 c = normal_chunk(static_cast<uint32_t>(p >> 3), static_cast<uint32_t>(j), key0, key1);
+    const uint4 c = f16 ? normal_chunk<true>(static_cast<uint32_t>(p >> 3), static_cast<uint32_t>(j), key0, key1)
+                        : normal_chunk<false>(static_cast<uint32_t>(p >> 3), static_cast<uint32_t>(j), key0, key1);
     const uint32_t pk[4] = {c.x, c.y, c.z, c.w};
     const uint32_t h = (pk[(p & 7) >> 1] >> (16 * (p & 1))) & 0xFFFFu;
-    v = __uint_as_float(h << 16);
+    v = f16 ? __half2float(__ushort_as_half(static_cast<unsigned short>(h))) : __uint_as_float(h << 16);
   }
   out[idx] = v;
 }

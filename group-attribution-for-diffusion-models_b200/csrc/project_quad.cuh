@@ -24,7 +24,7 @@ constexpr uint32_t kQuadShipBytes = kQuadOwnRows * kBlockK * 2;  // 8 KiB
 
 template <int kRows, int kGroupThreads>
 __device__ __forceinline__ void gen_rademacher_rows(uint32_t smem_b, int row_base, uint32_t p_div32, uint32_t j0,
-                                                    uint32_t k0, uint32_t k1, int tig, int lane) {
+                                                    uint32_t k0, uint32_t k1, int tig, int lane, uint32_t ones) {
   constexpr int kJGroups = kRows / 4;
   constexpr int kCalls = kJGroups * 2;
   const int rot = (lane >> 1) & 3;
@@ -44,13 +44,13 @@ __device__ __forceinline__ void gen_rademacher_rows(uint32_t smem_b, int row_bas
       for (int cc = 0; cc < 4; ++cc) {
         const uint32_t byte = (words[i] >> (8 * cc)) & 0xFFu;
         const uint32_t chunk = 4 * pg + cc;
-        st_shared_v4(row_addr + ((chunk ^ sw) << 4), rademacher_expand8(byte));
+        st_shared_v4(row_addr + ((chunk ^ sw) << 4), rademacher_expand8(byte, ones));
       }
     }
   }
 }
 
-template <int kRows, int kGroupThreads>
+template <int kRows, int kGroupThreads, bool kF16>
 __device__ __forceinline__ void gen_normal_rows(uint32_t smem_b, int row_base, uint32_t p_div8, uint32_t j0,
                                                 uint32_t k0, uint32_t k1, int tig) {
   constexpr int kCalls = kRows * 8;
@@ -58,7 +58,7 @@ __device__ __forceinline__ void gen_normal_rows(uint32_t smem_b, int row_base, u
   for (int e = tig; e < kCalls; e += kGroupThreads) {
     const int row = row_base + e % kRows;
     const int c = e / kRows;
-    const uint4 v = normal_chunk(p_div8 + c, j0 + row, k0, k1);
+    const uint4 v = normal_chunk<kF16>(p_div8 + c, j0 + row, k0, k1);
     st_shared_v4(smem_b + row * 128 + ((c ^ (row & 7)) << 4), v);
   }
 }
@@ -68,7 +68,7 @@ __device__ __forceinline__ void gen_normal_rows(uint32_t smem_b, int row_base, u
 // kGroups == 2: twice the warps per k-block, so a slot is ready in half the time -- the per-slot chain
 // generate -> fence -> ship over DSMEM -> relay -> MMA -> commit has to fit into the 4-slot window.
 template <int kWarpsPerGroup, int kGroups = kMaxGenGroups>
-__global__ void __launch_bounds__(Roles<kWarpsPerGroup>::kThreads, 1)
+__global__ void GADM_PROJ_BOUNDS
 project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
   using C = Cfg<2>;
   using R = Roles<kWarpsPerGroup>;
@@ -144,7 +144,7 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
     if (lane == 0) {
       if (rank == 0) {
         // ===================== MMA issuer of this pair
-        const uint32_t idesc = umma_idesc_ab(a.a_fmt, UMMA_FMT_BF16, kAccRows * 2, kTileN);
+        const uint32_t idesc = umma_idesc(a.a_fmt, kAccRows * 2, kTileN);
         const uint16_t pair_mask = static_cast<uint16_t>(0x3u << leader4);
         uint32_t it = 0, seg_iter = 0;
         for (uint32_t u = cid; u < a.n_units; u += n_clusters) {
@@ -230,9 +230,12 @@ project_quad_kernel(const __grid_constant__ CUtensorMap tmap_g, const Args a) {
         mbar_wait<kGenBackoffNs>(empty_bar(s), ph ^ 1u, 0x2500 + s);
         const uint32_t p_div64 = a.p_base_div64 + kb;
         if (a.proj_type == kProjRademacher)
-          gen_rademacher_rows<kQuadOwnRows, kGroupThreadsQ>(smem_b(s), row_base, p_div64 * 2u, j0, a.key0, a.key1, tig, lane);
+          gen_rademacher_rows<kQuadOwnRows, kGroupThreadsQ>(smem_b(s), row_base, p_div64 * 2u, j0, a.key0, a.key1, tig, lane,
+                                                            a.a_fmt == UMMA_FMT_F16 ? kOnesF16 : kOnesBf16);
+        else if (a.a_fmt == UMMA_FMT_F16)
+          gen_normal_rows<kQuadOwnRows, kGroupThreadsQ, true>(smem_b(s), row_base, p_div64 * 8u, j0, a.key0, a.key1, tig);
         else
-          gen_normal_rows<kQuadOwnRows, kGroupThreadsQ>(smem_b(s), row_base, p_div64 * 8u, j0, a.key0, a.key1, tig);
+          gen_normal_rows<kQuadOwnRows, kGroupThreadsQ, false>(smem_b(s), row_base, p_div64 * 8u, j0, a.key0, a.key1, tig);
         fence_proxy_async_smem();                           // my generic writes -> async proxy (UMMA and the bulk copy)
         named_bar_sync(1 + group, kGroupThreadsQ);          // the whole 64-row half is written and fenced
         if (tig == 0) {

@@ -32,7 +32,7 @@ namespace stage {
 
 constexpr int kGroupKb = 512;                 // k-blocks (of 64 columns) per scale group
 constexpr int kGroupCols = kGroupKb * 64;     // 32768
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;  // 128 threads x <= 32 registers = the 4096 registers a resident projection CTA leaves free on its SM
 constexpr int kMaxBlocks = 1024;              // parameter blocks per launch (kernel-parameter space: 24 B each)
 
 // Parameter blocks of one example, sorted by position in the flattened gradient.  Entry i covers columns
@@ -137,8 +137,13 @@ __device__ __forceinline__ float exp2_int(int s) { return __uint_as_float(static
 // grid = (groups, batch).  CTA (g, b) stages columns [g * 32768, ...) of example b into row row0 + b.
 // v * scale is formed once (pass 2): |.| and the rounding of a product by a constant are monotonic, so the group
 // maximum of |v * scale| is |max|v| * scale|, and 2^s is folded into the multiplier (exact).
+//
+// Co-residency: the persistent projection kernel owns every SM (768 threads x 80 registers, ~215 KB of shared memory),
+// which leaves 4096 registers, 1280 threads and ~15 KB of shared memory per SM.  A staging CTA is sized to fit into
+// exactly that (128 threads, __maxnreg__(32), 32 B of static shared memory), so that staging the next pass on another
+// stream proceeds WHILE a pass is being projected instead of queueing behind it; alone, 16 such CTAs fill an SM.
 template <typename T, bool kF16>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __maxnreg__(32)
 stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
                     int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
   __shared__ float red[kThreads / 32];
@@ -186,7 +191,7 @@ stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict
 // grid = (ceil(d_pad / 8192), batch)
 constexpr int kAccCols = 8192;
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __maxnreg__(32)
 accumulate_rows_kernel(const __grid_constant__ BlockTable tab, float* __restrict__ slab, int64_t d_pad, int64_t row0,
                        float scale, int accumulate) {
   const int64_t b = blockIdx.y;

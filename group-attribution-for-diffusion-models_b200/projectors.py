@@ -276,8 +276,8 @@ class CudaProjector:
         seed64 = (self.seed + SEED_MODEL_ID_STRIDE * int(model_id)) & 0xFFFFFFFFFFFFFFFF
         with torch.cuda.device(self.device):
             _lib.check(self._handle.lib.gadm_materialize_p(self._handle.ptr, row0, nrows, self.proj_dim, seed64,
-                                                          _PROJ_CODE[self.proj_type], out.data_ptr(),
-                                                          _lib.stream_ptr(self.device)))
+                                                          _PROJ_CODE[self.proj_type], _STAGE_CODES[self.stage_dtype],
+                                                          out.data_ptr(), _lib.stream_ptr(self.device)))
         return out
 
 

