@@ -17,6 +17,7 @@
 #include "project.cuh"
 #include "project_quad.cuh"
 #include "stage.cuh"
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -34,6 +35,7 @@ struct gadm_ctx {
                                 // flight on different streams of one device never share a barrier
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
   bool attr_gemm = false, attr_gemm_ts = false, attr_potrf = false;  // per-device kernel attributes already set
+  uint32_t attr_stage = 0;      // bit per staging-kernel instantiation whose carveout preference has been set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start / panel / rest / end
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
@@ -322,12 +324,25 @@ int launch_stage(gadm_handle h, const gadm::stage::BlockTable& tab, int64_t batc
   const int64_t groups = stage_scale_count(d_pad);
   dim3 grid((unsigned)groups, (unsigned)batch);
   auto* dst = reinterpret_cast<uint16_t*>(staged);
-  if (stage_dtype == GADM_STAGE_F16G)
+  // Same shared-memory carveout preference as the persistent projection kernel (maximum): an SM serves one carveout
+  // configuration at a time, and a staging CTA that asks for a small one would wait for the projection CTA to leave
+  // instead of running beside it.
+  auto prefer_max_smem = [&](auto kernel, uint32_t bit) -> int {
+    if (h->attr_stage & bit) return GADM_OK;
+    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    h->attr_stage |= bit;
+    return GADM_OK;
+  };
+  const uint32_t bit = 1u << (2 * sizeof(T) + (stage_dtype == GADM_STAGE_F16G ? 1 : 0) + (std::is_same<T, __half>::value ? 8 : 0));
+  if (stage_dtype == GADM_STAGE_F16G) {
+    GADM_TRY_RC(prefer_max_smem(gadm::stage::stage_groups_kernel<T, true>, bit));
     gadm::stage::stage_groups_kernel<T, true><<<grid, gadm::stage::kThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
                                                                                       inv_scale, groups);
-  else
+  } else {
+    GADM_TRY_RC(prefer_max_smem(gadm::stage::stage_groups_kernel<T, false>, bit));
     gadm::stage::stage_groups_kernel<T, false><<<grid, gadm::stage::kThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
                                                                                        nullptr, groups);
+  }
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

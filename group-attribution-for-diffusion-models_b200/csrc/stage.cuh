@@ -112,7 +112,117 @@ struct BlockCursor {
   }
 };
 
+// ---- asynchronous chunk stream -------------------------------------------------------------------------------------
+// A staging CTA that runs beside the persistent projection kernel gets 4 warps and 32 registers per thread: with
+// plain loads that is ~32 bytes in flight per thread, ~0.5 TB/s for the whole GPU, and staging (not the projection)
+// sets the pace.  The loads therefore go through cp.async into a shared-memory ring (no registers held while in
+// flight): a warp owns chunks of 256 consecutive columns, kDepth chunks ahead, copied with fully coalesced
+// instructions -- 16-byte copies (512 contiguous bytes per instruction) when the chunk's source is 16-byte aligned,
+// 4-byte copies (128 contiguous bytes per instruction) otherwise (fp32 rows of odd length) -- and lane l then reads
+// columns 8 l .. 8 l + 7 of the chunk back.  Chunks that straddle a block boundary / gap are fetched synchronously.
+constexpr int kDepth = 3;
+constexpr int kChunk = 256;  // columns per warp per ring slot
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+template <typename T>
+struct ChunkStream {
+  static constexpr uint32_t kSlotBytes = kChunk * sizeof(T);  // per warp
+  static constexpr uint32_t kRingBytes = kDepth * (kThreads / 32) * kSlotBytes;
+  BlockCursor<T> cur;
+  uint32_t ring;  // shared-memory address of this warp's slot 0; slot r lives (kThreads / 32) * kSlotBytes further
+  int lane;
+  __device__ __forceinline__ ChunkStream(const BlockTable& t, int64_t ex, uint32_t ring_base)
+      : cur(t, ex), ring(ring_base + (threadIdx.x >> 5) * kSlotBytes), lane(threadIdx.x & 31) {}
+  __device__ __forceinline__ uint32_t slot_addr(int r) const { return ring + r * ((kThreads / 32) * kSlotBytes); }
+
+  // p0: first column of the chunk (the same for every lane of the warp)
+  __device__ __forceinline__ void issue(int64_t p0, int r) {
+    const uint32_t dst = slot_addr(r);
+    if (!(p0 >= cur.lo && p0 < cur.hi)) cur.seek(p0);
+    if (p0 >= cur.lo && p0 + kChunk <= cur.hi && (reinterpret_cast<uintptr_t>(cur.base + (p0 - cur.lo)) & 3) == 0) {
+      const char* s = reinterpret_cast<const char*>(cur.base + (p0 - cur.lo));
+      if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+#pragma unroll
+        for (uint32_t o = 0; o < kSlotBytes; o += 512) cp_async_16(dst + o + lane * 16, s + o + lane * 16);
+      } else {
+#pragma unroll
+        for (uint32_t o = 0; o < kSlotBytes; o += 128) cp_async_4(dst + o + lane * 4, s + o + lane * 4);
+      }
+    } else {
+      // straddles a block boundary / gap (or 2-byte elements at an odd offset): element i * 32 + lane, synchronously
+#pragma unroll
+      for (int i = 0; i < kChunk / 32; ++i) {
+        const int64_t c = p0 + i * 32 + lane;
+        if (!(c >= cur.lo && c < cur.hi)) cur.seek(c);
+        T v;
+        if (c >= cur.lo && c < cur.hi) v = cur.base[c - cur.lo];
+        else v = static_cast<T>(0.f);
+        const uint32_t d = dst + (i * 32 + lane) * sizeof(T);
+        if constexpr (sizeof(T) == 4)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(d), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
+        else
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(d), "h"(*reinterpret_cast<const unsigned short*>(&v)) : "memory");
+      }
+    }
+    cp_async_commit();
+  }
+
+  // this lane's 8 columns (8 * lane ...) of the chunk in slot r
+  __device__ __forceinline__ void consume(int r, float (&v)[8]) const {
+    const uint32_t src = slot_addr(r) + lane * 8 * sizeof(T);
+    if constexpr (sizeof(T) == 4) {
+      uint4 q0, q1;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(src) : "memory");
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(src + 16) : "memory");
+      v[0] = __uint_as_float(q0.x); v[1] = __uint_as_float(q0.y); v[2] = __uint_as_float(q0.z); v[3] = __uint_as_float(q0.w);
+      v[4] = __uint_as_float(q1.x); v[5] = __uint_as_float(q1.y); v[6] = __uint_as_float(q1.z); v[7] = __uint_as_float(q1.w);
+    } else {
+      uint4 q;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(src) : "memory");
+      const T* h = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = load_as_float(h + i);
+    }
+  }
+
+  // f(p, v) for every octet of [c_lo, c_hi) ((c_hi - c_lo) % 64 == 0) that belongs to this thread; v reads as zero
+  // beyond c_hi is never produced: chunks are clipped to whole 64-column rows by the caller's bounds check on p.
+  // kEvery > 1: only every kEvery-th step of the warp (the columns [1024 j, 1024 j + 1024) of the range with
+  // j % kEvery == 0) -- the sample pass of the scale guess.
+  template <int kEvery = 1, typename F>
+  __device__ __forceinline__ void for_each(int64_t c_lo, int64_t c_hi, F&& f) {
+    constexpr int kWarps = kThreads / 32;
+    const int64_t first = c_lo + static_cast<int64_t>(threadIdx.x >> 5) * kChunk;
+    constexpr int64_t kStep = static_cast<int64_t>(kWarps) * kChunk * kEvery;
+    const int n = first < c_hi ? static_cast<int>((c_hi - first + kStep - 1) / kStep) : 0;
+#pragma unroll
+    for (int i = 0; i < kDepth; ++i)
+      if (i < n) issue(first + i * kStep, i);
+    int r = 0;
+    for (int i = 0; i < n; ++i) {
+      if (n - i >= kDepth) cp_async_wait<kDepth - 1>(); else cp_async_wait<0>();
+      __syncwarp();  // every lane's copies of this slot have landed
+      float v[8];
+      consume(r, v);
+      const int64_t p = first + i * kStep + 8 * lane;
+      if (p < c_hi) f(p, v);
+      __syncwarp();  // every lane has read the slot before it is refilled
+      if (i + kDepth < n) issue(first + (i + kDepth) * kStep, r);
+      r = (r + 1 == kDepth) ? 0 : r + 1;
+    }
+  }
+};
+
 __device__ __forceinline__ float block_max(float v, float* smem) {
+  __syncthreads();  // the previous result has been read by everyone
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
@@ -123,68 +233,86 @@ __device__ __forceinline__ float block_max(float v, float* smem) {
   return m;
 }
 
-// scale exponent for a group whose largest magnitude is amax: amax * 2^s in [2^13, 2^14); clamped so that both
-// 2^s and 2^-s are normal fp32 numbers.  amax == 0 (or NaN / Inf, which then propagate) -> s = 0.
-__device__ __forceinline__ int group_scale_exponent(float amax) {
+// scale exponent that puts a magnitude amax into [2^top, 2^(top + 1)); clamped so that both 2^s and 2^-s are normal
+// fp32 numbers.  amax == 0 (or NaN / Inf, which then propagate) -> s = 0.
+__device__ __forceinline__ int group_scale_exponent(float amax, int top) {
   if (!(amax > 0.f) || !(amax < __int_as_float(0x7f800000))) return 0;
   int e = static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu) - 127;  // floor(log2(amax)) for normal amax
   if (e < -100) e = -100;
   if (e > 100) e = 100;
-  return 13 - e;
+  return top - e;
 }
 __device__ __forceinline__ float exp2_int(int s) { return __uint_as_float(static_cast<uint32_t>(s + 127) << 23); }
 
 // grid = (groups, batch).  CTA (g, b) stages columns [g * 32768, ...) of example b into row row0 + b.
-// v * scale is formed once (pass 2): |.| and the rounding of a product by a constant are monotonic, so the group
-// maximum of |v * scale| is |max|v| * scale|, and 2^s is folded into the multiplier (exact).
+//
+// Scale of a group (F16G).  fp16 rounding is invariant under power-of-two scaling as long as nothing overflows or
+// falls into the subnormal range, so the scale does not have to come from the exact group maximum -- it only has to
+// put the maximum safely below 65504 and far above 2^-14.  The group is therefore staged in ONE pass with a scale
+// GUESSED from a sample (columns [1024 j, 1024 j + 1024) of the group with j % 8 == 0, one eighth of it): sampled
+// maximum -> [2^11, 2^12).  The pass computes the true maximum on the side; if the guess leaves it outside
+// [2^8, 65504) (an outlier the sample missed, or an all-zero sample) the group is staged again with the exact
+// scale (true maximum -> [2^13, 2^14)).  Deterministic: the scale is a function of the row's own values only.
+// v * scale is never formed separately: |.| and rounding are monotonic, so max|v * scale| = |max|v| * scale|, and
+// 2^s is folded into the multiplier (exact).
 //
 // Co-residency: the persistent projection kernel owns every SM (768 threads x 80 registers, ~215 KB of shared memory),
 // which leaves 4096 registers, 1280 threads and ~15 KB of shared memory per SM.  A staging CTA is sized to fit into
-// exactly that (128 threads, __maxnreg__(32), 32 B of static shared memory), so that staging the next pass on another
+// exactly that (128 threads, __maxnreg__(32), a 12 KiB cp.async ring), so that staging the next pass on another
 // stream proceeds WHILE a pass is being projected instead of queueing behind it; alone, 16 such CTAs fill an SM.
 template <typename T, bool kF16>
 __global__ void __maxnreg__(32)
 stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
                     int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
   __shared__ float red[kThreads / 32];
+  __shared__ __align__(16) uint8_t ring[ChunkStream<T>::kRingBytes];
   const int64_t g = blockIdx.x, b = blockIdx.y;
   const int64_t row = row0 + b;
   const int64_t c_lo = g * kGroupCols;
   const int64_t c_hi = (c_lo + kGroupCols < d_pad) ? c_lo + kGroupCols : d_pad;
-  BlockCursor<T> cur(tab, b);
-  float mul = scale;
-  if constexpr (kF16) {
-    float amax = 0.f;
-    for (int64_t p = c_lo + 8 * threadIdx.x; p < c_hi; p += 8 * kThreads) {
-      float v[8];
-      cur.octet(p, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));  // NaNs are skipped here and stored as NaN below
-    }
-    amax = block_max(amax, red) * fabsf(scale);
-    const int s = group_scale_exponent(amax);
-    mul = scale * exp2_int(s);  // exact unless it leaves the normal range, which the exponent clamp excludes for
-                                // |scale| in [2^-20, 2^20]
-    if (threadIdx.x == 0) inv_scale[row * groups_per_row + g] = exp2_int(-s);
-  }
+  ChunkStream<T> in(tab, b, static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
   uint16_t* drow = dst + row * 64;
-  for (int64_t p = c_lo + 8 * threadIdx.x; p < c_hi; p += 8 * kThreads) {
-    float v[8];
-    cur.octet(p, v);
-    uint4 out;
-    uint32_t* o = reinterpret_cast<uint32_t*>(&out);
+  float mul = scale;
+  float amax = 0.f;
+  auto convert_pass = [&]() {
+    amax = 0.f;
+    in.for_each(c_lo, c_hi, [&](int64_t p, const float (&v)[8]) {
+      uint4 out;
+      uint32_t* o = reinterpret_cast<uint32_t*>(&out);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if constexpr (kF16) {
-        const __half2 h = __floats2half2_rn(__fmul_rn(v[2 * i], mul), __fmul_rn(v[2 * i + 1], mul));  // |.| < 2^14
-        o[i] = *reinterpret_cast<const uint32_t*>(&h);
-      } else {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(__fmul_rn(v[2 * i], mul), __fmul_rn(v[2 * i + 1], mul));
-        o[i] = *reinterpret_cast<const uint32_t*>(&h);
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (kF16) {
+          amax = fmaxf(amax, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));  // NaNs are skipped here, stored as NaN
+          const __half2 h = __floats2half2_rn(__fmul_rn(v[2 * i], mul), __fmul_rn(v[2 * i + 1], mul));
+          o[i] = *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(__fmul_rn(v[2 * i], mul), __fmul_rn(v[2 * i + 1], mul));
+          o[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
       }
-    }
-    *reinterpret_cast<uint4*>(drow + (p >> 6) * (m_cap * 64) + (p & 63)) = out;
+      *reinterpret_cast<uint4*>(drow + (p >> 6) * (m_cap * 64) + (p & 63)) = out;
+    });
+  };
+  if constexpr (!kF16) {
+    convert_pass();
+    return;
   }
+  in.template for_each<8>(c_lo, c_hi, [&](int64_t, const float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+  });
+  int s = group_scale_exponent(block_max(amax, red) * fabsf(scale), 11);
+  mul = scale * exp2_int(s);  // exact unless it leaves the normal range, which the exponent clamp excludes for
+                              // |scale| in [2^-20, 2^20]
+  convert_pass();
+  const float true_max = block_max(amax, red) * fabsf(scale);
+  const float landed = true_max * exp2_int(s);
+  if (!(landed >= 256.f && landed < 65504.f) && !(true_max == 0.f)) {  // the sample misjudged the group: exact scale
+    s = group_scale_exponent(true_max, 13);
+    mul = scale * exp2_int(s);
+    convert_pass();
+  }
+  if (threadIdx.x == 0) inv_scale[row * groups_per_row + g] = exp2_int(-s);
 }
 
 // Timestep accumulator: slab[row0 + b, p] = (accumulate ? slab : 0) + scale * src   (fp32 slab [rows][d_pad]).
@@ -198,10 +326,9 @@ accumulate_rows_kernel(const __grid_constant__ BlockTable tab, float* __restrict
   const int64_t c_lo = static_cast<int64_t>(blockIdx.x) * kAccCols;
   const int64_t c_hi = (c_lo + kAccCols < d_pad) ? c_lo + kAccCols : d_pad;
   float* out = slab + (row0 + b) * d_pad;
-  BlockCursor<T> cur(tab, b);
-  for (int64_t p = c_lo + 8 * threadIdx.x; p < c_hi; p += 8 * kThreads) {
-    float v[8];
-    cur.octet(p, v);
+  __shared__ __align__(16) uint8_t ring[ChunkStream<T>::kRingBytes];
+  ChunkStream<T> in(tab, b, static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
+  in.for_each(c_lo, c_hi, [&](int64_t p, const float (&v)[8]) {
     float4* o = reinterpret_cast<float4*>(out + p);  // d_pad % 64 == 0 and p % 8 == 0: 32-byte aligned
     // separate round-to-nearest multiply and add (no FMA contraction): bit-identical to emb += grads * scale in fp32
     float4 r0 = make_float4(__fmul_rn(v[0], scale), __fmul_rn(v[1], scale), __fmul_rn(v[2], scale), __fmul_rn(v[3], scale));
@@ -213,7 +340,7 @@ accumulate_rows_kernel(const __grid_constant__ BlockTable tab, float* __restrict
     }
     o[0] = r0;
     o[1] = r1;
-  }
+  });
 }
 
 }  // namespace stage

@@ -48,8 +48,9 @@ enum { GADM_DTYPE_F32 = 0, GADM_DTYPE_BF16 = 1, GADM_DTYPE_F16 = 2 };
 /* 16-bit formats of the staged gradients (the A operand of the projection GEMM):
  *   GADM_STAGE_BF16  bf16(v): 8 significant bits, no scaling (P generated as bf16).
  *   GADM_STAGE_F16G  fp16(v * 2^s), one power-of-two scale per (example row, group of GADM_STAGE_GROUP_COLS columns)
- *                    chosen so that the group's largest magnitude lands in [2^13, 2^14): 11 significant bits and no
- *                    fp16 range problem (P generated as fp16).  The inverse scales live in a caller-owned fp32 array
+ *                    chosen so that the group's largest magnitude lands in [2^8, 65504) (guessed from a sample of the
+ *                    group, exact when the guess misses; csrc/stage.cuh): 11 significant bits and no fp16 range
+ *                    problem (P generated as fp16).  The inverse scales live in a caller-owned fp32 array
  *                    inv_scale[m_cap][gadm_stage_scale_count(d_pad)] written by gadm_stage_rows and read by
  *                    gadm_project_staged (multiplied in, exactly, when accumulation segments are promoted). */
 enum { GADM_STAGE_BF16 = 0, GADM_STAGE_F16G = 1 };

@@ -87,33 +87,50 @@ def round_to_bf16(x: np.ndarray) -> np.ndarray:
 STAGE_GROUP_COLS = 32768  # GADM_STAGE_GROUP_COLS (include/gadm.h)
 
 
-def round_to_f16_groups(x: np.ndarray, scale: float = 1.0, col0: int = 0) -> np.ndarray:
-    """The GADM_STAGE_F16G staging format (csrc/stage.cuh), returned as float32 values.
+def _floor_log2(a: np.ndarray) -> np.ndarray:
+    return ((a.astype(np.float32).view(np.uint32) >> np.uint32(23)) & np.uint32(0xFF)).astype(np.int64) - 127
 
-    Per (row, group of 32768 columns on the global column grid): amax = max|x| * |scale| (float32), e = floor(log2 amax)
-    clamped to [-100, 100], s = 13 - e (s = 0 for amax == 0 or non-finite); the staged value is
-    float16(float32(x * (scale * 2^s))) (round-to-nearest-even twice) and it stands for staged * 2^-s.
-    ``col0``: global column index of x[:, 0] (a multiple of 32768 keeps the group grid)."""
+
+def f16_group_scale_exponents(blk: np.ndarray, scale: float = 1.0) -> np.ndarray:
+    """Scale exponent s per row of one 32768-column group (csrc/stage.cuh ``stage_groups_kernel``): guessed from the
+    sample columns [1024 j, 1024 j + 1024), j % 8 == 0 (sampled max -> [2^11, 2^12)); kept if the true maximum then
+    lands in [2^8, 65504), otherwise the exact scale (true max -> [2^13, 2^14)); 0 for an all-zero / non-finite group."""
+    sc = np.float32(abs(scale))
+    cols = np.arange(blk.shape[1])
+    sample = blk[:, (cols // 1024) % 8 == 0]
+
+    def amax_of(x):
+        with np.errstate(invalid="ignore"):
+            m = np.fmax.reduce(np.abs(x), axis=1, initial=0.0).astype(np.float32)  # fmax skips NaNs like the kernel
+        return (m * sc).astype(np.float32)
+
+    def expo(a, top):
+        ok = (a > 0) & np.isfinite(a)
+        e = np.clip(np.where(ok, _floor_log2(np.where(ok, a, np.float32(1))), 0), -100, 100)
+        return np.where(ok, top - e, 0)
+
+    s_guess = expo(amax_of(sample), 11)
+    true_max = amax_of(blk)
+    with np.errstate(over="ignore", invalid="ignore"):
+        landed = (true_max * np.ldexp(np.float32(1), s_guess).astype(np.float32)).astype(np.float32)
+    keep = ((landed >= 256) & (landed < 65504)) | (true_max == 0)
+    return np.where(keep, s_guess, expo(true_max, 13))
+
+
+def round_to_f16_groups(x: np.ndarray, scale: float = 1.0) -> np.ndarray:
+    """The GADM_STAGE_F16G staging format (csrc/stage.cuh), returned as the float32 values the kernel multiplies by P:
+    per (row, group of 32768 columns) a power-of-two scale 2^s (``f16_group_scale_exponents``), staged value
+    float16(float32(x * (scale * 2^s))) (round-to-nearest-even twice), standing for staged * 2^-s."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     out = np.empty_like(x)
-    n = x.shape[1]
     sc = np.float32(scale)
-    first = -(col0 % STAGE_GROUP_COLS)
-    for lo in range(first, n, STAGE_GROUP_COLS):
-        a, b = max(lo, 0), min(lo + STAGE_GROUP_COLS, n)
-        blk = x[:, a:b]
-        with np.errstate(invalid="ignore"):
-            amax = (np.nanmax(np.abs(blk), axis=1) if blk.size else np.zeros(x.shape[0], np.float32)).astype(np.float32)
-        amax = (amax * np.abs(sc)).astype(np.float32)
-        ok = (amax > 0) & np.isfinite(amax)
-        e = np.zeros(x.shape[0], dtype=np.int64)
-        e[ok] = ((amax[ok].view(np.uint32) >> np.uint32(23)) & np.uint32(0xFF)).astype(np.int64) - 127
-        e = np.clip(e, -100, 100)
-        s = np.where(ok, 13 - e, 0)
+    for lo in range(0, x.shape[1], STAGE_GROUP_COLS):
+        blk = x[:, lo:lo + STAGE_GROUP_COLS]
+        s = f16_group_scale_exponents(blk, scale)
         mul = (sc * np.ldexp(np.float32(1.0), s).astype(np.float32)).astype(np.float32)
         with np.errstate(over="ignore", invalid="ignore"):
             staged = (blk * mul[:, None]).astype(np.float32).astype(np.float16)
-        out[:, a:b] = np.ldexp(staged.astype(np.float32), -s[:, None]).astype(np.float32)
+        out[:, lo:lo + STAGE_GROUP_COLS] = np.ldexp(staged.astype(np.float32), -s[:, None]).astype(np.float32)
     return out
 
 

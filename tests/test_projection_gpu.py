@@ -164,14 +164,15 @@ def test_linearity_and_seed_semantics():
 def test_staging_is_bit_identical_to_the_oracle_rounding(stage_dtype, src_dtype):
     """gadm_stage_rows (one launch for the whole block table) vs oracle.philox.round_staged: every staged 16-bit value
     times its group's inverse scale equals the oracle's rounding bit for bit -- flat input with an odd row pitch
-    (scalar path), per-parameter blocks of awkward sizes (block-boundary path), rows of very different magnitude,
-    an all-zero group, and the folded 1/K scale."""
+    (4-byte copies), per-parameter blocks of awkward sizes (block-boundary path), rows of very different magnitude,
+    an all-zero group, outliers inside and outside the sampled columns of the scale guess, and the folded 1/K scale."""
     D, B = 3 * 32768 + 4321, 5
     g = torch.Generator(device="cpu").manual_seed(7)
     grads = torch.randn(B, D, generator=g)
     grads *= torch.tensor([1.0, 1e-6, 3e4, 1e-3, 7.0])[:, None]
     grads[3, 32768:65536] = 0          # a whole scale group of zeros
-    grads[0, 100] = 900.0              # an outlier sets its group's scale
+    grads[0, 100] = 900.0              # an outlier inside the sampled columns sets its group's scale
+    grads[4, 40000] = 1e8              # an outlier the sample misses: the group is staged again with the exact scale
     grads = grads.to(src_dtype).to(DEV)
     p = _proj(D, 512, 3, "rademacher", stage_dtype=stage_dtype, stage_rows=8)
     ref = grads.float().cpu().numpy()
