@@ -59,7 +59,8 @@ _SIGNATURES = {
     "gadm_dgemm": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gadm_sym_eig_workspace_bytes": (c_i64, [c_i64]),
     "gadm_sym_eig": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),
-    "gadm_ridge_gcv": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "gadm_ridge_gcv_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
+    "gadm_ridge_gcv": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "gadm_ridge_select": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "gadm_ridge_intercept": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gadm_datamodel_slot_bytes": (c_i64, [c_i64]),

@@ -66,57 +66,128 @@ __global__ void mask_gram_kernel(const uint32_t* __restrict__ colbits, int64_t d
 // out[i, k] = ( sum_r X[r,i] * (Y[r,k] - shift[k]) - half * sum_r (Y[r,k] - shift[k]) ) * scale
 //   Shapley: shift = v0, half = 0, scale = 1/n   (datashapley.py:30)
 //   Banzhaf: shift = 0 (null), half = 0.5, scale = 1   (databanzhaf.py:23)
-// Block = 64 behaviour columns x 4 mask words: thread (kx, s) owns the 32 players of word (4*blockIdx.y + s)
-// for column k, so a block covers 128 players and Y is streamed from HBM once when d <= 128 (coalesced 512-B
-// row segments; the mask word is a warp-wide broadcast).  Rows are visited in order: deterministic sums.
-constexpr int kXtyCols = 64;
-constexpr int kXtyWords = 4;
+//
+// This is the dense fp64 contraction X^T Y with a 0/1 left operand: 2 d n K flops over 8 n K bytes of Y, i.e. d / 4
+// flop per byte (25 at d = 100) -- far to the right of the fp64 ridge (~6 flop / B on B200), so the bound is the
+// fp64 FMA pipe, not HBM.  Round 1 did it with predicated adds (one useful flop and ~3 issue slots per (player, row,
+// behaviour): 28 % of the fp64 pipe, 0.4 TB/s of Y).  Now a register-tiled DFMA GEMM: the mask bits of a 16-row chunk
+// are expanded once per CTA into 0.0 / 1.0 doubles in shared memory, Y arrives as coalesced 512-byte row segments,
+// and every thread owns 8 players x 4 behaviours (32 independent accumulators; 32 DFMA per 6 LDS.128).  fma(x, y, acc)
+// with x in {0, 1} is exactly "acc += y or nothing" and every (player, behaviour) sum still visits the rows in order,
+// so the results are bit-identical to the predicated form and deterministic.
+// CTA = 256 threads = 16 (behaviour groups of 4) x 16 (player groups of 8) -> tile 128 players x 64 behaviours.
+constexpr int kXtyCols = 64;      // behaviours per CTA
+constexpr int kXtyPlayers = 128;  // outputs (players, or test rows for X_test @ attrs) per CTA
+constexpr int kXtyRows = 16;      // summed rows per shared-memory chunk
+constexpr int kXtyThreads = 256;
 
-// acc[t] += y for every set bit t < kBits of `bits`.  ptxas compiles the conditional add to R2P (7 predicates per
-// instruction) + an unconditional DADD + two FSELs per player -- also when it is written as a predicated
-// add.rn.f64 in PTX -- so a player costs ~3 issue slots next to the half-rate fp64 add: the kernel is fp64-issue
-// bound (ncu: fp64 pipe 28.6 %, issue 59 %), not HBM bound.
-template <int kBits>
-__device__ __forceinline__ void masked_accumulate(double (&acc)[32], uint32_t bits, double y) {
-#pragma unroll
-  for (int t = 0; t < kBits; ++t)
-    if ((bits >> t) & 1u) acc[t] += y;
+// 8-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros instead (bounds handling without a branch)
+__device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-template <int kBits>
-__device__ __forceinline__ void mask_xty_rows(const uint32_t* __restrict__ rowbits, int64_t wd, int64_t word,
-                                              const double* __restrict__ Y, int64_t n, int64_t K, int64_t k, double sh,
-                                              double (&acc)[32], double& tot) {
-#pragma unroll 2
-  for (int64_t r = 0; r < n; ++r) {
-    const double y = Y[r * K + k] - sh;
-    const uint32_t bits = rowbits[r * wd + word];
-    tot += y;
-    masked_accumulate<kBits>(acc, bits, y);
-  }
-}
-
-__global__ void __launch_bounds__(kXtyCols * kXtyWords)
+// The next chunk's Y rows travel global -> shared by cp.async while the current chunk is being multiplied (a plain
+// load + store would park every warp on the store until the load returns: the in-order issue exposed the full DRAM
+// latency once per 16 rows and held the fp64 pipe at 39 %); its mask words wait in a register meanwhile.
+template <bool kShift>
+__global__ void __launch_bounds__(kXtyThreads)
 mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ Y, int64_t n, int64_t d,
                 int64_t K, const double* __restrict__ shift, double half, double scale, double* __restrict__ out) {
-  const int64_t k = static_cast<int64_t>(blockIdx.x) * kXtyCols + threadIdx.x;
-  const int64_t word = static_cast<int64_t>(blockIdx.y) * kXtyWords + threadIdx.y;
-  if (k >= K || word >= wd) return;
-  const double sh = shift ? shift[k] : 0.0;
-  double acc[32];
+  __shared__ __align__(16) double xs[2][kXtyRows][kXtyPlayers];  // 0.0 / 1.0
+  __shared__ __align__(16) double ys[2][kXtyRows][kXtyCols];     // raw Y (zeros beyond n / K)
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kXtyCols;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kXtyPlayers;
+  const int64_t word0 = i0 >> 5;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;  // loader role: row lr, columns lc .. lc + 3 of the Y chunk
+  double sh[4] = {0.0, 0.0, 0.0, 0.0};           // shift of this thread's COMPUTE columns
+  if (kShift) {
 #pragma unroll
-  for (int t = 0; t < 32; ++t) acc[t] = 0.0;
-  double tot = 0.0;
-  // players of this word that exist (the last word of d = 100 holds 4): only those are accumulated, rounded up to 8
-  const int valid = static_cast<int>((d - word * 32) < 32 ? (d - word * 32) : 32);
-  if (valid > 24) mask_xty_rows<32>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
-  else if (valid > 16) mask_xty_rows<24>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
-  else if (valid > 8) mask_xty_rows<16>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
-  else mask_xty_rows<8>(rowbits, wd, word, Y, n, K, k, sh, acc, tot);
+    for (int c = 0; c < 4; ++c) sh[c] = (k0 + tx * 4 + c < K) ? shift[k0 + tx * 4 + c] : 0.0;
+  }
+
+  auto issue_y = [&](int buf, int64_t r0) {
+    const int64_t r = r0 + lr;
+    const double* src = Y + (r < n ? r : 0) * K + k0 + lc;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    const int64_t i = word * 32 + t;
-    if (i < d) out[i * K + k] = (acc[t] - half * tot) * scale;
+    for (int c = 0; c < 4; ++c) {
+      const bool ok = r < n && k0 + lc + c < K;
+      cp_async_f64(&ys[buf][lr][lc + c], ok ? src + c : Y, ok);
+    }
+  };
+  auto load_bits = [&](int64_t r0) -> uint32_t {
+    if (tid >= kXtyRows * 4) return 0u;
+    const int64_t rw = r0 + (tid >> 2);
+    const int w = tid & 3;
+    return (rw < n && word0 + w < wd) ? rowbits[rw * wd + word0 + w] : 0u;
+  };
+  auto expand_bits = [&](int buf, uint32_t bits) {
+    if (tid < kXtyRows * 4) {
+      double* dst = &xs[buf][tid >> 2][(tid & 3) * 32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) dst[t] = ((bits >> t) & 1u) ? 1.0 : 0.0;
+    }
+  };
+
+  double acc[8][4];
+  double tot[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[p][c] = 0.0;
+
+  issue_y(0, 0);
+  expand_bits(0, load_bits(0));
+  cp_async_commit_wait_all();
+  __syncthreads();
+  int buf = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += kXtyRows) {
+    const bool more = r0 + kXtyRows < n;
+    uint32_t next_bits = 0u;
+    if (more) {
+      issue_y(buf ^ 1, r0 + kXtyRows);  // the other buffer: last read before the previous barrier
+      next_bits = load_bits(r0 + kXtyRows);
+    }
+    const int rows = static_cast<int>((n - r0) < kXtyRows ? (n - r0) : kXtyRows);
+#pragma unroll 4
+    for (int rr = 0; rr < rows; ++rr) {
+      double x[8], y[4];
+      const double2* xp = reinterpret_cast<const double2*>(&xs[buf][rr][ty * 8]);
+      const double2* yp = reinterpret_cast<const double2*>(&ys[buf][rr][tx * 4]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const double2 t2 = xp[q]; x[2 * q] = t2.x; x[2 * q + 1] = t2.y; }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) { const double2 t2 = yp[q]; y[2 * q] = t2.x; y[2 * q + 1] = t2.y; }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (kShift) y[c] -= sh[c];
+        tot[c] += y[c];
+      }
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[p][c] = fma(x[p], y[c], acc[p][c]);
+    }
+    if (more) expand_bits(buf ^ 1, next_bits);
+    cp_async_commit_wait_all();
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int64_t i = i0 + ty * 8 + p;
+    if (i >= d) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t k = k0 + tx * 4 + c;
+      if (k < K) out[i * K + k] = (acc[p][c] - half * tot[c]) * scale;
+    }
   }
 }
 

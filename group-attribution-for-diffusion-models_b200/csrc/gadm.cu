@@ -930,9 +930,13 @@ int gadm_mask_xty(gadm_handle h, const uint32_t* rowbits, const double* y, int64
   DeviceGuard guard(h->device);
   const int64_t wd = (d + 31) / 32;
   dim3 grid((unsigned)((k + gadm::agg::kXtyCols - 1) / gadm::agg::kXtyCols),
-            (unsigned)((wd + gadm::agg::kXtyWords - 1) / gadm::agg::kXtyWords));
-  gadm::agg::mask_xty_kernel<<<grid, dim3(gadm::agg::kXtyCols, gadm::agg::kXtyWords), 0, as_stream(stream)>>>(
-      rowbits, wd, y, n, d, k, shift, half, scale, out);
+            (unsigned)((d + gadm::agg::kXtyPlayers - 1) / gadm::agg::kXtyPlayers));
+  if (shift)
+    gadm::agg::mask_xty_kernel<true><<<grid, gadm::agg::kXtyThreads, 0, as_stream(stream)>>>(rowbits, wd, y, n, d, k, shift,
+                                                                                            half, scale, out);
+  else
+    gadm::agg::mask_xty_kernel<false><<<grid, gadm::agg::kXtyThreads, 0, as_stream(stream)>>>(rowbits, wd, y, n, d, k,
+                                                                                             nullptr, half, scale, out);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }
@@ -943,8 +947,8 @@ int gadm_mask_times_matrix(gadm_handle h, const uint32_t* colbits, const double*
   DeviceGuard guard(h->device);
   const int64_t wm = (m + 31) / 32;  // words per player in the column bit planes
   dim3 grid((unsigned)((k + gadm::agg::kXtyCols - 1) / gadm::agg::kXtyCols),
-            (unsigned)((wm + gadm::agg::kXtyWords - 1) / gadm::agg::kXtyWords));
-  gadm::agg::mask_xty_kernel<<<grid, dim3(gadm::agg::kXtyCols, gadm::agg::kXtyWords), 0, as_stream(stream)>>>(
+            (unsigned)((m + gadm::agg::kXtyPlayers - 1) / gadm::agg::kXtyPlayers));
+  gadm::agg::mask_xty_kernel<false><<<grid, gadm::agg::kXtyThreads, 0, as_stream(stream)>>>(
       colbits, wm, mat, /*summed=*/d, /*outputs=*/m, k, nullptr, 0.0, 1.0, out);
   GADM_LAUNCHED(h);
   return GADM_OK;
@@ -1022,35 +1026,47 @@ int gadm_sym_eig(gadm_handle h, const double* a, int64_t d, double* evals, doubl
   return GADM_OK;
 }
 
+int64_t gadm_ridge_gcv_workspace_bytes(int64_t n, int64_t d, int64_t k, int64_t n_alphas) {
+  const int64_t tiles = (n + gadm::ridge::kGcvRows - 1) / gadm::ridge::kGcvRows;
+  // q [d] | den [A, n] | Z^T [d, n] | per-tile partial sums [A, tiles, k]
+  return (d + n_alphas * n + d * n + n_alphas * tiles * k) * (int64_t)sizeof(double) + 256;
+}
+
 int gadm_ridge_gcv(gadm_handle h, const double* z, const double* t, const double* yc, const double* evals,
-                   const double* alphas, int64_t n, int64_t d, int64_t k, int64_t n_alphas, double* q_work,
-                   double* den_work, double* score, void* stream) {
-  GADM_REQUIRE(h && z && t && yc && evals && alphas && q_work && den_work && score, "null argument");
-  GADM_REQUIRE(n > 0 && d > 0 && k > 0 && n_alphas > 0 && n_alphas <= 65535, "bad size");
-  GADM_REQUIRE(d <= 1600, "d = %lld: the GCV kernel stages a [d, 16] slab in shared memory (d <= 1600)", (long long)d);
+                   const double* alphas, int64_t n, int64_t d, int64_t k, int64_t n_alphas, void* workspace,
+                   int64_t workspace_bytes, double* score, void* stream) {
+  GADM_REQUIRE(h && z && t && yc && evals && alphas && workspace && score, "null argument");
+  GADM_REQUIRE(n > 0 && d > 0 && k > 0 && n_alphas > 0, "bad size");
+  if (workspace_bytes < gadm_ridge_gcv_workspace_bytes(n, d, k, n_alphas))
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes,
+                (long long)gadm_ridge_gcv_workspace_bytes(n, d, k, n_alphas));
   DeviceGuard guard(h->device);
   cudaStream_t st = as_stream(stream);
+  const int64_t tiles = (n + gadm::ridge::kGcvRows - 1) / gadm::ridge::kGcvRows;
+  double* q_work = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  double* den_work = q_work + d;
+  double* zt = den_work + n_alphas * n;
+  double* partial = zt + d * n;
   gadm::ridge::column_sums_kernel<<<(unsigned)((d + 63) / 64), 64, 0, st>>>(z, n, d, q_work);
   GADM_LAUNCHED(h);
   const int64_t jobs = n_alphas * n;
   gadm::ridge::ridge_denominator_kernel<<<(unsigned)((jobs + 7) / 8), 256, 0, st>>>(z, evals, q_work, alphas, n, d,
                                                                                     n_alphas, den_work);
   GADM_LAUNCHED(h);
-  if (d <= 400) {
-    constexpr int kTX = 32;
-    const size_t smem = ((size_t)d * 2 * kTX + (256 / kTX) * 2 * kTX) * sizeof(double);
-    auto kernel = gadm::ridge::ridge_gcv_score_kernel<kTX>;
-    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((k + 2 * kTX - 1) / (2 * kTX)), (unsigned)n_alphas);
-    kernel<<<grid, dim3(kTX, 256 / kTX), smem, st>>>(z, t, yc, evals, den_work, alphas, n, d, k, score);
-  } else {
-    constexpr int kTX = 8;
-    const size_t smem = ((size_t)d * 2 * kTX + (256 / kTX) * 2 * kTX) * sizeof(double);
-    auto kernel = gadm::ridge::ridge_gcv_score_kernel<kTX>;
-    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((k + 2 * kTX - 1) / (2 * kTX)), (unsigned)n_alphas);
-    kernel<<<grid, dim3(kTX, 256 / kTX), smem, st>>>(z, t, yc, evals, den_work, alphas, n, d, k, score);
-  }
+  dim3 tgrid((unsigned)((d + 31) / 32), (unsigned)((n + 31) / 32));
+  gadm::ridge::transpose_f64_kernel<<<tgrid, dim3(32, 8), 0, st>>>(z, n, d, zt);
+  GADM_LAUNCHED(h);
+  auto kernel = gadm::ridge::ridge_gcv_score_kernel;
+  const int64_t gcv_smem = gadm::ridge::kGcvSmemBytes + d * (int64_t)sizeof(double);
+  GADM_REQUIRE(gcv_smem <= 227 * 1024, "d = %lld: the w(alpha) table does not fit in shared memory", (long long)d);
+  GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gcv_smem));
+  dim3 grid((unsigned)((k + gadm::ridge::kGcvCols - 1) / gadm::ridge::kGcvCols), (unsigned)tiles);
+  GADM_REQUIRE(grid.y < 65536, "too many row tiles");
+  kernel<<<grid, gadm::ridge::kGcvThreads, (size_t)gcv_smem, st>>>(zt, t, yc, evals, den_work, alphas, n, d, k, n_alphas,
+                                                                  partial);
+  GADM_LAUNCHED(h);
+  gadm::ridge::ridge_gcv_reduce_kernel<<<(unsigned)((n_alphas * k + 255) / 256), 256, 0, st>>>(partial, n_alphas, tiles, k, n,
+                                                                                              score);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

@@ -143,69 +143,155 @@ __global__ void ridge_denominator_kernel(const double* __restrict__ Z, const dou
 }
 
 // score[a, k] = -(1/n) sum_i ( (Yc[i,k] - sum_j Z[i,j] w_j(a) T[j,k]) / den[a,i] )^2
-// Block = (alpha a, 2*kTX behaviours); Wt[j][kk] = w_j T[j, k0+kk] staged in smem (d x 2kTX doubles); each thread owns
-// 2 adjacent behaviours x 4 rows per pass (8 accumulators, Z read as warp broadcasts).  blockDim = (kTX, 256 / kTX).
-template <int kTX>
-__global__ void __launch_bounds__(256)
-ridge_gcv_score_kernel(const double* __restrict__ Z, const double* __restrict__ T, const double* __restrict__ Yc,
+//
+// 2 A n d K flops of fp64 over 8 n K bytes of Yc: ~2500 flop / byte at (A, d) = (100, 100), i.e. bound by the fp64
+// FMA pipe.  Round 1 ran one CTA per (alpha, 64 behaviours): Yc was re-read once per alpha (176.8 GB of DRAM traffic
+// for ~2 GB at K = 2 * 10^5) and the 8-accumulator thread tile kept the pipe at 31 %.  Now one CTA owns a tile of
+// 128 rows x 64 behaviours for ALL alphas: its 8 x 4 Yc values per thread stay in registers across the alpha loop,
+// Z^T (contiguous along rows) and T stream through shared memory by cp.async in chunks of 32 contraction indices, one
+// chunk ahead of the arithmetic, w_j(alpha) is applied on the fly, and the inner loop is 32 DFMA per 6 LDS.128.  Row tiles write per-tile partial sums; ridge_gcv_reduce_kernel adds them
+// in tile order (deterministic).  No limit on d any more.
+constexpr int kGcvRows = 128;
+constexpr int kGcvCols = 64;
+constexpr int kGcvJ = 32;
+constexpr int kGcvThreads = 256;
+constexpr int kGcvSmemBytes = 2 * kGcvJ * (kGcvRows + kGcvCols) * 8 + 16 * kGcvCols * 8;  // double-buffered chunks + reduce
+                                                                                          // (+ d doubles: w table)
+
+// Zt[j, i] = Z[i, j]  (so that a row tile of Z^T is contiguous)
+__global__ void transpose_f64_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32, r0 = static_cast<int64_t>(blockIdx.y) * 32;
+  for (int t = threadIdx.y; t < 32; t += blockDim.y) {
+    const int64_t r = r0 + t, c = c0 + threadIdx.x;
+    tile[t][threadIdx.x] = (r < rows && c < cols) ? in[r * cols + c] : 0.0;
+  }
+  __syncthreads();
+  for (int t = threadIdx.y; t < 32; t += blockDim.y) {
+    const int64_t c = c0 + t, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[c * rows + r] = tile[threadIdx.x][t];
+  }
+}
+
+__global__ void __launch_bounds__(kGcvThreads)
+ridge_gcv_score_kernel(const double* __restrict__ Zt, const double* __restrict__ T, const double* __restrict__ Yc,
                        const double* __restrict__ evals, const double* __restrict__ den,
-                       const double* __restrict__ alphas, int64_t n, int64_t d, int64_t K, double* __restrict__ score) {
-  constexpr int kTK = 2 * kTX;
-  constexpr int kTY = 256 / kTX;
-  extern __shared__ double ridge_smem[];  // Wt [d][kTK], then red [kTY][kTK]
-  double* Wt = ridge_smem;
-  double* red = ridge_smem + static_cast<size_t>(d) * kTK;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int64_t a = blockIdx.y;
-  const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kTK;
-  const double alpha = alphas[a];
-  for (int idx = ty * kTX + tx; idx < d * kTK; idx += 256) {
-    const int j = idx / kTK, kk = idx % kTK;
-    const int64_t k = k0 + kk;
-    Wt[idx] = (k < K) ? T[static_cast<int64_t>(j) * K + k] / (evals[j] + alpha) : 0.0;
-  }
-  __syncthreads();
-  const int64_t ka = k0 + 2 * tx, kb = ka + 1;
-  double sum_a = 0.0, sum_b = 0.0;
-  const double* dn = den + a * n;
-  for (int64_t i0 = static_cast<int64_t>(ty) * 4; i0 < n; i0 += kTY * 4) {
-    double acc[4][2];
-    const double* zr[4];
+                       const double* __restrict__ alphas, int64_t n, int64_t d, int64_t K, int64_t A,
+                       double* __restrict__ partial) {
+  extern __shared__ __align__(16) double gcv_smem[];
+  double* zt = gcv_smem;                                  // [2][kGcvJ][kGcvRows]  Z^T chunk
+  double* tt = gcv_smem + 2 * kGcvJ * kGcvRows;           // [2][kGcvJ][kGcvCols]  T chunk (unscaled)
+  double* red = tt + 2 * kGcvJ * kGcvCols;                // [16][kGcvCols]
+  double* wtab = red + 16 * kGcvCols;                     // [d]  w_j(alpha) of the current alpha
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kGcvCols;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kGcvRows;
+  const int64_t tiles = gridDim.y;
+  double yc[8][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      acc[r][0] = acc[r][1] = 0.0;
-      const int64_t i = (i0 + r < n) ? i0 + r : n - 1;  // clamped rows are discarded below
-      zr[r] = Z + i * d;
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t i = i0 + ty * 8 + p, k = k0 + tx * 4 + c;
+      yc[p][c] = (i < n && k < K) ? Yc[i * K + k] : 0.0;
     }
+  const int nchunks = static_cast<int>((d + kGcvJ - 1) / kGcvJ);
+  // chunk loads: asynchronous 8-byte copies (zero-filled out of range), issued one chunk ahead of the arithmetic
+  auto issue_chunk = [&](int buf, int c) {
+    const int64_t j = static_cast<int64_t>(c) * kGcvJ + (tid >> 3);
+    {
+      const int cc = (tid & 7) * 16;
+      double* dst = zt + (buf * kGcvJ + (tid >> 3)) * kGcvRows + cc;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int64_t i = i0 + cc + e;
+        const bool ok = j < d && i < n;
+        agg::cp_async_f64(dst + e, ok ? Zt + j * n + i : Zt, ok);
+      }
+    }
+    {
+      const int cc = (tid & 7) * 8;
+      double* dst = tt + (buf * kGcvJ + (tid >> 3)) * kGcvCols + cc;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int64_t k = k0 + cc + e;
+        const bool ok = j < d && k < K;
+        agg::cp_async_f64(dst + e, ok ? T + j * K + k : T, ok);
+      }
+    }
+  };
+
+  for (int64_t a = 0; a < A; ++a) {
+    const double alpha = alphas[a];
+    double acc[8][4];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[p][c] = 0.0;
+    issue_chunk(0, 0);
+    for (int64_t j = tid; j < d; j += kGcvThreads) wtab[j] = 1.0 / (evals[j] + alpha);
+    agg::cp_async_commit_wait_all();
+    __syncthreads();
+    int buf = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      if (c + 1 < nchunks) issue_chunk(buf ^ 1, c + 1);
+      const int64_t j0 = static_cast<int64_t>(c) * kGcvJ;
+      const int jn = static_cast<int>((d - j0) < kGcvJ ? (d - j0) : kGcvJ);
+      const double* zb = zt + buf * kGcvJ * kGcvRows + ty * 8;
+      const double* tb = tt + buf * kGcvJ * kGcvCols + tx * 4;
 #pragma unroll 4
-    for (int64_t j = 0; j < d; ++j) {
-      const double2 w = *reinterpret_cast<const double2*>(Wt + j * kTK + 2 * tx);
+      for (int jj = 0; jj < jn; ++jj) {
+        const double w = wtab[j0 + jj];
+        double x[8], y[4];
+        const double2* xp = reinterpret_cast<const double2*>(zb + jj * kGcvRows);
+        const double2* yp = reinterpret_cast<const double2*>(tb + jj * kGcvCols);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const double z = zr[r][j];
-        acc[r][0] += z * w.x;
-        acc[r][1] += z * w.y;
+        for (int q = 0; q < 4; ++q) { const double2 t2 = xp[q]; x[2 * q] = t2.x; x[2 * q + 1] = t2.y; }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { const double2 t2 = yp[q]; y[2 * q] = t2.x * w; y[2 * q + 1] = t2.y * w; }
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) acc[p][cc] = fma(x[p], y[cc], acc[p][cc]);
       }
+      agg::cp_async_commit_wait_all();
+      __syncthreads();
+      buf ^= 1;
     }
+    // squared leave-one-out errors of this thread's 8 rows, summed in row order; then over the 16 row groups in order
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t i = i0 + r;
+    for (int p = 0; p < 8; ++p) {
+      const int64_t i = i0 + ty * 8 + p;
       if (i < n) {
-        const double dd = dn[i];
-        if (ka < K) { const double e = (Yc[i * K + ka] - acc[r][0]) / dd; sum_a += e * e; }
-        if (kb < K) { const double e = (Yc[i * K + kb] - acc[r][1]) / dd; sum_b += e * e; }
+        const double dd = den[a * n + i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const double e = (yc[p][c] - acc[p][c]) / dd; s[c] += e * e; }
       }
     }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[ty * kGcvCols + tx * 4 + c] = s[c];
+    __syncthreads();
+    if (tid < kGcvCols) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) t += red[g * kGcvCols + tid];
+      const int64_t k = k0 + tid;
+      if (k < K) partial[(a * tiles + blockIdx.y) * K + k] = t;
+    }
+    __syncthreads();
   }
-  red[ty * kTK + 2 * tx] = sum_a;
-  red[ty * kTK + 2 * tx + 1] = sum_b;
-  __syncthreads();
-  if (ty == 0) {
-    double sa = 0.0, sb = 0.0;
-    for (int t = 0; t < kTY; ++t) { sa += red[t * kTK + 2 * tx]; sb += red[t * kTK + 2 * tx + 1]; }
-    if (ka < K) score[a * K + ka] = -sa / static_cast<double>(n);
-    if (kb < K) score[a * K + kb] = -sb / static_cast<double>(n);
-  }
+}
+
+// score[a, k] = -(sum over row tiles, in order) / n
+__global__ void ridge_gcv_reduce_kernel(const double* __restrict__ partial, int64_t A, int64_t tiles, int64_t K, int64_t n,
+                                        double* __restrict__ score) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= A * K) return;
+  const int64_t a = idx / K, k = idx % K;
+  double t = 0.0;
+  for (int64_t r = 0; r < tiles; ++r) t += partial[(a * tiles + r) * K + k];
+  score[idx] = -t / static_cast<double>(n);
 }
 
 // Model selection (_RidgeGCV.fit loop): best[k] = first alpha index with the strictly largest score

@@ -71,11 +71,10 @@ def ridge_cv_batched(x_train, y_train, alphas=DEFAULT_ALPHAS, alpha_per_target: 
                                       C.cast(info.data_ptr(), C.POINTER(C.c_int)), st))
         z = _gemm(h, dev, False, xc, v, n, d, d)                         # Z = Xc V
         t = _gemm(h, dev, True, z, yc, d, n, K)                          # T = Z^T Yc
-        q = torch.empty(d, dtype=_f64, device=dev)
-        den = torch.empty(A, n, dtype=_f64, device=dev)
+        gws = torch.empty(int(h.lib.gadm_ridge_gcv_workspace_bytes(n, d, K, A)), dtype=torch.uint8, device=dev)
         score = torch.empty(A, K, dtype=_f64, device=dev)
         _lib.check(h.lib.gadm_ridge_gcv(h.ptr, z.data_ptr(), t.data_ptr(), yc.data_ptr(), evals.data_ptr(), al_t.data_ptr(),
-                                        n, d, K, A, q.data_ptr(), den.data_ptr(), score.data_ptr(), st))
+                                        n, d, K, A, gws.data_ptr(), gws.numel(), score.data_ptr(), st))
         best = torch.empty(K, dtype=torch.int32, device=dev)
         best_score = torch.empty(K, dtype=_f64, device=dev)
         ts = torch.empty_like(t)

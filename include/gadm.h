@@ -248,10 +248,11 @@ int64_t gadm_sym_eig_workspace_bytes(int64_t d);
 int gadm_sym_eig(gadm_handle h, const double* a, int64_t d, double* evals, double* v, void* workspace,
                  int64_t workspace_bytes, int* info, void* stream);
 /* score[a, k] = -mean_i looe(a)[i, k]^2 (sklearn _RidgeGCV with intercept).  z = Xc V [n, d], t = z^T yc [d, k],
- * yc [n, k] centred targets; q_work: d doubles, den_work: n_alphas * n doubles. */
+ * yc [n, k] centred targets; workspace of gadm_ridge_gcv_workspace_bytes(n, d, k, n_alphas) bytes. */
+int64_t gadm_ridge_gcv_workspace_bytes(int64_t n, int64_t d, int64_t k, int64_t n_alphas);
 int gadm_ridge_gcv(gadm_handle h, const double* z, const double* t, const double* yc, const double* evals,
-                   const double* alphas, int64_t n, int64_t d, int64_t k, int64_t n_alphas, double* q_work,
-                   double* den_work, double* score, void* stream);
+                   const double* alphas, int64_t n, int64_t d, int64_t k, int64_t n_alphas, void* workspace,
+                   int64_t workspace_bytes, double* score, void* stream);
 /* best[k] = first alpha index with the largest score (per behaviour, or of the mean over behaviours when
  * per_target = 0); t_scaled[j, k] = t[j, k] / (evals[j] + alphas[best[k]]) (coef = v t_scaled). */
 int gadm_ridge_select(gadm_handle h, const double* score, int64_t n_alphas, int64_t k, int per_target,
