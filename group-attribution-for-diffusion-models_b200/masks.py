@@ -13,9 +13,30 @@ import math
 import numpy as np
 
 
-def remove_data_by_shapley(dataset_size: int, seed: int = 0):
-    """src/datasets.py:677-697: size ~ (n-1)/(s(n-s)), then the first s of a shuffle.  Returns (remaining, removed)."""
+def _class_split(labels, kept_classes):
+    """Indices whose label is (not) among ``kept_classes``, ascending."""
+    labels = np.asarray(labels)
+    keep = np.isin(labels, np.asarray(list(kept_classes)))
+    idx = np.arange(len(labels))
+    return idx[keep], idx[~keep]
+
+
+def remove_data_by_shapley(dataset_size: int, seed: int = 0, by_class: bool = False, labels=None):
+    """src/datasets.py:677-697: size ~ (n-1)/(s(n-s)), then the first s of a shuffle.  Returns (remaining, removed).
+    ``by_class`` (src/datasets.py:651-673): the same draw over the distinct class labels -- the classes after the
+    sampled size in the shuffled order are removed as a whole; ``labels`` is the per-example label vector (the
+    reference iterates ``dataset`` for ``data[1]``)."""
     rng = np.random.RandomState(seed)
+    if by_class:
+        classes = np.unique(np.asarray(labels))
+        sizes = np.arange(1, len(classes))
+        probs = (len(classes) - 1) / (sizes * (len(classes) - sizes))
+        probs /= probs.sum()
+        n_kept = rng.choice(sizes, size=1, p=probs)[0]
+        order = np.arange(len(classes))
+        rng.shuffle(order)
+        removed_idx, remaining_idx = _class_split(labels, classes[order[n_kept:]])
+        return remaining_idx, removed_idx
     possible_remaining_sizes = np.arange(1, dataset_size)
     remaining_size_probs = (dataset_size - 1) / (possible_remaining_sizes * (dataset_size - possible_remaining_sizes))
     remaining_size_probs /= remaining_size_probs.sum()
@@ -33,9 +54,16 @@ def remove_data_by_uniform(dataset_size: int, seed: int = 0):
     return all_idx[selected], all_idx[~selected]
 
 
-def remove_data_by_datamodel(dataset_size: int, alpha: float = 0.5, seed: int = 0):
-    """src/datasets.py:619-626: the first int(alpha * n) of a shuffle."""
+def remove_data_by_datamodel(dataset_size: int, alpha: float = 0.5, seed: int = 0, by_class: bool = False, labels=None):
+    """src/datasets.py:619-626: the first int(alpha * n) of a shuffle.  ``by_class`` (src/datasets.py:603-617): the
+    first int(alpha * n_classes) of a shuffle of the distinct labels (a Python list, shuffled in place like the
+    reference's) are kept as whole classes."""
     rng = np.random.RandomState(seed)
+    if by_class:
+        classes = np.unique(np.asarray(labels)).tolist()
+        n_kept = int(alpha * len(classes))
+        rng.shuffle(classes)
+        return _class_split(labels, classes[:n_kept])
     all_idx = np.arange(dataset_size)
     num_selected = int(alpha * dataset_size)
     rng.shuffle(all_idx)

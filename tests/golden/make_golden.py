@@ -311,9 +311,31 @@ def make_datamodel():
     print("datamodel_golden.npz", {k: v.shape for k, v in res.items()})
 
 
+def make_masks_by_class():
+    """src/datasets.py:603-617 (datamodel, by_class) and :651-673 (Shapley kernel, by_class) through the reference's
+    own functions, on a dataset of (x, label) tuples with unequal class sizes."""
+    ds = _load("src/datasets.py", "ref_datasets")
+    rng = np.random.RandomState(123)
+    labels = rng.choice(10, size=200, p=np.arange(1, 11) / 55.0)
+    dataset = [(None, int(c)) for c in labels]
+    res = {"labels": labels}
+    for seed in range(6):
+        rem, removed = ds.remove_data_by_datamodel(dataset, alpha=0.5, seed=seed, by_class=True)
+        res[f"datamodel_rem_{seed}"], res[f"datamodel_removed_{seed}"] = np.asarray(rem), np.asarray(removed)
+        rem, removed = ds.remove_data_by_shapley(dataset, seed=seed, by_class=True)
+        res[f"shapley_rem_{seed}"], res[f"shapley_removed_{seed}"] = np.asarray(rem), np.asarray(removed)
+    np.savez_compressed(os.path.join(HERE, "masks_by_class_golden.npz"), **res)
+    print("masks_by_class_golden.npz", len(res))
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))  # repo root (oracle/)
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "masks_by_class":
+        with tempfile.TemporaryDirectory() as tmp:
+            _inject_env(tmp)
+            make_masks_by_class()
+        sys.exit(0)
     if only == "ridge":  # regenerate only the sklearn-based fixture
         make_ridge()
         sys.exit(0)
@@ -329,4 +351,5 @@ if __name__ == "__main__":
         make_gradient_scores(tmp, consts)
         make_lds_py(tmp)
         make_datamodel()
+        make_masks_by_class()
     make_ridge()

@@ -125,3 +125,23 @@ def test_numpy_pairwise_sum_restatement_is_numpys_order():
     want = x.mean(axis=-1)
     got = np.array([(0.0 + numpy_pairwise_sum(r)) / 53 for r in x])
     np.testing.assert_array_equal(got, want)
+
+
+def test_by_class_mask_samplers_match_reference_functions(golden_dir):
+    """src/datasets.py:603-617,651-673 (by_class branches), golden produced by the reference's own functions."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(golden_dir))
+    spec = importlib.util.spec_from_file_location(
+        "gadm_masks", os.path.join(root, "group-attribution-for-diffusion-models_b200", "masks.py"))
+    masks = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(masks)
+    g = np.load(os.path.join(golden_dir, "masks_by_class_golden.npz"))
+    labels = g["labels"]
+    for seed in range(6):
+        rem, removed = masks.remove_data_by_datamodel(len(labels), 0.5, seed, by_class=True, labels=labels)
+        np.testing.assert_array_equal(rem, g[f"datamodel_rem_{seed}"])
+        np.testing.assert_array_equal(removed, g[f"datamodel_removed_{seed}"])
+        rem, removed = masks.remove_data_by_shapley(len(labels), seed, by_class=True, labels=labels)
+        np.testing.assert_array_equal(rem, g[f"shapley_rem_{seed}"])
+        np.testing.assert_array_equal(removed, g[f"shapley_removed_{seed}"])
