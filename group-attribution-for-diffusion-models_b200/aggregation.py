@@ -218,7 +218,10 @@ def spearman_matrix(x_test, y_test, attrs, idx=None, device=None, as_numpy: bool
         n_eval, rows = 1, masks.n
         idx_ptr = None
     else:
-        idx_t = torch.as_tensor(np.ascontiguousarray(np.asarray(idx, dtype=np.int32))).to(dev)
+        idx_np = np.ascontiguousarray(np.asarray(idx, dtype=np.int64))
+        if idx_np.size and (idx_np.min() < 0 or idx_np.max() >= masks.n):  # the kernel gathers rows without a bounds check
+            raise IndexError(f"resampling indices must lie in [0, {masks.n}), got [{idx_np.min()}, {idx_np.max()}]")
+        idx_t = torch.as_tensor(idx_np.astype(np.int32)).to(dev)
         if idx_t.dim() == 1:
             idx_t = idx_t[None, :]
         n_eval, rows = int(idx_t.shape[0]), int(idx_t.shape[1])

@@ -81,6 +81,10 @@ constexpr int kXtyPlayers = 128;  // outputs (players, or test rows for X_test @
 constexpr int kXtyRows = 16;      // summed rows per shared-memory chunk
 constexpr int kXtyThreads = 256;
 
+// column c of a 64-wide Y tile row lives at this position, so that the 16 threads that read columns 4 tx + 2 q .. + 1
+// with one LDS.128 touch 256 consecutive bytes (no bank conflicts) instead of 16 segments 32 bytes apart (4-way)
+__host__ __device__ constexpr int xty_col_pos(int c) { return ((c >> 1) & 1) * 32 + (c >> 2) * 2 + (c & 1); }
+
 // 8-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros instead (bounds handling without a branch)
 __device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* src, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -118,7 +122,7 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const bool ok = r < n && k0 + lc + c < K;
-      cp_async_f64(&ys[buf][lr][lc + c], ok ? src + c : Y, ok);
+      cp_async_f64(&ys[buf][lr][xty_col_pos(lc + c)], ok ? src + c : Y, ok);
     }
   };
   auto load_bits = [&](int64_t r0) -> uint32_t {
@@ -159,11 +163,13 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
     for (int rr = 0; rr < rows; ++rr) {
       double x[8], y[4];
       const double2* xp = reinterpret_cast<const double2*>(&xs[buf][rr][ty * 8]);
-      const double2* yp = reinterpret_cast<const double2*>(&ys[buf][rr][tx * 4]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) { const double2 t2 = xp[q]; x[2 * q] = t2.x; x[2 * q + 1] = t2.y; }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) { const double2 t2 = yp[q]; y[2 * q] = t2.x; y[2 * q + 1] = t2.y; }
+      for (int q = 0; q < 2; ++q) {
+        const double2 t2 = *reinterpret_cast<const double2*>(&ys[buf][rr][q * 32 + tx * 2]);
+        y[2 * q] = t2.x; y[2 * q + 1] = t2.y;
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (kShift) y[c] -= sh[c];

@@ -502,6 +502,11 @@ __device__ __forceinline__ void smem_block_mm(const float* A, int lda, const flo
   }
 }
 
+#ifdef GADM_POTRF_PROFILE
+#define POTRF_T(i) do { __syncthreads(); if (threadIdx.x == 0) prof_t[i] = clock64(); } while (0)
+#else
+#define POTRF_T(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kPotrfThreads, 1)
 potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__ linv, float* __restrict__ linv_t,
                   int* __restrict__ info, int block_index) {
@@ -510,6 +515,11 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
   float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse of the factor
   float* Tm = X + kPotrfNb * kPotrfLd;          // [64][kPotrfTLd] scratch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef GADM_POTRF_PROFILE
+  __shared__ long long prof_t[24];
+  long long acc_f = 0, acc_p = 0, acc_u = 0;
+#endif
+  POTRF_T(0);
   // load; rows / columns >= nb are padded with the identity so that every sub-block step is well defined
   for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) {
     const int r = idx / kPotrfNb, c = idx % kPotrfNb;
@@ -518,8 +528,10 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
   }
   __syncthreads();
 
+  POTRF_T(1);
   for (int jb = 0; jb < kPotrfNb / kPotrfSb; ++jb) {
     const int j0 = jb * kPotrfSb;
+    POTRF_T(4);
     if (warp == 0) {
       // ---- factor the 32 x 32 diagonal sub-block in registers: lane i owns row i
       float r[kPotrfSb];
@@ -563,6 +575,7 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
       for (int i = 0; i < kPotrfSb; ++i) X[(j0 + i) * kPotrfLd + j0 + lane] = x[i];
     }
     __syncthreads();
+    POTRF_T(5);
     const int rem = kPotrfNb - (j0 + kPotrfSb);  // rows below the diagonal sub-block
     if (rem > 0) {
       // ---- panel: P = A[below, j0:j0+32] * D^-T  (computed into scratch, then copied back: in-place rows)
@@ -578,6 +591,7 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
         }
         __syncthreads();
       }
+      POTRF_T(6);
       // ---- trailing update (lower part incl. diagonal sub-blocks): A22 -= P P^T
       for (int idx = tid; idx < rem * rem; idx += kPotrfThreads) {
         const int rr = idx / rem, c = idx % rem;
@@ -590,8 +604,16 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
         L[(j0 + kPotrfSb + rr) * kPotrfLd + j0 + kPotrfSb + c] -= acc;
       }
       __syncthreads();
+      POTRF_T(7);
+#ifdef GADM_POTRF_PROFILE
+      if (tid == 0) { acc_p += prof_t[6] - prof_t[5]; acc_u += prof_t[7] - prof_t[6]; }
+#endif
     }
+#ifdef GADM_POTRF_PROFILE
+    if (tid == 0) acc_f += prof_t[5] - prof_t[4];
+#endif
   }
+  POTRF_T(2);
   // ---- X = L^-1 from the four 32 x 32 diagonal inverses: X21 = -X22 (L21 X11), level 32 -> 64, then 64 -> 128
   for (int half = kPotrfSb; half < kPotrfNb; half *= 2) {
     for (int g0 = 0; g0 < kPotrfNb; g0 += 2 * half) {
@@ -604,13 +626,22 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
       __syncthreads();
     }
   }
+  POTRF_T(3);
   for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) {
     const int r = idx / kPotrfNb, c = idx % kPotrfNb;
     if (r < nb && c < nb) A[static_cast<int64_t>(r) * ld + c] = (c <= r) ? L[r * kPotrfLd + c] : 0.f;
-    const float x = X[r * kPotrfLd + c];  // identity padding (rows >= nb) keeps the block invertible
-    linv[r * kPotrfNb + c] = x;
-    linv_t[c * kPotrfNb + r] = x;
+    // identity padding (rows >= nb) keeps the block invertible.  Both outputs are written with consecutive threads on
+    // consecutive addresses; the transpose is taken on the shared-memory side (pitch 129: conflict-free)
+    linv[r * kPotrfNb + c] = X[r * kPotrfLd + c];
+    linv_t[r * kPotrfNb + c] = X[c * kPotrfLd + r];
   }
+#ifdef GADM_POTRF_PROFILE
+  POTRF_T(8);
+  if (tid == 0 && block_index == 0)
+    printf("potrf cycles: load %lld | factor+invert (warp 0) %lld | panel %lld | trailing %lld | loop total %lld | assemble X %lld | store %lld | all %lld\n",
+           prof_t[1] - prof_t[0], acc_f, acc_p, acc_u, prof_t[2] - prof_t[1], prof_t[3] - prof_t[2], prof_t[8] - prof_t[3],
+           prof_t[8] - prof_t[0]);
+#endif
 }
 
 // X (lower) and Xt (upper) <- the 128 x 128 diagonal-block inverses that potrf_diag_kernel left in the workspace;

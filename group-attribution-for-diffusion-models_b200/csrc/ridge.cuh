@@ -155,8 +155,11 @@ constexpr int kGcvRows = 128;
 constexpr int kGcvCols = 64;
 constexpr int kGcvJ = 32;
 constexpr int kGcvThreads = 256;
-constexpr int kGcvSmemBytes = 2 * kGcvJ * (kGcvRows + kGcvCols) * 8 + 16 * kGcvCols * 8;  // double-buffered chunks + reduce
-                                                                                          // (+ d doubles: w table)
+// double-buffered chunks + reduce scratch + the Yc tile (+ d doubles: w table)
+constexpr int kGcvSmemBytes = 2 * kGcvJ * (kGcvRows + kGcvCols) * 8 + 16 * kGcvCols * 8 + kGcvRows * kGcvCols * 8;
+// column c of a 64-wide tile row lives at this position, so that the 16 threads that read columns 4 tx + 2 q .. + 1
+// with one LDS.128 touch 256 consecutive bytes (no bank conflicts) instead of 16 segments 32 bytes apart (4-way)
+__host__ __device__ constexpr int gcv_col_pos(int c) { return ((c >> 1) & 1) * 32 + (c >> 2) * 2 + (c & 1); }
 
 // Zt[j, i] = Z[i, j]  (so that a row tile of Z^T is contiguous)
 __global__ void transpose_f64_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, double* __restrict__ out) {
@@ -182,19 +185,16 @@ ridge_gcv_score_kernel(const double* __restrict__ Zt, const double* __restrict__
   double* zt = gcv_smem;                                  // [2][kGcvJ][kGcvRows]  Z^T chunk
   double* tt = gcv_smem + 2 * kGcvJ * kGcvRows;           // [2][kGcvJ][kGcvCols]  T chunk (unscaled)
   double* red = tt + 2 * kGcvJ * kGcvCols;                // [16][kGcvCols]
-  double* wtab = red + 16 * kGcvCols;                     // [d]  w_j(alpha) of the current alpha
+  double* ycs = red + 16 * kGcvCols;                      // [kGcvRows][kGcvCols]  Yc tile (read once per alpha)
+  double* wtab = ycs + kGcvRows * kGcvCols;               // [d]  w_j(alpha) of the current alpha
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kGcvCols;
   const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kGcvRows;
   const int64_t tiles = gridDim.y;
-  double yc[8][4];
-#pragma unroll
-  for (int p = 0; p < 8; ++p)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int64_t i = i0 + ty * 8 + p, k = k0 + tx * 4 + c;
-      yc[p][c] = (i < n && k < K) ? Yc[i * K + k] : 0.0;
-    }
+  for (int idx = tid; idx < kGcvRows * kGcvCols; idx += kGcvThreads) {
+    const int64_t i = i0 + idx / kGcvCols, k = k0 + idx % kGcvCols;
+    ycs[idx] = (i < n && k < K) ? Yc[i * K + k] : 0.0;
+  }
   const int nchunks = static_cast<int>((d + kGcvJ - 1) / kGcvJ);
   // chunk loads: asynchronous 8-byte copies (zero-filled out of range), issued one chunk ahead of the arithmetic
   auto issue_chunk = [&](int buf, int c) {
@@ -216,7 +216,7 @@ ridge_gcv_score_kernel(const double* __restrict__ Zt, const double* __restrict__
       for (int e = 0; e < 8; ++e) {
         const int64_t k = k0 + cc + e;
         const bool ok = j < d && k < K;
-        agg::cp_async_f64(dst + e, ok ? T + j * K + k : T, ok);
+        agg::cp_async_f64(dst - cc + gcv_col_pos(cc + e), ok ? T + j * K + k : T, ok);
       }
     }
   };
@@ -238,17 +238,20 @@ ridge_gcv_score_kernel(const double* __restrict__ Zt, const double* __restrict__
       const int64_t j0 = static_cast<int64_t>(c) * kGcvJ;
       const int jn = static_cast<int>((d - j0) < kGcvJ ? (d - j0) : kGcvJ);
       const double* zb = zt + buf * kGcvJ * kGcvRows + ty * 8;
-      const double* tb = tt + buf * kGcvJ * kGcvCols + tx * 4;
+      const double* tb = tt + buf * kGcvJ * kGcvCols + tx * 2;
 #pragma unroll 4
       for (int jj = 0; jj < jn; ++jj) {
         const double w = wtab[j0 + jj];
         double x[8], y[4];
         const double2* xp = reinterpret_cast<const double2*>(zb + jj * kGcvRows);
-        const double2* yp = reinterpret_cast<const double2*>(tb + jj * kGcvCols);
+        const double* yrow = tb + jj * kGcvCols;
 #pragma unroll
         for (int q = 0; q < 4; ++q) { const double2 t2 = xp[q]; x[2 * q] = t2.x; x[2 * q + 1] = t2.y; }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) { const double2 t2 = yp[q]; y[2 * q] = t2.x * w; y[2 * q + 1] = t2.y * w; }
+        for (int q = 0; q < 2; ++q) {
+          const double2 t2 = *reinterpret_cast<const double2*>(yrow + q * 32);
+          y[2 * q] = t2.x * w; y[2 * q + 1] = t2.y * w;
+        }
 #pragma unroll
         for (int p = 0; p < 8; ++p)
 #pragma unroll
@@ -266,7 +269,10 @@ ridge_gcv_score_kernel(const double* __restrict__ Zt, const double* __restrict__
       if (i < n) {
         const double dd = den[a * n + i];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { const double e = (yc[p][c] - acc[p][c]) / dd; s[c] += e * e; }
+        for (int c = 0; c < 4; ++c) {
+          const double e = (ycs[(ty * 8 + p) * kGcvCols + tx * 4 + c] - acc[p][c]) / dd;
+          s[c] += e * e;
+        }
       }
     }
 #pragma unroll

@@ -381,3 +381,37 @@ def test_full_size_scores_match_fp64_and_beat_reference_fp32(N, T, k, tag):
     sw = want["scores_head"]
     assert float((s.double() - sw).abs().max()) < 2e-4 * float(sw.abs().max()), tag
     print(f"{tag} full-size score error (ours, reference fp32) vs fp64: {report}")
+
+
+def test_failed_or_ill_conditioned_factorisation_is_an_error_not_garbage(tmp_path):
+    """potrf substitutes 1 for a non-positive pivot and carries on, so without a check an ill-conditioned or
+    NaN Gram matrix yields finite-looking garbage.  Every reference-level entry point now reads the factorisation
+    status once (one small D2H) and raises; the kernel cache is never written from a factorisation that failed."""
+    import gadm_b200 as G
+
+    N, k, T = 2000, 512, 8
+    train, gen = _rand((N, k), 51), _rand((T, k), 52)
+    bad = train * torch.logspace(0, 5, k, device=DEV)[None, :]  # cond(Phi^T Phi + 0.5 I) ~ 1e10: beyond fp32
+    with pytest.raises(G.GadmError):
+        G.trak_scores(bad, gen, lam=0.5)
+    with pytest.raises(G.GadmError):
+        G.gradient_scores(bad, gen, "trak")
+    nan = train.clone()
+    nan[17, 3] = float("nan")
+    with pytest.raises(G.GadmError):
+        G.trak_scores(nan, gen, lam=0.5)
+    # well-conditioned input passes the same check, and the check can be skipped explicitly
+    ok = G.trak_scores(train, gen, lam=0.5)
+    assert bool(torch.isfinite(ok["trak"]).all())
+    G.trak_scores(bad, gen, lam=0.5, check=False)
+    # compute_gradient_scores: no kernel_*.npy is left behind by a failed factorisation
+    sample_dir, tdir = tmp_path / "samples" / "d_trak", tmp_path / "out" / "cifar100" / "d_trak" / "full"
+    sample_dir.mkdir(parents=True)
+    tdir.mkdir(parents=True)
+    gen.cpu().numpy().tofile(sample_dir / f"reference_f=loss_t=uniform_k=10_d={k}")
+    bad.cpu().numpy().tofile(tdir / f"train_f=loss_t=uniform_k=10_d={k}")
+    args = argparse.Namespace(dataset="cifar100", sample_dir=str(tmp_path / "samples"), gradient_type="trak", k_partition=10,
+                              projector_dim=k, sample_size=T, model_behavior_key="fid", by_class=False)
+    with pytest.raises(G.GadmError):
+        G.compute_gradient_scores(args, outdir=str(tmp_path / "out"))
+    assert not (tdir / f"kernel_train_f=loss_t=uniform_k=10_d={k}.npy").exists()
