@@ -475,11 +475,13 @@ transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t
 //   * the 32 x 32 diagonal sub-block is factored by ONE warp in registers (lane i owns row i, the column
 //     broadcasts are warp shuffles: no block barrier inside the 32 columns) and inverted by the same warp
 //     (lane j owns column j of the inverse, factor entries are smem broadcasts);
-//   * the sub-blocks below it are multiplied by that inverse and the trailing sub-blocks updated by all 16 warps;
+//   * the rows below it are solved against that factor by forward substitution (one thread per row, broadcast reads
+//     of the factor) WHILE warp 0 inverts the sub-block, and the trailing part is updated by all 16 warps with
+//     4 x 4 register tiles (round 1: multiply by the inverse after waiting for it, one output element per thread);
 //   * the 128 x 128 inverse is assembled from the four 32 x 32 inverses by two levels of
-//     X21 = -X22 (L21 X11)  (32 -> 64 -> 128).
-// 4 block barriers per 32 columns instead of 2 per column: 177 us -> ~35 us per block, which was a quarter of the
-// whole TRAK score time at config 2 (32 blocks, strictly serial with the panel / trailing GEMMs).
+//     X21 = -X22 (L21 X11)  (32 -> 64 -> 128), register-tiled as well.
+// 3 block barriers per 32 columns.  The 32 launches of this kernel are strictly serial with the panel / trailing GEMMs
+// of the blocked Cholesky: at 80-100 us each they were 3.6 of the 4.5 ms factorisation of the config-2 Gram matrix.
 constexpr int kPotrfNb = 128;
 constexpr int kPotrfLd = kPotrfNb + 1;
 constexpr int kPotrfSb = 32;
@@ -502,6 +504,44 @@ __device__ __forceinline__ void smem_block_mm(const float* A, int lda, const flo
   }
 }
 
+// The same product with a 4 x 4 register tile per thread (8 shared-memory loads per 16 FMAs instead of 2 per 1):
+// R and Cn are multiples of 4.  kLowerOnly skips output tiles strictly above the diagonal (symmetric updates).
+template <bool kBT, bool kAccum, bool kLowerOnly>
+__device__ __forceinline__ void smem_tile_mm(const float* A, int lda, const float* B, int ldb, float* Cm, int ldc, int R,
+                                             int Cn, int T, float sign) {
+  const int tr = R >> 2, tc = Cn >> 2;
+  for (int idx = threadIdx.x; idx < tr * tc; idx += kPotrfThreads) {
+    const int ti = idx / tc, tj = idx % tc;
+    if (kLowerOnly && tj > ti) continue;
+    const float* a = A + (ti * 4) * lda;
+    const float* b = kBT ? B + (tj * 4) * ldb : B + tj * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = a[i * lda + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = kBT ? b[j * ldb + t] : b[t * ldb + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float* c = Cm + (ti * 4 + i) * ldc + tj * 4 + j;
+        *c = kAccum ? fmaf(sign, acc[i][j], *c) : sign * acc[i][j];
+      }
+  }
+}
+
 #ifdef GADM_POTRF_PROFILE
 #define POTRF_T(i) do { __syncthreads(); if (threadIdx.x == 0) prof_t[i] = clock64(); } while (0)
 #else
@@ -514,6 +554,7 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
   float* L = potrf_smem;                        // [128][kPotrfLd]: the block, then its factor
   float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse of the factor
   float* Tm = X + kPotrfNb * kPotrfLd;          // [64][kPotrfTLd] scratch
+  __shared__ float dinv_s[kPotrfSb];            // 1 / diagonal of the current 32 x 32 factor
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef GADM_POTRF_PROFILE
   __shared__ long long prof_t[24];
@@ -550,7 +591,7 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
         float y = rsqrtf(d);
         y = y * fmaf(-0.5f * d * y, y, 1.5f);
         const float lc = (lane == c) ? d * y : r[c] * y;  // column c of the factor, held by lane = row
-        if (lane == c) dinv = y;                          // 1 / L[c][c], reused by the inverse below
+        if (lane == c) dinv = y;                          // 1 / L[c][c], reused by the panel solve and the inverse
         r[c] = lc;
 #pragma unroll
         for (int t = c + 1; t < kPotrfSb; ++t) {
@@ -560,49 +601,54 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
       }
 #pragma unroll
       for (int c = 0; c < kPotrfSb; ++c) L[(j0 + lane) * kPotrfLd + j0 + c] = (c <= lane) ? r[c] : 0.f;
-      __syncwarp();
-      // ---- invert it: lane j owns column j of the inverse (forward substitution down the rows)
-      float x[kPotrfSb];
-#pragma unroll
-      for (int i = 0; i < kPotrfSb; ++i) {
-        float s = (i == lane) ? 1.f : 0.f;
-#pragma unroll
-        for (int t = 0; t < i; ++t) s = fmaf(-L[(j0 + i) * kPotrfLd + j0 + t], x[t], s);  // x[t] = 0 for t < lane
-        const float di = __shfl_sync(0xffffffffu, dinv, i);  // every lane takes part: never inside the conditional
-        x[i] = (i >= lane) ? s * di : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < kPotrfSb; ++i) X[(j0 + i) * kPotrfLd + j0 + lane] = x[i];
+      dinv_s[lane] = dinv;
     }
     __syncthreads();
     POTRF_T(5);
     const int rem = kPotrfNb - (j0 + kPotrfSb);  // rows below the diagonal sub-block
-    if (rem > 0) {
-      // ---- panel: P = A[below, j0:j0+32] * D^-T  (computed into scratch, then copied back: in-place rows)
-      // scratch Tm is 64 x 65; the panel has up to 96 rows -> two passes of <= 64 rows
-      for (int p0 = 0; p0 < rem; p0 += 64) {
-        const int pr = (rem - p0) < 64 ? (rem - p0) : 64;
-        smem_block_mm<true, false>(L + (j0 + kPotrfSb + p0) * kPotrfLd + j0, kPotrfLd, X + j0 * kPotrfLd + j0, kPotrfLd, Tm,
-                                   kPotrfTLd, pr, kPotrfSb, kPotrfSb, 1.f);
-        __syncthreads();
-        for (int idx = tid; idx < pr * kPotrfSb; idx += kPotrfThreads) {
-          const int rr = idx / kPotrfSb, c = idx % kPotrfSb;
-          L[(j0 + kPotrfSb + p0 + rr) * kPotrfLd + j0 + c] = Tm[rr * kPotrfTLd + c];
+    if (warp == 0) {
+      // ---- invert the sub-block (needed for the 128 x 128 inverse only: off the critical path, it runs while warps
+      // 1..3 solve the panel): lane j owns column j of the inverse (forward substitution down the rows)
+      float x[kPotrfSb];
+#pragma unroll
+      for (int i = 0; i < kPotrfSb; ++i) {
+        float s0 = (i == lane) ? 1.f : 0.f;
+#pragma unroll
+        for (int t = 0; t < i; ++t) s0 = fmaf(-L[(j0 + i) * kPotrfLd + j0 + t], x[t], s0);  // x[t] = 0 for t < lane
+        x[i] = (i >= lane) ? s0 * dinv_s[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kPotrfSb; ++i) X[(j0 + i) * kPotrfLd + j0 + lane] = x[i];
+    } else if (tid - 32 < rem) {
+      // ---- panel by forward substitution, one thread per row: p D^T = a  (D = the 32 x 32 factor, broadcast reads)
+      // instead of waiting for D^-1 and multiplying by it; four partial sums shorten the dependent FMA chain
+      float* arow = L + (j0 + kPotrfSb + (tid - 32)) * kPotrfLd + j0;
+      float pr[kPotrfSb];
+#pragma unroll
+      for (int c = 0; c < kPotrfSb; ++c) {
+        const float* drow = L + (j0 + c) * kPotrfLd + j0;
+        float s0 = arow[c], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int t = 0; t + 3 < c; t += 4) {
+          s0 = fmaf(-pr[t], drow[t], s0);
+          s1 = fmaf(-pr[t + 1], drow[t + 1], s1);
+          s2 = fmaf(-pr[t + 2], drow[t + 2], s2);
+          s3 = fmaf(-pr[t + 3], drow[t + 3], s3);
         }
-        __syncthreads();
+#pragma unroll
+        for (int t = c & ~3; t < c; ++t) s0 = fmaf(-pr[t], drow[t], s0);
+        pr[c] = ((s0 + s1) + (s2 + s3)) * dinv_s[c];
       }
-      POTRF_T(6);
-      // ---- trailing update (lower part incl. diagonal sub-blocks): A22 -= P P^T
-      for (int idx = tid; idx < rem * rem; idx += kPotrfThreads) {
-        const int rr = idx / rem, c = idx % rem;
-        if ((c / kPotrfSb) > (rr / kPotrfSb)) continue;  // sub-blocks above the diagonal are never read
-        const float* pa = L + (j0 + kPotrfSb + rr) * kPotrfLd + j0;
-        const float* pb = L + (j0 + kPotrfSb + c) * kPotrfLd + j0;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int t = 0; t < kPotrfSb; ++t) acc = fmaf(pa[t], pb[t], acc);
-        L[(j0 + kPotrfSb + rr) * kPotrfLd + j0 + kPotrfSb + c] -= acc;
-      }
+#pragma unroll
+      for (int c = 0; c < kPotrfSb; ++c) arow[c] = pr[c];
+    }
+    __syncthreads();
+    POTRF_T(6);
+    if (rem > 0) {
+      // ---- trailing update (lower 4 x 4 tiles incl. the diagonal ones): A22 -= P P^T, P = the panel just solved
+      smem_tile_mm<true, true, true>(L + (j0 + kPotrfSb) * kPotrfLd + j0, kPotrfLd, L + (j0 + kPotrfSb) * kPotrfLd + j0,
+                                     kPotrfLd, L + (j0 + kPotrfSb) * kPotrfLd + j0 + kPotrfSb, kPotrfLd, rem, rem, kPotrfSb,
+                                     -1.f);
       __syncthreads();
       POTRF_T(7);
 #ifdef GADM_POTRF_PROFILE
@@ -618,11 +664,11 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
   for (int half = kPotrfSb; half < kPotrfNb; half *= 2) {
     for (int g0 = 0; g0 < kPotrfNb; g0 += 2 * half) {
       // groups are independent but share the scratch: serialised (2 groups at the first level, 1 at the second)
-      smem_block_mm<false, false>(L + (g0 + half) * kPotrfLd + g0, kPotrfLd, X + g0 * kPotrfLd + g0, kPotrfLd, Tm, kPotrfTLd,
-                                  half, half, half, 1.f);                                        // T = L21 X11
+      smem_tile_mm<false, false, false>(L + (g0 + half) * kPotrfLd + g0, kPotrfLd, X + g0 * kPotrfLd + g0, kPotrfLd, Tm,
+                                        kPotrfTLd, half, half, half, 1.f);                              // T = L21 X11
       __syncthreads();
-      smem_block_mm<false, false>(X + (g0 + half) * kPotrfLd + g0 + half, kPotrfLd, Tm, kPotrfTLd,
-                                  X + (g0 + half) * kPotrfLd + g0, kPotrfLd, half, half, half, -1.f);  // X21 = -X22 T
+      smem_tile_mm<false, false, false>(X + (g0 + half) * kPotrfLd + g0 + half, kPotrfLd, Tm, kPotrfTLd,
+                                        X + (g0 + half) * kPotrfLd + g0, kPotrfLd, half, half, half, -1.f);  // X21 = -X22 T
       __syncthreads();
     }
   }
