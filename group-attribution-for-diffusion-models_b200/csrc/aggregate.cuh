@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "gadm_ptx.cuh"
+
 namespace gadm {
 namespace agg {
 
@@ -78,12 +80,8 @@ __global__ void mask_gram_kernel(const uint32_t* __restrict__ colbits, int64_t d
 // CTA = 256 threads = 16 (behaviour groups of 4) x 16 (player groups of 8) -> tile 128 players x 64 behaviours.
 constexpr int kXtyCols = 64;      // behaviours per CTA
 constexpr int kXtyPlayers = 128;  // outputs (players, or test rows for X_test @ attrs) per CTA
-constexpr int kXtyRows = 16;      // summed rows per shared-memory chunk
+constexpr int kXtyRows = 32;      // summed rows per shared-memory chunk
 constexpr int kXtyThreads = 256;
-
-// column c of a 64-wide Y tile row lives at this position, so that the 16 threads that read columns 4 tx + 2 q .. + 1
-// with one LDS.128 touch 256 consecutive bytes (no bank conflicts) instead of 16 segments 32 bytes apart (4-way)
-__host__ __device__ constexpr int xty_col_pos(int c) { return ((c >> 1) & 1) * 32 + (c >> 2) * 2 + (c & 1); }
 
 // 8-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros instead (bounds handling without a branch)
 __device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* src, bool valid) {
@@ -95,35 +93,68 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// The next chunk's Y rows travel global -> shared by cp.async while the current chunk is being multiplied (a plain
-// load + store would park every warp on the store until the load returns: the in-order issue exposed the full DRAM
-// latency once per 16 rows and held the fp64 pipe at 39 %); its mask words wait in a register meanwhile.
+// Column ownership inside a 64-column tile row: thread tx owns columns {2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx}, so
+// that the 16 threads of one LDS.128 read 256 consecutive bytes of the natural row layout (columns 4 tx .. 4 tx + 3
+// would be 16 segments 32 bytes apart: 4-way bank conflicts).
+__device__ __forceinline__ int tile_col(int tx, int c) { return (c >> 1) * 32 + 2 * tx + (c & 1); }
+
+// The next chunk's Y rows travel global -> shared asynchronously while the current chunk is being multiplied (a plain
+// load + store parks every warp on the store until the load returns: the in-order issue exposed the full DRAM latency
+// once per chunk and held the fp64 pipe at 39 %).  One thread issues one TMA bulk copy per 512-byte row (mbarrier
+// completion); per-thread 8-byte cp.async -- the fallback for odd K / unaligned Y -- worked too but 1536 small
+// requests per chunk kept the LSU queue full (ncu: stall_lg 26 % in the sister kernel of ridge.cuh).  The chunk's mask
+// words wait in a register meanwhile and are expanded to 0.0 / 1.0 after the multiply.
+constexpr int kXtySmemBytes = 2 * kXtyRows * (kXtyPlayers + kXtyCols) * 8 + 64;
 template <bool kShift>
-__global__ void __launch_bounds__(kXtyThreads)
+__global__ void __launch_bounds__(kXtyThreads, 2)
 mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* __restrict__ Y, int64_t n, int64_t d,
                 int64_t K, const double* __restrict__ shift, double half, double scale, double* __restrict__ out) {
-  __shared__ __align__(16) double xs[2][kXtyRows][kXtyPlayers];  // 0.0 / 1.0
-  __shared__ __align__(16) double ys[2][kXtyRows][kXtyCols];     // raw Y (zeros beyond n / K)
+  extern __shared__ __align__(16) double xty_smem[];
+  double (*xs)[kXtyRows][kXtyPlayers] = reinterpret_cast<double (*)[kXtyRows][kXtyPlayers]>(xty_smem);  // 0.0 / 1.0
+  double (*ys)[kXtyRows][kXtyCols] =
+      reinterpret_cast<double (*)[kXtyRows][kXtyCols]>(xty_smem + 2 * kXtyRows * kXtyPlayers);          // raw Y
+  const uint32_t bar0 = smem_u32(xty_smem + 2 * kXtyRows * (kXtyPlayers + kXtyCols));
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kXtyCols;
   const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kXtyPlayers;
   const int64_t word0 = i0 >> 5;
-  const int lr = tid >> 4, lc = (tid & 15) * 4;  // loader role: row lr, columns lc .. lc + 3 of the Y chunk
-  double sh[4] = {0.0, 0.0, 0.0, 0.0};           // shift of this thread's COMPUTE columns
+  const int vc = static_cast<int>((K - k0) < kXtyCols ? (K - k0) : kXtyCols);  // valid columns of this tile
+  const bool bulk = (K % 2 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+  double sh[4] = {0.0, 0.0, 0.0, 0.0};  // shift of this thread's columns
   if (kShift) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) sh[c] = (k0 + tx * 4 + c < K) ? shift[k0 + tx * 4 + c] : 0.0;
+    for (int c = 0; c < 4; ++c) sh[c] = (tile_col(tx, c) < vc) ? shift[k0 + tile_col(tx, c)] : 0.0;
   }
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+  }
+  // columns beyond K are never copied: zero them once (both buffers)
+  for (int idx = tid; idx < 2 * kXtyRows * kXtyCols; idx += kXtyThreads)
+    if (idx % kXtyCols >= vc) (&ys[0][0][0])[idx] = 0.0;
+  __syncthreads();
 
   auto issue_y = [&](int buf, int64_t r0) {
-    const int64_t r = r0 + lr;
-    const double* src = Y + (r < n ? r : 0) * K + k0 + lc;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const bool ok = r < n && k0 + lc + c < K;
-      cp_async_f64(&ys[buf][lr][xty_col_pos(lc + c)], ok ? src + c : Y, ok);
+    const int rows = static_cast<int>((n - r0) < kXtyRows ? (n - r0) : kXtyRows);
+    if (bulk) {
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar0 + 8 * buf, static_cast<uint32_t>(rows * vc * 8));
+        for (int r = 0; r < rows; ++r)
+          bulk_copy_global_to_smem(smem_u32(&ys[buf][r][0]), Y + (r0 + r) * K + k0, static_cast<uint32_t>(vc * 8),
+                                   bar0 + 8 * buf);
+      }
+    } else {
+      for (int idx = tid; idx < rows * vc; idx += kXtyThreads) {
+        const int r = idx / vc, c = idx % vc;
+        cp_async_f64(&ys[buf][r][c], Y + (r0 + r) * K + k0 + c, true);
+      }
     }
+  };
+  auto wait_y = [&](int buf, uint32_t phase) {
+    if (bulk) mbar_wait(bar0 + 8 * buf, phase, 0x900 + buf);
+    else cp_async_commit_wait_all();
   };
   auto load_bits = [&](int64_t r0) -> uint32_t {
     if (tid >= kXtyRows * 4) return 0u;
@@ -148,10 +179,11 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
 
   issue_y(0, 0);
   expand_bits(0, load_bits(0));
-  cp_async_commit_wait_all();
+  wait_y(0, 0);
   __syncthreads();
   int buf = 0;
-  for (int64_t r0 = 0; r0 < n; r0 += kXtyRows) {
+  uint32_t it = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += kXtyRows, ++it) {
     const bool more = r0 + kXtyRows < n;
     uint32_t next_bits = 0u;
     if (more) {
@@ -180,8 +212,10 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[p][c] = fma(x[p], y[c], acc[p][c]);
     }
-    if (more) expand_bits(buf ^ 1, next_bits);
-    cp_async_commit_wait_all();
+    if (more) {
+      expand_bits(buf ^ 1, next_bits);
+      wait_y(buf ^ 1, ((it + 1) >> 1) & 1u);  // buffer b is filled for the (j + 1)-th time at iteration 2 j + b
+    }
     __syncthreads();
     buf ^= 1;
   }
@@ -191,8 +225,8 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
     if (i >= d) continue;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int64_t k = k0 + tx * 4 + c;
-      if (k < K) out[i * K + k] = (acc[p][c] - half * tot[c]) * scale;
+      const int col = tile_col(tx, c);
+      if (col < vc) out[i * K + k0 + col] = (acc[p][c] - half * tot[c]) * scale;
     }
   }
 }

@@ -931,12 +931,16 @@ int gadm_mask_xty(gadm_handle h, const uint32_t* rowbits, const double* y, int64
   const int64_t wd = (d + 31) / 32;
   dim3 grid((unsigned)((k + gadm::agg::kXtyCols - 1) / gadm::agg::kXtyCols),
             (unsigned)((d + gadm::agg::kXtyPlayers - 1) / gadm::agg::kXtyPlayers));
+  GADM_CUDA(cudaFuncSetAttribute(gadm::agg::mask_xty_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gadm::agg::kXtySmemBytes));
+  GADM_CUDA(cudaFuncSetAttribute(gadm::agg::mask_xty_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gadm::agg::kXtySmemBytes));
   if (shift)
-    gadm::agg::mask_xty_kernel<true><<<grid, gadm::agg::kXtyThreads, 0, as_stream(stream)>>>(rowbits, wd, y, n, d, k, shift,
-                                                                                            half, scale, out);
+    gadm::agg::mask_xty_kernel<true><<<grid, gadm::agg::kXtyThreads, gadm::agg::kXtySmemBytes, as_stream(stream)>>>(
+        rowbits, wd, y, n, d, k, shift, half, scale, out);
   else
-    gadm::agg::mask_xty_kernel<false><<<grid, gadm::agg::kXtyThreads, 0, as_stream(stream)>>>(rowbits, wd, y, n, d, k,
-                                                                                             nullptr, half, scale, out);
+    gadm::agg::mask_xty_kernel<false><<<grid, gadm::agg::kXtyThreads, gadm::agg::kXtySmemBytes, as_stream(stream)>>>(
+        rowbits, wd, y, n, d, k, nullptr, half, scale, out);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }
@@ -948,7 +952,9 @@ int gadm_mask_times_matrix(gadm_handle h, const uint32_t* colbits, const double*
   const int64_t wm = (m + 31) / 32;  // words per player in the column bit planes
   dim3 grid((unsigned)((k + gadm::agg::kXtyCols - 1) / gadm::agg::kXtyCols),
             (unsigned)((m + gadm::agg::kXtyPlayers - 1) / gadm::agg::kXtyPlayers));
-  gadm::agg::mask_xty_kernel<false><<<grid, gadm::agg::kXtyThreads, 0, as_stream(stream)>>>(
+  GADM_CUDA(cudaFuncSetAttribute(gadm::agg::mask_xty_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gadm::agg::kXtySmemBytes));
+  gadm::agg::mask_xty_kernel<false><<<grid, gadm::agg::kXtyThreads, gadm::agg::kXtySmemBytes, as_stream(stream)>>>(
       colbits, wm, mat, /*summed=*/d, /*outputs=*/m, k, nullptr, 0.0, 1.0, out);
   GADM_LAUNCHED(h);
   return GADM_OK;
@@ -1028,8 +1034,8 @@ int gadm_sym_eig(gadm_handle h, const double* a, int64_t d, double* evals, doubl
 
 int64_t gadm_ridge_gcv_workspace_bytes(int64_t n, int64_t d, int64_t k, int64_t n_alphas) {
   const int64_t tiles = (n + gadm::ridge::kGcvRows - 1) / gadm::ridge::kGcvRows;
-  // q [d] | den [A, n] | Z^T [d, n] | per-tile partial sums [A, tiles, k]
-  return (d + n_alphas * n + d * n + n_alphas * tiles * k) * (int64_t)sizeof(double) + 256;
+  // q [d] | den [A, n] | Z^T [d, n] | per-tile partial sums [A, tiles, k]; every part starts 16-byte aligned
+  return ((d + 1) / 2 * 2 + (n_alphas * n + 1) / 2 * 2 + (d * n + 1) / 2 * 2 + n_alphas * tiles * k) * (int64_t)sizeof(double) + 256;
 }
 
 int gadm_ridge_gcv(gadm_handle h, const double* z, const double* t, const double* yc, const double* evals,
@@ -1044,9 +1050,9 @@ int gadm_ridge_gcv(gadm_handle h, const double* z, const double* t, const double
   cudaStream_t st = as_stream(stream);
   const int64_t tiles = (n + gadm::ridge::kGcvRows - 1) / gadm::ridge::kGcvRows;
   double* q_work = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  double* den_work = q_work + d;
-  double* zt = den_work + n_alphas * n;
-  double* partial = zt + d * n;
+  double* den_work = q_work + (d + 1) / 2 * 2;
+  double* zt = den_work + (n_alphas * n + 1) / 2 * 2;
+  double* partial = zt + (d * n + 1) / 2 * 2;
   gadm::ridge::column_sums_kernel<<<(unsigned)((d + 63) / 64), 64, 0, st>>>(z, n, d, q_work);
   GADM_LAUNCHED(h);
   const int64_t jobs = n_alphas * n;

@@ -161,6 +161,15 @@ __device__ __forceinline__ void tma_load_3d_cg2(uint32_t smem_dst, const void* t
       : "memory");
 }
 
+// 1-D bulk copy global -> shared::cta through the TMA engine (no tensor map): src / dst 16-byte aligned, bytes % 16 == 0;
+// completion bytes are signalled on an mbarrier of the executing CTA
+__device__ __forceinline__ void bulk_copy_global_to_smem(uint32_t smem_dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
 // shared::cta -> (peer) shared::cluster bulk copy through the async proxy; completion bytes are signalled on an
 // mbarrier that lives in the destination CTA
 __device__ __forceinline__ void bulk_copy_smem_to_cluster(uint32_t cluster_dst, uint32_t smem_src, uint32_t bytes,

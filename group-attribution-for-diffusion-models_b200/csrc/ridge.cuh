@@ -147,19 +147,17 @@ __global__ void ridge_denominator_kernel(const double* __restrict__ Z, const dou
 // 2 A n d K flops of fp64 over 8 n K bytes of Yc: ~2500 flop / byte at (A, d) = (100, 100), i.e. bound by the fp64
 // FMA pipe.  Round 1 ran one CTA per (alpha, 64 behaviours): Yc was re-read once per alpha (176.8 GB of DRAM traffic
 // for ~2 GB at K = 2 * 10^5) and the 8-accumulator thread tile kept the pipe at 31 %.  Now one CTA owns a tile of
-// 128 rows x 64 behaviours for ALL alphas: its 8 x 4 Yc values per thread stay in registers across the alpha loop,
+// 128 rows x 64 behaviours for ALL alphas: the Yc tile stays in shared memory across the alpha loop,
 // Z^T (contiguous along rows) and T stream through shared memory by cp.async in chunks of 32 contraction indices, one
 // chunk ahead of the arithmetic, w_j(alpha) is applied on the fly, and the inner loop is 32 DFMA per 6 LDS.128.  Row tiles write per-tile partial sums; ridge_gcv_reduce_kernel adds them
 // in tile order (deterministic).  No limit on d any more.
 constexpr int kGcvRows = 128;
 constexpr int kGcvCols = 64;
 constexpr int kGcvJ = 32;
-constexpr int kGcvThreads = 256;
-// double-buffered chunks + reduce scratch + the Yc tile (+ d doubles: w table)
-constexpr int kGcvSmemBytes = 2 * kGcvJ * (kGcvRows + kGcvCols) * 8 + 16 * kGcvCols * 8 + kGcvRows * kGcvCols * 8;
-// column c of a 64-wide tile row lives at this position, so that the 16 threads that read columns 4 tx + 2 q .. + 1
-// with one LDS.128 touch 256 consecutive bytes (no bank conflicts) instead of 16 segments 32 bytes apart (4-way)
-__host__ __device__ constexpr int gcv_col_pos(int c) { return ((c >> 1) & 1) * 32 + (c >> 2) * 2 + (c & 1); }
+constexpr int kGcvThreads = 512;  // 16 (column groups of 4) x 32 (row groups of 4): 16 warps per SM
+// double-buffered chunks + reduce scratch + the Yc tile + two mbarriers (+ d doubles: w table)
+constexpr int kGcvSmemBytes =
+    2 * kGcvJ * (kGcvRows + kGcvCols) * 8 + (kGcvThreads / 16) * kGcvCols * 8 + kGcvRows * kGcvCols * 8 + 64;
 
 // Zt[j, i] = Z[i, j]  (so that a row tile of Z^T is contiguous)
 __global__ void transpose_f64_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, double* __restrict__ out) {
@@ -182,108 +180,131 @@ ridge_gcv_score_kernel(const double* __restrict__ Zt, const double* __restrict__
                        const double* __restrict__ alphas, int64_t n, int64_t d, int64_t K, int64_t A,
                        double* __restrict__ partial) {
   extern __shared__ __align__(16) double gcv_smem[];
+  constexpr int kGroups = kGcvThreads / 16;               // row groups of 4
   double* zt = gcv_smem;                                  // [2][kGcvJ][kGcvRows]  Z^T chunk
   double* tt = gcv_smem + 2 * kGcvJ * kGcvRows;           // [2][kGcvJ][kGcvCols]  T chunk (unscaled)
-  double* red = tt + 2 * kGcvJ * kGcvCols;                // [16][kGcvCols]
-  double* ycs = red + 16 * kGcvCols;                      // [kGcvRows][kGcvCols]  Yc tile (read once per alpha)
-  double* wtab = ycs + kGcvRows * kGcvCols;               // [d]  w_j(alpha) of the current alpha
+  double* red = tt + 2 * kGcvJ * kGcvCols;                // [kGroups][kGcvCols]
+  double* ycs = red + kGroups * kGcvCols;                 // [kGcvRows][kGcvCols]  Yc tile (read once per alpha)
+  double* bars = ycs + kGcvRows * kGcvCols;               // two mbarriers
+  double* wtab = bars + 8;                                // [d]  w_j(alpha) of the current alpha
+  const uint32_t bar0 = smem_u32(bars);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kGcvCols;
   const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kGcvRows;
   const int64_t tiles = gridDim.y;
-  for (int idx = tid; idx < kGcvRows * kGcvCols; idx += kGcvThreads) {
-    const int64_t i = i0 + idx / kGcvCols, k = k0 + idx % kGcvCols;
-    ycs[idx] = (i < n && k < K) ? Yc[i * K + k] : 0.0;
+  const int vr = static_cast<int>((n - i0) < kGcvRows ? (n - i0) : kGcvRows);  // valid rows / columns of this tile
+  const int vc = static_cast<int>((K - k0) < kGcvCols ? (K - k0) : kGcvCols);
+  // one TMA bulk copy per tile row needs 16-byte aligned, even-length rows; otherwise per-thread 8-byte cp.async
+  const bool bulk = (n % 2 == 0) && (K % 2 == 0) && ((reinterpret_cast<uintptr_t>(Zt) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(T) & 15) == 0);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
   }
+  for (int idx = tid; idx < kGcvRows * kGcvCols; idx += kGcvThreads) {
+    const int r = idx / kGcvCols, c = idx % kGcvCols;
+    ycs[idx] = (r < vr && c < vc) ? Yc[(i0 + r) * K + k0 + c] : 0.0;
+  }
+  // rows / columns beyond the matrix are never copied: zero them once (both buffers)
+  for (int idx = tid; idx < 2 * kGcvJ * kGcvRows; idx += kGcvThreads)
+    if (idx % kGcvRows >= vr) zt[idx] = 0.0;
+  for (int idx = tid; idx < 2 * kGcvJ * kGcvCols; idx += kGcvThreads)
+    if (idx % kGcvCols >= vc) tt[idx] = 0.0;
+  __syncthreads();
   const int nchunks = static_cast<int>((d + kGcvJ - 1) / kGcvJ);
-  // chunk loads: asynchronous 8-byte copies (zero-filled out of range), issued one chunk ahead of the arithmetic
   auto issue_chunk = [&](int buf, int c) {
-    const int64_t j = static_cast<int64_t>(c) * kGcvJ + (tid >> 3);
-    {
-      const int cc = (tid & 7) * 16;
-      double* dst = zt + (buf * kGcvJ + (tid >> 3)) * kGcvRows + cc;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int64_t i = i0 + cc + e;
-        const bool ok = j < d && i < n;
-        agg::cp_async_f64(dst + e, ok ? Zt + j * n + i : Zt, ok);
+    const int64_t j0 = static_cast<int64_t>(c) * kGcvJ;
+    const int jn = static_cast<int>((d - j0) < kGcvJ ? (d - j0) : kGcvJ);
+    if (bulk) {
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar0 + 8 * buf, static_cast<uint32_t>(jn * (vr + vc) * 8));
+        for (int jj = 0; jj < jn; ++jj) {
+          bulk_copy_global_to_smem(smem_u32(zt + (buf * kGcvJ + jj) * kGcvRows), Zt + (j0 + jj) * n + i0,
+                                   static_cast<uint32_t>(vr * 8), bar0 + 8 * buf);
+          bulk_copy_global_to_smem(smem_u32(tt + (buf * kGcvJ + jj) * kGcvCols), T + (j0 + jj) * K + k0,
+                                   static_cast<uint32_t>(vc * 8), bar0 + 8 * buf);
+        }
       }
-    }
-    {
-      const int cc = (tid & 7) * 8;
-      double* dst = tt + (buf * kGcvJ + (tid >> 3)) * kGcvCols + cc;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int64_t k = k0 + cc + e;
-        const bool ok = j < d && k < K;
-        agg::cp_async_f64(dst - cc + gcv_col_pos(cc + e), ok ? T + j * K + k : T, ok);
-      }
+    } else {
+      for (int idx = tid; idx < jn * vr; idx += kGcvThreads)
+        agg::cp_async_f64(zt + (buf * kGcvJ + idx / vr) * kGcvRows + idx % vr, Zt + (j0 + idx / vr) * n + i0 + idx % vr, true);
+      for (int idx = tid; idx < jn * vc; idx += kGcvThreads)
+        agg::cp_async_f64(tt + (buf * kGcvJ + idx / vc) * kGcvCols + idx % vc, T + (j0 + idx / vc) * K + k0 + idx % vc, true);
     }
   };
+  auto wait_chunk = [&](int buf, uint32_t phase) {
+    if (bulk) mbar_wait(bar0 + 8 * buf, phase, 0x910 + buf);
+    else agg::cp_async_commit_wait_all();
+  };
 
+  uint32_t fills[2] = {0u, 0u};  // how often each buffer has been filled (mbarrier phase parity)
   for (int64_t a = 0; a < A; ++a) {
     const double alpha = alphas[a];
-    double acc[8][4];
+    double acc[4][4];
 #pragma unroll
-    for (int p = 0; p < 8; ++p)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[p][c] = 0.0;
     issue_chunk(0, 0);
     for (int64_t j = tid; j < d; j += kGcvThreads) wtab[j] = 1.0 / (evals[j] + alpha);
-    agg::cp_async_commit_wait_all();
+    wait_chunk(0, fills[0] & 1u);
+    ++fills[0];
     __syncthreads();
     int buf = 0;
     for (int c = 0; c < nchunks; ++c) {
       if (c + 1 < nchunks) issue_chunk(buf ^ 1, c + 1);
       const int64_t j0 = static_cast<int64_t>(c) * kGcvJ;
       const int jn = static_cast<int>((d - j0) < kGcvJ ? (d - j0) : kGcvJ);
-      const double* zb = zt + buf * kGcvJ * kGcvRows + ty * 8;
+      const double* zb = zt + buf * kGcvJ * kGcvRows + ty * 4;
       const double* tb = tt + buf * kGcvJ * kGcvCols + tx * 2;
 #pragma unroll 4
       for (int jj = 0; jj < jn; ++jj) {
         const double w = wtab[j0 + jj];
-        double x[8], y[4];
+        double x[4], y[4];
         const double2* xp = reinterpret_cast<const double2*>(zb + jj * kGcvRows);
         const double* yrow = tb + jj * kGcvCols;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const double2 t2 = xp[q]; x[2 * q] = t2.x; x[2 * q + 1] = t2.y; }
+        for (int q = 0; q < 2; ++q) { const double2 t2 = xp[q]; x[2 * q] = t2.x; x[2 * q + 1] = t2.y; }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const double2 t2 = *reinterpret_cast<const double2*>(yrow + q * 32);
+          const double2 t2 = *reinterpret_cast<const double2*>(yrow + q * 32);  // columns agg::tile_col(tx, .)
           y[2 * q] = t2.x * w; y[2 * q + 1] = t2.y * w;
         }
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) acc[p][cc] = fma(x[p], y[cc], acc[p][cc]);
       }
-      agg::cp_async_commit_wait_all();
+      if (c + 1 < nchunks) {
+        wait_chunk(buf ^ 1, fills[buf ^ 1] & 1u);
+        ++fills[buf ^ 1];
+      }
       __syncthreads();
       buf ^= 1;
     }
-    // squared leave-one-out errors of this thread's 8 rows, summed in row order; then over the 16 row groups in order
+    // squared leave-one-out errors of this thread's 4 rows, summed in row order; then over the row groups in order
     double s[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int64_t i = i0 + ty * 8 + p;
-      if (i < n) {
-        const double dd = den[a * n + i];
+    for (int p = 0; p < 4; ++p) {
+      const int r = ty * 4 + p;
+      if (r < vr) {
+        const double dd = den[a * n + i0 + r];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const double e = (ycs[(ty * 8 + p) * kGcvCols + tx * 4 + c] - acc[p][c]) / dd;
+          const double e = (ycs[r * kGcvCols + agg::tile_col(tx, c)] - acc[p][c]) / dd;
           s[c] += e * e;
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) red[ty * kGcvCols + tx * 4 + c] = s[c];
+    for (int c = 0; c < 4; ++c) red[ty * kGcvCols + agg::tile_col(tx, c)] = s[c];
     __syncthreads();
     if (tid < kGcvCols) {
       double t = 0.0;
-#pragma unroll
-      for (int g = 0; g < 16; ++g) t += red[g * kGcvCols + tid];
-      const int64_t k = k0 + tid;
-      if (k < K) partial[(a * tiles + blockIdx.y) * K + k] = t;
+#pragma unroll 8
+      for (int g = 0; g < kGroups; ++g) t += red[g * kGcvCols + tid];
+      if (tid < vc) partial[(a * tiles + blockIdx.y) * K + k0 + tid] = t;
     }
     __syncthreads();
   }
