@@ -35,6 +35,15 @@ METRIC = "projected_grads_per_sec"
 UNIT = "grads/s"
 
 
+def bench_config(proj_type: str, rows: int, world: int):
+    """The workload both arms are measured on (the reference arm prints the same dict)."""
+    return {"workload": "CIFAR-10 DDPM TRAK featurisation (BASELINE configs[1]): JL projection of per-example U-Net "
+                        f"gradients, fp32 [32, D] batches -> [{rows}, 4096] features per step per GPU",
+            "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": proj_type, "rows_per_step_per_gpu": rows,
+            "sharding": f"examples x{world}",
+            "l2": f"staged input ({rows * GRAD_DIM * 2 / 1e9:.1f} GB) and split-K partials exceed the 126 MB L2"}
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -134,7 +143,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     t_begin = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        v, cores, sample, t_blk = _cpu_projector_rate(seconds_target=3.0)
+        v, cores, sample, t_blk = _cpu_projector_rate(seconds_target=3.0, proj_type=args.proj_type)
         if i >= args.warmup:
             vals.append(v)
         if time.perf_counter() - t_begin > 150 and vals:
@@ -144,8 +153,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": args.warmup, "ms_per_step": 1e3 * 1024 / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CIFAR-10 DDPM TRAK featurisation: JL projection of per-example U-Net gradients",
-                   "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": "normal", "batch": 8},
+        "config": bench_config(args.proj_type, 1024 if args.proj_type == "normal" else STAGE_ROWS, max(1, args.gpus)),
+        "reference_batch": 8,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -397,14 +406,10 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 staged gradients x bf16 P, fp32 accumulate" if proj.stage_dtype == "f16" else "bf16",
             "data": "synthetic",
-            "config": {"workload": "CIFAR-10 DDPM TRAK featurisation: JL projection of per-example U-Net gradients "
-                                   f"(BASELINE configs[1]), {rows} examples per step per GPU through "
-                                   "CudaProjector.deferred().add(fp32 [32, D] on the device) -> result()",
-                       "grad_dim": GRAD_DIM, "proj_dim": PROJ_DIM, "proj_type": args.proj_type,
-                       "rows_per_step_per_gpu": rows, "sharding": f"examples x{world}",
-                       "staging": f"{proj.stage_dtype} staging inside the timed region"
-                                  + (", overlapped with the previous pass (second staging buffer, side stream)" if overlap else ", serial"),
-                       "l2": f"staged input ({rows * GRAD_DIM * 2 / 1e9:.1f} GB) and split-K partials exceed the 126 MB L2"},
+            "config": bench_config(args.proj_type, rows, world),
+            "pipeline": {"api": "CudaProjector.deferred().add(fp32 [32, D] on the device) -> result()",
+                         "staging": f"{proj.stage_dtype} staging inside the timed region"
+                                    + (", overlapped with the previous pass (second staging buffer, side stream)" if overlap else ", serial")},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                          "peak_kind": f"bf16_tflops_sustained of measured ({peaks['source']}); timed inside a multi-step loop",
