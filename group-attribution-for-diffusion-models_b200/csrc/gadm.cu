@@ -660,7 +660,10 @@ int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, i
   dim3 grid((unsigned)((cols + gadm::gemm::kTrCols - 1) / gadm::gemm::kTrCols),
             (unsigned)((rows + gadm::gemm::kTrRows - 1) / gadm::gemm::kTrRows));
   GADM_REQUIRE(grid.y < 65536, "too many row tiles");
-  gadm::gemm::transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, rows, cols, ld_in, out, ld_out);
+  GADM_CUDA(cudaFuncSetAttribute(gadm::gemm::transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gadm::gemm::kTrSmemBytes));
+  gadm::gemm::transpose_kernel<<<grid, dim3(32, 8), gadm::gemm::kTrSmemBytes, as_stream(stream)>>>(in, rows, cols, ld_in, out,
+                                                                                                  ld_out);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

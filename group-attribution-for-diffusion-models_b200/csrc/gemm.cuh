@@ -431,30 +431,38 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // ------------------------------------------------------------------ helpers around the GEMM
 
 // out[c, r] = in[r, c]; in: [R, C] pitch ld_in; out: [C, R_pad] pitch ld_out (columns R..ld_out untouched).
-// HBM-bound (8 B per element).  Tile = 128 rows x 64 columns: 256-byte read segments, 512-byte contiguous write
-// segments per output row -- with 32 x 32 tiles every 128-byte segment opened its own DRAM page on both sides
-// and the kernel ran at 300 GB/s (5.5 ms for the 50 000 x 4096 features of config 2).
-constexpr int kTrRows = 128, kTrCols = 64;
+// HBM-bound (8 B per element).  Tile = 128 rows x 128 columns: 512-byte contiguous segments on BOTH sides -- with
+// 32 x 32 tiles every 128-byte segment opened its own DRAM page on both sides and the kernel ran at 300 GB/s (5.5 ms
+// for the 50 000 x 4096 features of config 2); 128 x 64 tiles (256-byte reads) reached 1.35 TB/s, 1.2 ms of the 8.7 ms
+// config-2 score.
+constexpr int kTrRows = 128, kTrCols = 128;
+constexpr int kTrSmemBytes = kTrCols * (kTrRows + 1) * 4;
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t ld_in, float* __restrict__ out,
                  int64_t ld_out) {
-  __shared__ float tile[kTrCols][kTrRows + 1];
+  extern __shared__ float tr_tile[];  // [kTrCols][kTrRows + 1]
+  auto tile = [&](int c, int r) -> float& { return tr_tile[c * (kTrRows + 1) + r]; };
   const int x = threadIdx.x, y = threadIdx.y;  // (32, 8)
   const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kTrCols, r0 = static_cast<int64_t>(blockIdx.y) * kTrRows;
   const bool vec_ok = (ld_in % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
 #pragma unroll 4
   for (int i = y; i < kTrRows; i += 8) {
-    const int64_t r = r0 + i, c = c0 + 2 * x;
-    float2 v = make_float2(0.f, 0.f);
-    if (r < R) {
-      if (vec_ok && c + 1 < Ccols) v = *reinterpret_cast<const float2*>(in + r * ld_in + c);
-      else {
-        if (c < Ccols) v.x = in[r * ld_in + c];
-        if (c + 1 < Ccols) v.y = in[r * ld_in + c + 1];
+    const int64_t r = r0 + i;
+#pragma unroll
+    for (int h = 0; h < kTrCols / 64; ++h) {  // a warp reads 2 x 256 contiguous bytes of one row
+      const int cl = h * 64 + 2 * x;
+      const int64_t c = c0 + cl;
+      float2 v = make_float2(0.f, 0.f);
+      if (r < R) {
+        if (vec_ok && c + 1 < Ccols) v = *reinterpret_cast<const float2*>(in + r * ld_in + c);
+        else {
+          if (c < Ccols) v.x = in[r * ld_in + c];
+          if (c + 1 < Ccols) v.y = in[r * ld_in + c + 1];
+        }
       }
+      tile(cl, i) = v.x;
+      tile(cl + 1, i) = v.y;
     }
-    tile[2 * x][i] = v.x;
-    tile[2 * x + 1][i] = v.y;
   }
   __syncthreads();
 #pragma unroll 2
@@ -464,7 +472,7 @@ transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t
 #pragma unroll
     for (int j = 0; j < kTrRows / 32; ++j) {
       const int64_t r = r0 + x + 32 * j;
-      if (r < R) out[c * ld_out + r] = tile[cc][x + 32 * j];
+      if (r < R) out[c * ld_out + r] = tile(cc, x + 32 * j);
     }
   }
 }
@@ -555,6 +563,7 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
   float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse of the factor
   float* Tm = X + kPotrfNb * kPotrfLd;          // [64][kPotrfTLd] scratch
   __shared__ float dinv_s[kPotrfSb];            // 1 / diagonal of the current 32 x 32 factor
+  __shared__ __align__(16) float col_s[2 * kPotrfSb];  // the factor column being eliminated (double-buffered)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef GADM_POTRF_PROFILE
   __shared__ long long prof_t[24];
@@ -574,7 +583,10 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
     const int j0 = jb * kPotrfSb;
     POTRF_T(4);
     if (warp == 0) {
-      // ---- factor the 32 x 32 diagonal sub-block in registers: lane i owns row i
+      // ---- factor the 32 x 32 diagonal sub-block in registers: lane i owns row i.  Column c of the factor is
+      // published through a double-buffered 32-float shared-memory line and read back as broadcast LDS.128 (8 loads)
+      // instead of one shuffle per remaining row (31 per column): the shuffles were the issue-bound part of this
+      // one-warp critical path (6.6 k cycles per sub-block, a third of the kernel).
       float r[kPotrfSb];
       float dinv = 1.f;
 #pragma unroll
@@ -593,10 +605,18 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
         const float lc = (lane == c) ? d * y : r[c] * y;  // column c of the factor, held by lane = row
         if (lane == c) dinv = y;                          // 1 / L[c][c], reused by the panel solve and the inverse
         r[c] = lc;
+        if (c + 1 < kPotrfSb) {
+          float* line = col_s + (c & 1) * kPotrfSb;
+          line[lane] = lc;
+          __syncwarp();
 #pragma unroll
-        for (int t = c + 1; t < kPotrfSb; ++t) {
-          const float ltc = __shfl_sync(0xffffffffu, lc, t);
-          r[t] = fmaf(-lc, ltc, r[t]);  // only rows >= t are meaningful; the others are never read again
+          for (int q = (c + 1) / 4; q < kPotrfSb / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(line + 4 * q);  // rows 4q .. 4q + 3 of column c
+            if (4 * q + 0 > c) r[4 * q + 0] = fmaf(-lc, v.x, r[4 * q + 0]);  // only rows >= t are meaningful;
+            if (4 * q + 1 > c) r[4 * q + 1] = fmaf(-lc, v.y, r[4 * q + 1]);  // the others are never read again
+            if (4 * q + 2 > c) r[4 * q + 2] = fmaf(-lc, v.z, r[4 * q + 2]);
+            if (4 * q + 3 > c) r[4 * q + 3] = fmaf(-lc, v.w, r[4 * q + 3]);
+          }
         }
       }
 #pragma unroll
