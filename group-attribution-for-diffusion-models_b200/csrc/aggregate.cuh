@@ -202,10 +202,13 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
         const double2 t2 = *reinterpret_cast<const double2*>(&ys[buf][rr][q * 32 + tx * 2]);
         y[2 * q] = t2.x; y[2 * q + 1] = t2.y;
       }
+      if (kShift) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (kShift) y[c] -= sh[c];
-        tot[c] += y[c];
+        for (int c = 0; c < 4; ++c) y[c] -= sh[c];
+      }
+      if (ty == 0) {  // the column totals are the same for every player group: one group computes them (rows in order)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tot[c] += y[c];
       }
 #pragma unroll
       for (int p = 0; p < 8; ++p)
@@ -219,6 +222,15 @@ mask_xty_kernel(const uint32_t* __restrict__ rowbits, int64_t wd, const double* 
     __syncthreads();
     buf ^= 1;
   }
+  // hand the column totals to the other player groups through the (now idle) Y buffer
+  double* tot_s = &ys[0][0][0];
+  if (ty == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tot_s[tile_col(tx, c)] = tot[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tot[c] = tot_s[tile_col(tx, c)];
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
     const int64_t i = i0 + ty * 8 + p;

@@ -657,8 +657,9 @@ int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, i
                    int64_t ld_out, void* stream) {
   GADM_REQUIRE(h && in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "bad argument");
   DeviceGuard guard(h->device);
+  const int64_t rows_per_cta = (int64_t)gadm::gemm::kTrRows * gadm::gemm::kTrSub;
   dim3 grid((unsigned)((cols + gadm::gemm::kTrCols - 1) / gadm::gemm::kTrCols),
-            (unsigned)((rows + gadm::gemm::kTrRows - 1) / gadm::gemm::kTrRows));
+            (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
   GADM_REQUIRE(grid.y < 65536, "too many row tiles");
   GADM_CUDA(cudaFuncSetAttribute(gadm::gemm::transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gadm::gemm::kTrSmemBytes));

@@ -431,11 +431,11 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // ------------------------------------------------------------------ helpers around the GEMM
 
 // out[c, r] = in[r, c]; in: [R, C] pitch ld_in; out: [C, R_pad] pitch ld_out (columns R..ld_out untouched).
-// HBM-bound (8 B per element).  Tile = 128 rows x 128 columns: 512-byte contiguous segments on BOTH sides -- with
-// 32 x 32 tiles every 128-byte segment opened its own DRAM page on both sides and the kernel ran at 300 GB/s (5.5 ms
-// for the 50 000 x 4096 features of config 2); 128 x 64 tiles (256-byte reads) reached 1.35 TB/s, 1.2 ms of the 8.7 ms
-// config-2 score.
-constexpr int kTrRows = 128, kTrCols = 128;
+// HBM-bound (8 B per element).  Tile = 128 rows x 64 columns: 256-byte read segments, 512-byte contiguous write
+// segments per output row -- with 32 x 32 tiles every 128-byte segment opened its own DRAM page on both sides and the
+// kernel ran at 300 GB/s (5.5 ms for the 50 000 x 4096 features of config 2); now 1.2 ms (1.35 TB/s).  Measured and
+// rejected in round 2: 128 x 128 tiles (1.38 ms) and four consecutive row tiles per CTA (worse).
+constexpr int kTrRows = 128, kTrCols = 64, kTrSub = 1;
 constexpr int kTrSmemBytes = kTrCols * (kTrRows + 1) * 4;
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t ld_in, float* __restrict__ out,
@@ -443,8 +443,12 @@ transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t
   extern __shared__ float tr_tile[];  // [kTrCols][kTrRows + 1]
   auto tile = [&](int c, int r) -> float& { return tr_tile[c * (kTrRows + 1) + r]; };
   const int x = threadIdx.x, y = threadIdx.y;  // (32, 8)
-  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kTrCols, r0 = static_cast<int64_t>(blockIdx.y) * kTrRows;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kTrCols;
   const bool vec_ok = (ld_in % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
+  for (int sub = 0; sub < kTrSub; ++sub) {
+  const int64_t r0 = (static_cast<int64_t>(blockIdx.y) * kTrSub + sub) * kTrRows;
+  if (r0 >= R) break;
+  if (sub) __syncthreads();  // the previous tile has been written out
 #pragma unroll 4
   for (int i = y; i < kTrRows; i += 8) {
     const int64_t r = r0 + i;
@@ -474,6 +478,7 @@ transpose_kernel(const float* __restrict__ in, int64_t R, int64_t Ccols, int64_t
       const int64_t r = r0 + x + 32 * j;
       if (r < R) out[c * ld_out + r] = tile(cc, x + 32 * j);
     }
+  }
   }
 }
 
