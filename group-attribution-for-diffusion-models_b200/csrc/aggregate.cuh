@@ -483,9 +483,6 @@ __global__ void dgemm_dk_kernel(const double* __restrict__ A, const double* __re
 //   colsum = 1^T Ainv ; dd = 1^T Ainv 1 ; c_k = colsum . b[:,k] - v1_k + v0_k ; rhs[:,k] = b[:,k] - c_k / dd
 __global__ void shapley_colsum_kernel(const double* __restrict__ Ainv, int64_t d, double* __restrict__ colsum) {
   // one block; colsum[d] holds dd
-  __shared__ double s_tot;
-  if (threadIdx.x == 0) s_tot = 0.0;
-  __syncthreads();
   for (int64_t j = threadIdx.x; j < d; j += blockDim.x) {
     double a = 0.0;
     for (int64_t i = 0; i < d; ++i) a += Ainv[i * d + j];
@@ -512,41 +509,99 @@ __global__ void shapley_rhs_kernel(const double* __restrict__ colsum, const doub
 
 // ------------------------------------------------------------------ Spearman / LDS
 // rho[e, k] = Spearman( pred[idx[e, :], k], y[idx[e, :], k] )  (average ranks for ties; NaN when a
-// side is constant -- scipy.stats.spearmanr semantics).  idx == nullptr: identity over the m rows.
+// side is constant or holds a NaN -- scipy.stats.spearmanr semantics).  idx == nullptr: identity over the m rows.
 // One warp per (e, k); m_r <= kLdsMaxRows rows.
+//
+// Ranks by sorting (round 1 counted "how many are smaller" for every element: O(m^2) comparisons per job): the warp
+// runs a bitonic network over (value, original index) keys in shared memory -- log2(mp) (log2(mp) + 1) / 2 stages of
+// mp / 2 compare-exchanges, mp = m rounded up to a power of two, padded with +inf keys that sort last -- then every
+// sorted position finds the ends of its run of equal values by two binary searches and scatters twice its average
+// rank to the element's original slot.  Twice-ranks are integers <= 2 m, and the three sums of products below are
+// sums of multiples of 1/4 far below 2^53, hence exact in any order: the result is bit-identical to the counting
+// kernel's.
 constexpr int kLdsMaxRows = 1024;
 constexpr int kLdsPerLane = kLdsMaxRows / 32;
+__host__ __device__ inline int64_t lds_pow2(int64_t m) { int64_t p = 32; while (p < m) p <<= 1; return p; }
+__host__ __device__ inline size_t lds_warp_smem_bytes(int64_t mr) {  // keys [mp] f64, order [mp] u16, twice-ranks 2 x [mp] u16
+  return static_cast<size_t>(lds_pow2(mr)) * (8 + 2 + 2 + 2);
+}
+
+// sorts key[0..mp) ascending by (key, ord); all 32 lanes participate
+__device__ __forceinline__ void warp_bitonic_sort(double* key, uint16_t* ord, int mp, int lane) {
+  for (int k = 2; k <= mp; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (mp >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const double a = key[i], b = key[l];
+        const uint16_t oa = ord[i], ob = ord[l];
+        const bool gt = (a > b) || (a == b && oa > ob);
+        if (gt == ((i & k) == 0)) {  // ascending block: swap when out of order; descending block: the opposite
+          key[i] = b; key[l] = a;
+          ord[i] = ob; ord[l] = oa;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// twice the average 1-based rank of every element, written to rank2[original index]; key / ord sorted, m real entries
+__device__ __forceinline__ void warp_average_ranks(const double* key, const uint16_t* ord, int m, uint16_t* rank2, int lane) {
+  for (int p = lane; p < m; p += 32) {
+    const double v = key[p];
+    int lo = 0, hi = p;  // first position holding v
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] < v) lo = mid + 1; else hi = mid; }
+    const int first = lo;
+    lo = p; hi = m - 1;  // last position holding v
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (key[mid] > v) hi = mid - 1; else lo = mid; }
+    rank2[ord[p]] = static_cast<uint16_t>(first + lo + 2);  // 2 * ((first + 1) + (last + 1)) / 2
+  }
+  __syncwarp();
+}
+
 __global__ void lds_spearman_kernel(const double* __restrict__ pred, const double* __restrict__ y, int64_t m, int64_t K,
                                     const int32_t* __restrict__ idx, int64_t R, int64_t mr, double* __restrict__ rho) {
-  extern __shared__ double lds_smem[];  // [warps][2][mr]
+  extern __shared__ __align__(16) unsigned char lds_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int64_t job = static_cast<int64_t>(blockIdx.x) * nw + warp;
   if (job >= R * K) return;
   const int64_t e = job / K, k = job % K;
-  double* sa = lds_smem + static_cast<size_t>(warp) * 2 * mr;
-  double* sb = sa + mr;
-  for (int64_t r = lane; r < mr; r += 32) {
-    const int64_t row = idx ? idx[e * mr + r] : r;
-    sa[r] = pred[row * K + k];
-    sb[r] = y[row * K + k];
-  }
-  __syncwarp();
-  const double mean = 0.5 * (static_cast<double>(mr) + 1.0);
-  double sab = 0.0, saa = 0.0, sbb = 0.0;
-  for (int64_t r = lane; r < mr; r += 32) {
-    const double a = sa[r], b = sb[r];
-    int la = 0, ea = 0, lb = 0, eb = 0;
-    for (int64_t t = 0; t < mr; ++t) {
-      const double at = sa[t], bt = sb[t];
-      la += (at < a); ea += (at == a);
-      lb += (bt < b); eb += (bt == b);
+  const int mp = static_cast<int>(lds_pow2(mr)), mi = static_cast<int>(mr);
+  unsigned char* base = lds_smem + static_cast<size_t>(warp) * lds_warp_smem_bytes(mr);
+  double* key = reinterpret_cast<double*>(base);
+  uint16_t* ord = reinterpret_cast<uint16_t*>(base + static_cast<size_t>(mp) * 8);
+  uint16_t* ra2 = ord + mp;
+  uint16_t* rb2 = ra2 + mp;
+  bool has_nan = false;
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const double* src = side == 0 ? pred : y;
+    for (int r = lane; r < mp; r += 32) {
+      double v = __longlong_as_double(0x7ff0000000000000ll);  // +inf padding, original index >= m: sorts last
+      if (r < mi) {
+        const int64_t row = idx ? idx[e * mr + r] : r;
+        v = src[row * K + k];
+        has_nan |= (v != v);
+      }
+      key[r] = v;
+      ord[r] = static_cast<uint16_t>(r);
     }
-    const double ra = la + 0.5 * (ea + 1) - mean;  // average rank (1-based) minus the mean rank
-    const double rb = lb + 0.5 * (eb + 1) - mean;
+    __syncwarp();
+    warp_bitonic_sort(key, ord, mp, lane);
+    warp_average_ranks(key, ord, mi, side == 0 ? ra2 : rb2, lane);
+  }
+  const double mean2 = static_cast<double>(mr) + 1.0;  // twice the mean rank
+  double sab = 0.0, saa = 0.0, sbb = 0.0;
+  for (int r = lane; r < mi; r += 32) {
+    const double ra = 0.5 * (static_cast<double>(ra2[r]) - mean2);  // average rank minus the mean rank (exact)
+    const double rb = 0.5 * (static_cast<double>(rb2[r]) - mean2);
     sab += ra * rb; saa += ra * ra; sbb += rb * rb;
   }
   sab = warp_sum(sab); saa = warp_sum(saa); sbb = warp_sum(sbb);
-  if (lane == 0) rho[job] = (sab / sqrt(saa)) / sqrt(sbb);  // corrcoef's two-step normalisation; 0/0 -> NaN
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  if (lane == 0)  // corrcoef's two-step normalisation; 0/0 -> NaN
+    rho[job] = has_nan ? __longlong_as_double(0x7ff8000000000000ll) : (sab / sqrt(saa)) / sqrt(sbb);
 }
 
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h, pairwise_sum_@TYPE@), restated over a stream of

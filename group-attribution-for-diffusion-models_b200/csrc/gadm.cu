@@ -35,6 +35,8 @@ struct gadm_ctx {
                                 // flight on different streams of one device never share a barrier
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
   bool attr_gemm = false, attr_gemm_ts = false, attr_potrf = false;  // per-device kernel attributes already set
+  cudaEvent_t pass_resident = nullptr;  // fires when every CTA of the last projection pass has begun (launch completion)
+  int pass_resident_state = 0;  // 0 = no pass launched yet, 1 = event recorded by the last launch, -1 = unsupported
   uint32_t attr_stage = 0;      // bit per staging-kernel instantiation whose carveout preference has been set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start / panel / rest / end
@@ -149,6 +151,11 @@ int plan_projection(gadm_handle h, int64_t m_rows, int64_t d_pad, int64_t proj_d
     const int qc = quad_cluster_count(h);
     if (qc <= 0) return fail(GADM_ERR_CUDA, "no co-resident 4-CTA clusters available for the quad projection kernel");
     p->n_clusters = (uint32_t)qc;
+    // a cluster count that is a multiple of the column-tile count gives every cluster exactly one (tile, D-split)
+    // unit with the fewest splits (C2: 32 clusters = 16 tiles x 2 halves instead of 33 x 16 partial tiles through the
+    // workspace) -- measured faster than the full 33 under the power cap, and it leaves whole SMs to the staging CTAs
+    const uint32_t even = (uint32_t)qc / p->n_tiles * p->n_tiles;
+    if (even > 0 && even * 16u >= (uint32_t)qc * 15u) p->n_clusters = even;
   } else {
     p->n_clusters = (uint32_t)(h->num_sms / cta_group);
   }
@@ -211,30 +218,63 @@ int launch_clusters(gadm_handle h, Kernel kernel, int cluster_size, int threads,
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster_size;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeCooperative;  // co-residency guarantee for the inter-cluster lockstep
-  attr[1].val.cooperative = 1;
+  // launch-completion event: lets gadm_wait_pass_resident hold the staging launches of the next pass back until
+  // this grid's clusters own their SMs (otherwise whichever grid becomes runnable first takes every SM and the
+  // other queues behind it for several milliseconds)
+  if (h->pass_resident_state >= 0 && !h->pass_resident &&
+      cudaEventCreateWithFlags(&h->pass_resident, cudaEventDisableTiming) != cudaSuccess) {
+    (void)cudaGetLastError();
+    h->pass_resident = nullptr;
+    h->pass_resident_state = -1;
+  }
   cfg.attrs = attr;
   gadm::proj::Args a = args;
   bool cooperative = true;
   int rc = setup_lockstep(h, &a, clusters, stream, &cooperative);
   if (rc != GADM_OK) return rc;
+  auto launch_with = [&](bool coop, bool with_event) -> cudaError_t {
+    unsigned n = 1;
+    if (with_event) {
+      attr[n].id = cudaLaunchAttributeLaunchCompletionEvent;
+      attr[n].val.launchCompletionEvent.event = h->pass_resident;
+      attr[n].val.launchCompletionEvent.flags = 0;
+      ++n;
+    }
+    if (coop) {  // co-residency guarantee for the inter-cluster lockstep
+      attr[n].id = cudaLaunchAttributeCooperative;
+      attr[n].val.cooperative = 1;
+      ++n;
+    }
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, tmap, a);
+  };
+  auto launch = [&](bool coop) -> cudaError_t {
+    if (h->pass_resident_state >= 0 && h->pass_resident) {
+      if (launch_with(coop, true) == cudaSuccess) {
+        h->pass_resident_state = 1;
+        return cudaSuccess;
+      }
+      (void)cudaGetLastError();
+      const cudaError_t e = launch_with(coop, false);
+      if (e == cudaSuccess) h->pass_resident_state = -1;  // it was the event attribute the driver refused
+      return e;
+    }
+    return launch_with(coop, false);
+  };
   if (a.sync_iters && cooperative) {
-    cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, a);
-    if (e == cudaSuccess) {
+    if (launch(true) == cudaSuccess) {
       h->launches++;
       return GADM_OK;
     }
     (void)cudaGetLastError();  // cooperative launch refused (GPU shared / too large): run without the lockstep
     a.sync_iters = 0;
   }
-  cfg.numAttrs = 1;
-  GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, a));
+  GADM_CUDA(launch(false));
   h->launches++;
   return GADM_OK;
 }
@@ -265,6 +305,7 @@ int quad_cluster_count(gadm_handle h) {
   } else {
     (void)cudaGetLastError();
   }
+  if (const char* e = getenv("GADM_QUAD_CLUSTERS")) { const int v = atoi(e); if (v >= 1 && v < n) n = v; }  // experiment
   h->quad_clusters = n;
   return n;
 }
@@ -320,28 +361,41 @@ inline int64_t stage_scale_count(int64_t d_pad) {
 
 template <typename T>
 int launch_stage(gadm_handle h, const gadm::stage::BlockTable& tab, int64_t batch, float scale, void* staged,
-                        int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale, cudaStream_t st) {
+                 int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale, int coresident,
+                 cudaStream_t st) {
   const int64_t groups = stage_scale_count(d_pad);
   dim3 grid((unsigned)groups, (unsigned)batch);
   auto* dst = reinterpret_cast<uint16_t*>(staged);
-  // Same shared-memory carveout preference as the persistent projection kernel (maximum): an SM serves one carveout
-  // configuration at a time, and a staging CTA that asks for a small one would wait for the projection CTA to leave
-  // instead of running beside it.
+  const bool f16 = stage_dtype == GADM_STAGE_F16G;
+  float* sc = f16 ? inv_scale : nullptr;
+  if (!coresident) {  // wide CTAs: the whole GPU when alone, the SMs a 4-CTA-cluster projection grid strands otherwise
+    if (f16)
+      gadm::stage::stage_groups_wide_kernel<T, true><<<grid, gadm::stage::kWideThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad,
+                                                                                                 scale, sc, groups);
+    else
+      gadm::stage::stage_groups_wide_kernel<T, false><<<grid, gadm::stage::kWideThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad,
+                                                                                                  scale, sc, groups);
+    GADM_LAUNCHED(h);
+    return GADM_OK;
+  }
+  // Narrow CTAs run beside a persistent projection CTA.  Same shared-memory carveout preference as that kernel
+  // (maximum): an SM serves one carveout configuration at a time, and a staging CTA that asks for a small one would
+  // wait for the projection CTA to leave instead of running beside it.
   auto prefer_max_smem = [&](auto kernel, uint32_t bit) -> int {
     if (h->attr_stage & bit) return GADM_OK;
     GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     h->attr_stage |= bit;
     return GADM_OK;
   };
-  const uint32_t bit = 1u << (2 * sizeof(T) + (stage_dtype == GADM_STAGE_F16G ? 1 : 0) + (std::is_same<T, __half>::value ? 8 : 0));
-  if (stage_dtype == GADM_STAGE_F16G) {
+  const uint32_t bit = 1u << (2 * sizeof(T) + (f16 ? 1 : 0) + (std::is_same<T, __half>::value ? 8 : 0));
+  if (f16) {
     GADM_TRY_RC(prefer_max_smem(gadm::stage::stage_groups_kernel<T, true>, bit));
-    gadm::stage::stage_groups_kernel<T, true><<<grid, gadm::stage::kThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
-                                                                                      inv_scale, groups);
+    gadm::stage::stage_groups_kernel<T, true><<<grid, gadm::stage::kNarrowThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
+                                                                                            sc, groups);
   } else {
     GADM_TRY_RC(prefer_max_smem(gadm::stage::stage_groups_kernel<T, false>, bit));
-    gadm::stage::stage_groups_kernel<T, false><<<grid, gadm::stage::kThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
-                                                                                       nullptr, groups);
+    gadm::stage::stage_groups_kernel<T, false><<<grid, gadm::stage::kNarrowThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
+                                                                                             sc, groups);
   }
   GADM_LAUNCHED(h);
   return GADM_OK;
@@ -388,11 +442,20 @@ int gadm_destroy(gadm_handle h) {
   if (h && h->scratch) cudaFree(h->scratch);
   if (h && h->hp_stream) cudaStreamDestroy(h->hp_stream);
   if (h) for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h && h->pass_resident) cudaEventDestroy(h->pass_resident);
   delete h;
   return GADM_OK;
 }
 
 int64_t gadm_launch_count(gadm_handle h) { return h ? h->launches : 0; }
+
+int gadm_wait_pass_resident(gadm_handle h, void* stream) {
+  GADM_REQUIRE(h, "null handle");
+  if (h->pass_resident_state != 1) return 0;  // nothing launched yet / attribute unsupported: no ordering added
+  DeviceGuard guard(h->device);
+  GADM_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), h->pass_resident, 0));
+  return 1;
+}
 
 int gadm_watchdog_code(gadm_handle h, unsigned int* code) {
   GADM_REQUIRE(h && code, "null argument");
@@ -454,7 +517,7 @@ int64_t gadm_stage_scale_count(int64_t d_pad) { return stage_scale_count(d_pad);
 
 int gadm_stage_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
                     void* staged, int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale,
-                    void* stream) {
+                    int coresident, void* stream) {
   GADM_REQUIRE(h && staged, "null argument");
   GADM_REQUIRE(stage_dtype == GADM_STAGE_BF16 || stage_dtype == GADM_STAGE_F16G, "unknown stage_dtype %d", stage_dtype);
   GADM_REQUIRE(stage_dtype == GADM_STAGE_BF16 || inv_scale, "the F16G staging format needs the inv_scale array");
@@ -466,9 +529,9 @@ int gadm_stage_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int d
   GADM_TRY_RC(fill_block_table(blocks, n_blocks, batch, d_pad, &tab));
   DeviceGuard guard(h->device);
   cudaStream_t st = as_stream(stream);
-  if (dtype == GADM_DTYPE_F32) return launch_stage<float>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, st);
-  if (dtype == GADM_DTYPE_BF16) return launch_stage<__nv_bfloat16>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, st);
-  if (dtype == GADM_DTYPE_F16) return launch_stage<__half>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, st);
+  if (dtype == GADM_DTYPE_F32) return launch_stage<float>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, coresident, st);
+  if (dtype == GADM_DTYPE_BF16) return launch_stage<__nv_bfloat16>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, coresident, st);
+  if (dtype == GADM_DTYPE_F16) return launch_stage<__half>(h, tab, batch, scale, staged, stage_dtype, d_pad, m_cap, row0, inv_scale, coresident, st);
   return fail(GADM_ERR_INVALID, "unknown dtype %d", dtype);
 }
 
@@ -485,11 +548,11 @@ int gadm_accumulate_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, 
   cudaStream_t st = as_stream(stream);
   dim3 grid((unsigned)((d_pad + gadm::stage::kAccCols - 1) / gadm::stage::kAccCols), (unsigned)batch);
   if (dtype == GADM_DTYPE_F32)
-    gadm::stage::accumulate_rows_kernel<float><<<grid, gadm::stage::kThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
+    gadm::stage::accumulate_rows_kernel<float><<<grid, gadm::stage::kWideThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
   else if (dtype == GADM_DTYPE_BF16)
-    gadm::stage::accumulate_rows_kernel<__nv_bfloat16><<<grid, gadm::stage::kThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
+    gadm::stage::accumulate_rows_kernel<__nv_bfloat16><<<grid, gadm::stage::kWideThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
   else if (dtype == GADM_DTYPE_F16)
-    gadm::stage::accumulate_rows_kernel<__half><<<grid, gadm::stage::kThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
+    gadm::stage::accumulate_rows_kernel<__half><<<grid, gadm::stage::kWideThreads, 0, st>>>(tab, slab, d_pad, row0, scale, accumulate);
   else
     return fail(GADM_ERR_INVALID, "unknown dtype %d", dtype);
   GADM_LAUNCHED(h);
@@ -1146,9 +1209,10 @@ int gadm_lds_spearman(gadm_handle h, const double* pred, const double* y, int64_
   GADM_REQUIRE(rows_per_eval > 0 && rows_per_eval <= gadm::agg::kLdsMaxRows, "rows_per_eval %lld out of range (1..%d)",
                (long long)rows_per_eval, gadm::agg::kLdsMaxRows);
   DeviceGuard guard(h->device);
+  const size_t per_warp = gadm::agg::lds_warp_smem_bytes(rows_per_eval);  // <= 14 KiB
   int warps = 8;
-  while (warps > 1 && (size_t)warps * 2 * rows_per_eval * sizeof(double) > 48 * 1024) warps /= 2;
-  const size_t smem = (size_t)warps * 2 * rows_per_eval * sizeof(double);
+  while (warps > 1 && (size_t)warps * per_warp > 48 * 1024) warps /= 2;
+  const size_t smem = (size_t)warps * per_warp;
   const int64_t jobs = n_eval * k;
   gadm::agg::lds_spearman_kernel<<<(unsigned)((jobs + warps - 1) / warps), warps * 32, smem, as_stream(stream)>>>(
       pred, y, m, k, idx, n_eval, rows_per_eval, rho);
@@ -1204,7 +1268,7 @@ int gadm_project(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtyp
                  uint64_t seed64, int proj_type, float* out, int64_t ld_out, int accumulate, void* workspace,
                  int64_t workspace_bytes, int cta_group, void* stream) {
   GADM_REQUIRE(h && blocks && n_blocks > 0 && staged && out && batch > 0, "bad argument");
-  GADM_TRY(gadm_stage_rows(h, blocks, n_blocks, dtype, batch, scale, staged, stage_dtype, d_pad, m_cap, 0, inv_scale, stream));
+  GADM_TRY(gadm_stage_rows(h, blocks, n_blocks, dtype, batch, scale, staged, stage_dtype, d_pad, m_cap, 0, inv_scale, 0, stream));
   return gadm_project_staged(h, staged, stage_dtype, inv_scale, batch, d_pad, m_cap, 0, proj_dim, seed64, proj_type, out,
                              ld_out, accumulate, workspace, workspace_bytes, cta_group, stream);
 }

@@ -76,7 +76,11 @@ __device__ __forceinline__ uint32_t box_muller_pair(uint32_t x) {
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(theta));
   if constexpr (kF16) {
     const __half2 v = __floats2half2_rn(__fmul_rn(r, c), __fmul_rn(r, s));  // .x (low) = even p
+#ifdef GADM_P_MASK  // experiment: clear the low mantissa bits of P (tensor-pipe power)
+    return *reinterpret_cast<const uint32_t*>(&v) & GADM_P_MASK;
+#else
     return *reinterpret_cast<const uint32_t*>(&v);
+#endif
   } else {
     const __nv_bfloat162 v = __floats2bfloat162_rn(__fmul_rn(r, c), __fmul_rn(r, s));
     return *reinterpret_cast<const uint32_t*>(&v);

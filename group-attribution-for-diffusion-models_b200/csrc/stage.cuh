@@ -32,7 +32,13 @@ namespace stage {
 
 constexpr int kGroupKb = 512;                 // k-blocks (of 64 columns) per scale group
 constexpr int kGroupCols = kGroupKb * 64;     // 32768
-constexpr int kThreads = 128;  // 128 threads x <= 32 registers = the 4096 registers a resident projection CTA leaves free on its SM
+// Two CTA shapes.  "narrow": 128 threads x <= 32 registers + a 12 KiB ring = what a resident projection CTA leaves
+// free on its SM, so the CTA runs BESIDE the persistent projection kernel.  "wide": 256 threads, a 32 KiB ring -- it
+// does not fit beside a projection CTA, so while the 4-CTA-cluster (quad) projection is running it is confined to
+// the 16 SMs that grid cannot use (33 clusters = 132 of 148 SMs) and does not disturb the other 132 at all; alone it
+// spreads over the whole GPU.
+constexpr int kNarrowThreads = 128, kNarrowDepth = 3;
+constexpr int kWideThreads = 256, kWideDepth = 4;
 constexpr int kMaxBlocks = 1024;              // parameter blocks per launch (kernel-parameter space: 24 B each)
 
 // Parameter blocks of one example, sorted by position in the flattened gradient.  Entry i covers columns
@@ -64,7 +70,7 @@ __device__ __forceinline__ float load_as_float<__half>(const __half* p) { return
 
 // Walks the columns [c_lo, c_hi) of example `ex` eight at a time on the global column grid (c_lo % 64 == 0, so an octet
 // never straddles a 64-column row of the staging buffer): f(p, v[8]); columns no block covers read as 0.  Thread t
-// takes octets t, t + kThreads, ...; the block that held the previous octet is cached, the table is only searched
+// takes octets t, t + blockDim.x, ...; the block that held the previous octet is cached, the table is only searched
 // when an octet leaves it (~n_blocks times per row), and an octet that straddles a block boundary takes the
 // per-element path.  Values are returned unscaled.
 template <typename T>
@@ -120,7 +126,6 @@ struct BlockCursor {
 // instructions -- 16-byte copies (512 contiguous bytes per instruction) when the chunk's source is 16-byte aligned,
 // 4-byte copies (128 contiguous bytes per instruction) otherwise (fp32 rows of odd length) -- and lane l then reads
 // columns 8 l .. 8 l + 7 of the chunk back.  Chunks that straddle a block boundary / gap are fetched synchronously.
-constexpr int kDepth = 3;
 constexpr int kChunk = 256;  // columns per warp per ring slot
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -132,7 +137,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-template <typename T>
+template <typename T, int kThreads, int kDepth>
 struct ChunkStream {
   static constexpr uint32_t kSlotBytes = kChunk * sizeof(T);  // per warp
   static constexpr uint32_t kRingBytes = kDepth * (kThreads / 32) * kSlotBytes;
@@ -193,34 +198,47 @@ struct ChunkStream {
     }
   }
 
-  // f(p, v) for every octet of [c_lo, c_hi) ((c_hi - c_lo) % 64 == 0) that belongs to this thread; v reads as zero
-  // beyond c_hi is never produced: chunks are clipped to whole 64-column rows by the caller's bounds check on p.
-  // kEvery > 1: only every kEvery-th step of the warp (the columns [1024 j, 1024 j + 1024) of the range with
-  // j % kEvery == 0) -- the sample pass of the scale guess.
-  template <int kEvery = 1, typename F>
-  __device__ __forceinline__ void for_each(int64_t c_lo, int64_t c_hi, F&& f) {
+  // f(p, v) for every octet of this warp's chunks; the warp takes the chunks s = warp, warp + kWarps, ... of a
+  // sequence of n_seq chunks whose first columns are given by start(s) -- all chunks of the range in order, or the
+  // sampled chunks of the scale guess -- with kDepth fetches in flight.  c_hi bounds the octets that are emitted.
+  template <typename Start, typename F>
+  __device__ __forceinline__ void for_each_chunk(int n_seq, int64_t c_hi, Start&& start, F&& f) {
     constexpr int kWarps = kThreads / 32;
-    const int64_t first = c_lo + static_cast<int64_t>(threadIdx.x >> 5) * kChunk;
-    constexpr int64_t kStep = static_cast<int64_t>(kWarps) * kChunk * kEvery;
-    const int n = first < c_hi ? static_cast<int>((c_hi - first + kStep - 1) / kStep) : 0;
+    const int w = threadIdx.x >> 5;
+    const int n = n_seq > w ? (n_seq - w + kWarps - 1) / kWarps : 0;
 #pragma unroll
     for (int i = 0; i < kDepth; ++i)
-      if (i < n) issue(first + i * kStep, i);
+      if (i < n) issue(start(w + i * kWarps), i);
     int r = 0;
     for (int i = 0; i < n; ++i) {
       if (n - i >= kDepth) cp_async_wait<kDepth - 1>(); else cp_async_wait<0>();
       __syncwarp();  // every lane's copies of this slot have landed
       float v[8];
       consume(r, v);
-      const int64_t p = first + i * kStep + 8 * lane;
+      const int64_t p = start(w + i * kWarps) + 8 * lane;
       if (p < c_hi) f(p, v);
       __syncwarp();  // every lane has read the slot before it is refilled
-      if (i + kDepth < n) issue(first + (i + kDepth) * kStep, r);
+      if (i + kDepth < n) issue(start(w + (i + kDepth) * kWarps), r);
       r = (r + 1 == kDepth) ? 0 : r + 1;
     }
   }
+  // every chunk of [c_lo, c_hi)  ((c_hi - c_lo) % 64 == 0)
+  template <typename F>
+  __device__ __forceinline__ void for_each(int64_t c_lo, int64_t c_hi, F&& f) {
+    const int n_chunks = static_cast<int>((c_hi - c_lo + kChunk - 1) / kChunk);
+    for_each_chunk(n_chunks, c_hi, [&](int s) { return c_lo + static_cast<int64_t>(s) * kChunk; }, f);
+  }
+  // the sample of the scale guess: the first 1024 of every 8192 columns of the range (chunks with id % 32 < 4) --
+  // a fixed set of columns, independent of the CTA shape
+  template <typename F>
+  __device__ __forceinline__ void for_each_sampled(int64_t c_lo, int64_t c_hi, F&& f) {
+    const int n_chunks = static_cast<int>((c_hi - c_lo + kChunk - 1) / kChunk);
+    const int n_seq = (n_chunks / 32) * 4 + ((n_chunks % 32) < 4 ? (n_chunks % 32) : 4);
+    for_each_chunk(n_seq, c_hi, [&](int s) { return c_lo + static_cast<int64_t>((s >> 2) * 32 + (s & 3)) * kChunk; }, f);
+  }
 };
 
+template <int kThreads>
 __device__ __forceinline__ float block_max(float v, float* smem) {
   __syncthreads();  // the previous result has been read by everyone
 #pragma unroll
@@ -260,17 +278,16 @@ __device__ __forceinline__ float exp2_int(int s) { return __uint_as_float(static
 // which leaves 4096 registers, 1280 threads and ~15 KB of shared memory per SM.  A staging CTA is sized to fit into
 // exactly that (128 threads, __maxnreg__(32), a 12 KiB cp.async ring), so that staging the next pass on another
 // stream proceeds WHILE a pass is being projected instead of queueing behind it; alone, 16 such CTAs fill an SM.
-template <typename T, bool kF16>
-__global__ void __maxnreg__(32)
-stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
+template <typename T, bool kF16, int kThreads, int kDepth>
+__device__ __forceinline__ void stage_groups_body(const BlockTable& tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
                     int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
   __shared__ float red[kThreads / 32];
-  __shared__ __align__(16) uint8_t ring[ChunkStream<T>::kRingBytes];
+  __shared__ __align__(16) uint8_t ring[ChunkStream<T, kThreads, kDepth>::kRingBytes];
   const int64_t g = blockIdx.x, b = blockIdx.y;
   const int64_t row = row0 + b;
   const int64_t c_lo = g * kGroupCols;
   const int64_t c_hi = (c_lo + kGroupCols < d_pad) ? c_lo + kGroupCols : d_pad;
-  ChunkStream<T> in(tab, b, static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
+  ChunkStream<T, kThreads, kDepth> in(tab, b, static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
   uint16_t* drow = dst + row * 64;
   float mul = scale;
   float amax = 0.f;
@@ -297,15 +314,15 @@ stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict
     convert_pass();
     return;
   }
-  in.template for_each<8>(c_lo, c_hi, [&](int64_t, const float (&v)[8]) {
+  in.for_each_sampled(c_lo, c_hi, [&](int64_t, const float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
   });
-  int s = group_scale_exponent(block_max(amax, red) * fabsf(scale), 11);
+  int s = group_scale_exponent(block_max<kThreads>(amax, red) * fabsf(scale), 11);
   mul = scale * exp2_int(s);  // exact unless it leaves the normal range, which the exponent clamp excludes for
                               // |scale| in [2^-20, 2^20]
   convert_pass();
-  const float true_max = block_max(amax, red) * fabsf(scale);
+  const float true_max = block_max<kThreads>(amax, red) * fabsf(scale);
   const float landed = true_max * exp2_int(s);
   if (!(landed >= 256.f && landed < 65504.f) && !(true_max == 0.f)) {  // the sample misjudged the group: exact scale
     s = group_scale_exponent(true_max, 13);
@@ -315,19 +332,32 @@ stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict
   if (threadIdx.x == 0) inv_scale[row * groups_per_row + g] = exp2_int(-s);
 }
 
+template <typename T, bool kF16>
+__global__ void __maxnreg__(32)
+stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
+                    int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
+  stage_groups_body<T, kF16, kNarrowThreads, kNarrowDepth>(tab, dst, m_cap, row0, d_pad, scale, inv_scale, groups_per_row);
+}
+template <typename T, bool kF16>
+__global__ void __launch_bounds__(kWideThreads)
+stage_groups_wide_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
+                         int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
+  stage_groups_body<T, kF16, kWideThreads, kWideDepth>(tab, dst, m_cap, row0, d_pad, scale, inv_scale, groups_per_row);
+}
+
 // Timestep accumulator: slab[row0 + b, p] = (accumulate ? slab : 0) + scale * src   (fp32 slab [rows][d_pad]).
 // grid = (ceil(d_pad / 8192), batch)
 constexpr int kAccCols = 8192;
 template <typename T>
-__global__ void __maxnreg__(32)
+__global__ void __launch_bounds__(kWideThreads)
 accumulate_rows_kernel(const __grid_constant__ BlockTable tab, float* __restrict__ slab, int64_t d_pad, int64_t row0,
                        float scale, int accumulate) {
   const int64_t b = blockIdx.y;
   const int64_t c_lo = static_cast<int64_t>(blockIdx.x) * kAccCols;
   const int64_t c_hi = (c_lo + kAccCols < d_pad) ? c_lo + kAccCols : d_pad;
   float* out = slab + (row0 + b) * d_pad;
-  __shared__ __align__(16) uint8_t ring[ChunkStream<T>::kRingBytes];
-  ChunkStream<T> in(tab, b, static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
+  __shared__ __align__(16) uint8_t ring[ChunkStream<T, kWideThreads, kWideDepth>::kRingBytes];
+  ChunkStream<T, kWideThreads, kWideDepth> in(tab, b, static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
   in.for_each(c_lo, c_hi, [&](int64_t p, const float (&v)[8]) {
     float4* o = reinterpret_cast<float4*>(out + p);  // d_pad % 64 == 0 and p % 8 == 0: 32-byte aligned
     // separate round-to-nearest multiply and add (no FMA contraction): bit-identical to emb += grads * scale in fp32

@@ -183,7 +183,9 @@ class CudaProjector:
 
     def _side_stream(self) -> torch.cuda.Stream:
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            # high priority: when a pass and the staging launches of the next one become runnable together, the
+            # pass's clusters are placed first as SMs drain (staging CTAs are short) instead of queueing behind them
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
         return self._side
 
     def _check_free(self, who) -> None:
@@ -218,14 +220,15 @@ class CudaProjector:
             i += 1
         return arr, len(live), _DTYPES[blocks[0].dtype], bsz
 
-    def _pack(self, blocks, stage: _Stage, row0: int, scale: float = 1.0) -> int:
-        """Stage a batch (all parameter blocks in one launch) into rows row0.. of `stage`."""
+    def _pack(self, blocks, stage: _Stage, row0: int, scale: float = 1.0, coresident: bool = False) -> int:
+        """Stage a batch (all parameter blocks in one launch) into rows row0.. of `stage`.  ``coresident``: narrow CTAs
+        that run beside a CTA-pair projection pass on the same SMs (gadm_stage_rows)."""
         arr, n, dtype, bsz = self._block_table(blocks)
         lib, h = self._handle.lib, self._handle.ptr
         _lib.check(lib.gadm_stage_rows(h, arr, n, dtype, bsz, float(scale), stage.data.data_ptr(),
                                        _STAGE_CODES[self.stage_dtype], self.d_pad, stage.rows, row0,
                                        stage.inv_scale.data_ptr() if stage.inv_scale is not None else None,
-                                       _lib.stream_ptr(self.device)))
+                                       int(coresident), _lib.stream_ptr(self.device)))
         return bsz
 
     def _accumulate(self, blocks, slab: torch.Tensor, scale: float, accumulate: bool) -> None:
@@ -337,7 +340,10 @@ class DeferredProjection:
             while done < bsz:
                 take = min(bsz - done, cap - self.rows)
                 stage = self.p._stage(cap, self.cur)
-                self.p._pack([b[done:done + take] for b in blocks], stage, self.rows, scale)
+                # while a pass runs on the side stream: the quad kernel strands 16 SMs, wide staging CTAs use exactly
+                # those; the pair kernels cover every SM, so the staging CTAs must be the narrow, co-resident shape
+                self.p._pack([b[done:done + take] for b in blocks], stage, self.rows, scale,
+                             coresident=self.overlap and self.p._group_for(cap) != 4)
                 self.rows += take
                 done += take
                 if self.rows == cap:
@@ -390,6 +396,8 @@ class DeferredProjection:
                 nxt = p._stage(p.stage_rows, self.cur)
                 if nxt.done is not None:  # the pass that last read the other buffer must be over before it is refilled
                     main.wait_event(nxt.done)
+                # ... and the pass just launched owns its SMs before the next staging launches take what is left
+                _lib.check(p._handle.lib.gadm_wait_pass_resident(p._handle.ptr, _lib.stream_ptr(p.device)))
         self.outputs.append(out)
         self.rows = 0
         p._owner = None

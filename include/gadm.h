@@ -100,10 +100,21 @@ int64_t gadm_stage_scale_count(int64_t d_pad);
 /* Stage a batch of examples in ONE launch: rows row0 .. row0 + batch of the staging buffer receive
  * convert(src * scale) for every column; `blocks` (host array, sorted by row_offset, non-overlapping, at most 1024)
  * lists the parameter blocks, columns no block covers (gaps, the tail up to d_pad) are written as zeros.
- * scale = 1/K folds the timestep mean (d_trak_grad.py:770).  inv_scale: see GADM_STAGE_F16G (NULL for bf16). */
+ * scale = 1/K folds the timestep mean (d_trak_grad.py:770).  inv_scale: see GADM_STAGE_F16G (NULL for bf16).
+ * coresident selects the CTA shape, results are identical: 0 = wide CTAs (the whole GPU when nothing else runs; while a
+ * 4-CTA-cluster projection is running on another stream they are confined to the 16 SMs that grid cannot use and do
+ * not disturb it), 1 = narrow CTAs sized to run beside a persistent projection CTA on the same SM (for the CTA-pair
+ * projection kernels, whose grid covers every SM). */
 int gadm_stage_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int dtype, int64_t batch, float scale,
                     void* staged, int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale,
-                    void* stream);
+                    int coresident, void* stream);
+
+/* Makes `stream` wait until every CTA of the projection pass this handle launched last (gadm_project_staged, on any
+ * stream) has begun execution -- a launch-completion event, best effort by the driver's definition; no-op before the
+ * first pass.  A pipelined caller puts it in front of the staging launches of the next pass: the pass then owns its
+ * SMs before the (wide) staging CTAs take what is left, instead of racing them for every SM.  Returns 1 when a wait
+ * was enqueued, 0 when there was nothing to wait for (or the driver refused the event attribute), < 0 on error. */
+int gadm_wait_pass_resident(gadm_handle h, void* stream);
 
 /* Timestep accumulator: slab[row0 + b, p] = (accumulate ? slab[row0 + b, p] : 0) + scale * src  for an fp32 slab
  * [slab_rows][d_pad] (32-byte aligned).  Sum K timesteps with scale = 1/K, then stage the slab rows with

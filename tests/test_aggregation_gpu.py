@@ -98,6 +98,60 @@ def test_spearman_ties_and_constant_input():
     _close(got[:4], want[:4], 1e-12)
 
 
+@pytest.mark.parametrize("m", [2, 3, 31, 32, 33, 100, 511, 1000, 1024])
+def test_spearman_sort_ranks_all_sizes(m):
+    """lds_spearman_kernel ranks by a warp bitonic sort over (value, index) keys padded to a power of two: every
+    size class (below / at / above a power of two, the 1024-row maximum), heavy ties, resampled rows with duplicates,
+    against scipy.stats.spearmanr (shapley_lds.py:138-150)."""
+    import gadm_b200 as G
+    from scipy.stats import spearmanr
+
+    rng = np.random.RandomState(m)
+    K = 4
+    pred = rng.normal(size=(m, K))
+    pred[:, 1] = np.round(pred[:, 1])             # heavy ties
+    pred[:, 2] = rng.randint(0, 2, size=m)        # two values only
+    Y = rng.normal(size=(m, K))
+    Y[:, 3] = np.round(Y[:, 3] * 2) / 2
+    eye = np.eye(m)                               # X_test = identity: X_test @ attrs == pred exactly
+    idx = np.stack([np.arange(m), rng.randint(0, m, size=m)])  # identity + a bootstrap resample with duplicates
+    got = G.spearman_matrix(eye, Y, pred, idx=idx)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for e in range(2):
+            want = np.array([spearmanr(pred[idx[e], k], Y[idx[e], k]).statistic for k in range(K)])
+            np.testing.assert_array_equal(np.isnan(got[e]), np.isnan(want))
+            ok = ~np.isnan(want)
+            _close(got[e][ok], want[ok], 1e-12)
+
+
+def test_spearman_infinities_and_nan():
+    """Through the C ABI directly (no mask product in front): +-inf rank as ordinary extreme values, a NaN on either
+    side gives NaN (scipy's nan_policy='propagate')."""
+    import ctypes as C
+    import torch
+    import gadm_b200._lib as L
+    from scipy.stats import spearmanr
+
+    h = L.get_handle(torch.device("cuda:0"))
+    rng = np.random.RandomState(0)
+    m, K = 37, 4
+    a = rng.normal(size=(m, K)); b = rng.normal(size=(m, K))
+    a[[0, 5, 9], 0] = np.inf; a[[1, 2], 0] = -np.inf
+    b[3, 1] = np.inf
+    a[4, 2] = np.nan
+    b[7, 3] = np.nan
+    ta, tb = torch.tensor(a, device="cuda:0"), torch.tensor(b, device="cuda:0")
+    rho = torch.empty(1, K, dtype=torch.float64, device="cuda:0")
+    L.check(h.lib.gadm_lds_spearman(h.ptr, ta.data_ptr(), tb.data_ptr(), m, K, None, 1, m, rho.data_ptr(),
+                                    L.stream_ptr(torch.device("cuda:0"))))
+    got = rho.cpu().numpy()[0]
+    want = np.array([spearmanr(a[:, k], b[:, k]).statistic for k in range(K)])
+    assert np.isnan(got[2]) and np.isnan(got[3]) and np.isnan(want[2]) and np.isnan(want[3])
+    _close(got[:2], want[:2], 1e-12)
+
+
 def test_config5_size_against_oracle():
     """BASELINE config 5: 1k masks x 100 contributors x 1k behaviours, 3 x 100 test subsets."""
     import gadm_b200 as G

@@ -176,7 +176,7 @@ def test_staging_is_bit_identical_to_the_oracle_rounding(stage_dtype, src_dtype)
     grads = grads.to(src_dtype).to(DEV)
     p = _proj(D, 512, 3, "rademacher", stage_dtype=stage_dtype, stage_rows=8)
     ref = grads.float().cpu().numpy()
-    for scale, as_blocks in ((1.0, False), (0.1, True)):
+    for scale, as_blocks, coresident in ((1.0, False, False), (0.1, True, False), (1.0, False, True), (0.1, True, True)):
         st = p._stage(8)
         st.data.fill_(7.0)             # stale contents must be overwritten, padding columns zeroed
         if as_blocks:
@@ -185,7 +185,7 @@ def test_staging_is_bit_identical_to_the_oracle_rounding(stage_dtype, src_dtype)
         else:
             inp = grads
         from gadm_b200.projectors import _as_blocks
-        p._pack(_as_blocks(inp), st, 2, scale)
+        p._pack(_as_blocks(inp), st, 2, scale, coresident=coresident)   # wide / narrow CTA shape: same bits
         torch.cuda.synchronize()
         staged = st.data[:, 2:2 + B, :].permute(1, 0, 2).reshape(B, -1).float()
         assert float(staged[:, D:].abs().max()) == 0.0

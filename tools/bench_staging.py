@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--aligned", action="store_true")
     ap.add_argument("--type", default="normal")
     ap.add_argument("--stage-dtype", default=None)
+    ap.add_argument("--wait-resident", type=int, default=1)
+    ap.add_argument("--coresident", type=int, default=None, help="0 wide CTAs, 1 narrow (default: what the API picks)")
     a = ap.parse_args()
     D = (a.D + 3) // 4 * 4 if a.aligned else a.D
     dev = torch.device("cuda:0")
@@ -30,10 +32,11 @@ def main():
     s0, s1 = p._stage(rows, 0), p._stage(rows, 1)
     out = torch.empty(rows, 4096, device=dev)
     bytes_per_add = 32 * D * 6
+    co = bool(a.coresident) if a.coresident is not None else p._group_for(rows) != 4
 
     def stage_all(st):
         for r in range(0, rows, 32):
-            p._pack(blocks, st, r)
+            p._pack(blocks, st, r, coresident=co)
 
     stage_all(s0)
     torch.cuda.synchronize()
@@ -45,9 +48,9 @@ def main():
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(); p._project_rows(s0, rows, 0, out); k1.record(); torch.cuda.synchronize()
     proj_alone_ms = k0.elapsed_time(k1)
-    side = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev, priority=-1)
     res = {}
-    for order in ("project_first", "stage_first"):
+    for order in ("project_first", "stage_first", "queued"):
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,6 +60,18 @@ def main():
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 a0.record(); p._project_rows(s0, rows, 0, out); a1.record()
+            if a.wait_resident:
+                res["wait_enqueued"] = p._handle.lib.gadm_wait_pass_resident(p._handle.ptr, torch.cuda.current_stream().cuda_stream)
+            b0.record(); stage_all(s1); b1.record()
+        elif order == "queued":  # as in the pipeline: everything is enqueued while an earlier staging still runs
+            stage_all(s0)
+            t0.record()
+            ev = torch.cuda.Event(); ev.record()
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                a0.record(); p._project_rows(s0, rows, 0, out); a1.record()
+            if a.wait_resident:
+                p._handle.lib.gadm_wait_pass_resident(p._handle.ptr, torch.cuda.current_stream().cuda_stream)
             b0.record(); stage_all(s1); b1.record()
         else:
             b0.record(); stage_all(s1); b1.record()
@@ -67,7 +82,7 @@ def main():
         t1.record()
         torch.cuda.synchronize()
         res[order] = {"project_ms": a0.elapsed_time(a1), "stage_ms": b0.elapsed_time(b1), "both_ms": t0.elapsed_time(t1)}
-    print(json.dumps({"D": D, "type": a.type, "stage_dtype": p.stage_dtype, "rows": rows,
+    print(json.dumps({"D": D, "type": a.type, "stage_dtype": p.stage_dtype, "rows": rows, "coresident": co,
                       "stage_alone_ms": alone_ms, "stage_alone_gbs_algorithmic": rows / 32 * bytes_per_add / alone_ms / 1e6,
                       "project_alone_ms": proj_alone_ms, "concurrent": res, "watchdog": p._handle.watchdog_code()}))
 
