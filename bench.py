@@ -404,7 +404,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 staged gradients x bf16 P, fp32 accumulate" if proj.stage_dtype == "f16" else "bf16",
+            "dtype": "f16 (group-scaled gradients, 11 bits) x f16 (P, 8 significant bits), fp32 accumulate" if proj.stage_dtype == "f16" else "bf16",
             "data": "synthetic",
             "config": bench_config(args.proj_type, rows, world),
             "pipeline": {"api": "CudaProjector.deferred().add(fp32 [32, D] on the device) -> result()",

@@ -26,7 +26,6 @@ _SIGNATURES = {
     "gadm_pack_block": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_float,
                                   c_vp]),
     "gadm_stage_scale_count": (c_i64, [c_i64]),
-    "gadm_wait_pass_resident": (C.c_int, [c_vp, c_vp]),
     "gadm_stage_rows": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, C.c_float, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp,
                                   C.c_int, c_vp]),
     "gadm_accumulate_rows": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, C.c_float, c_vp, c_i64, c_i64, c_i64, C.c_int,

@@ -35,8 +35,7 @@ struct gadm_ctx {
                                 // flight on different streams of one device never share a barrier
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
   bool attr_gemm = false, attr_gemm_ts = false, attr_potrf = false;  // per-device kernel attributes already set
-  cudaEvent_t pass_resident = nullptr;  // fires when every CTA of the last projection pass has begun (launch completion)
-  int pass_resident_state = 0;  // 0 = no pass launched yet, 1 = event recorded by the last launch, -1 = unsupported
+  uint32_t attr_stage_wide = 0; // same, dynamic shared-memory opt-in of the wide staging kernels
   uint32_t attr_stage = 0;      // bit per staging-kernel instantiation whose carveout preference has been set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start / panel / rest / end
@@ -218,53 +217,23 @@ int launch_clusters(gadm_handle h, Kernel kernel, int cluster_size, int threads,
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster_size;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // launch-completion event: lets gadm_wait_pass_resident hold the staging launches of the next pass back until
-  // this grid's clusters own their SMs (otherwise whichever grid becomes runnable first takes every SM and the
-  // other queues behind it for several milliseconds)
-  if (h->pass_resident_state >= 0 && !h->pass_resident &&
-      cudaEventCreateWithFlags(&h->pass_resident, cudaEventDisableTiming) != cudaSuccess) {
-    (void)cudaGetLastError();
-    h->pass_resident = nullptr;
-    h->pass_resident_state = -1;
-  }
+  attr[1].id = cudaLaunchAttributeCooperative;  // co-residency guarantee for the inter-cluster lockstep
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
   gadm::proj::Args a = args;
   bool cooperative = true;
   int rc = setup_lockstep(h, &a, clusters, stream, &cooperative);
   if (rc != GADM_OK) return rc;
-  auto launch_with = [&](bool coop, bool with_event) -> cudaError_t {
-    unsigned n = 1;
-    if (with_event) {
-      attr[n].id = cudaLaunchAttributeLaunchCompletionEvent;
-      attr[n].val.launchCompletionEvent.event = h->pass_resident;
-      attr[n].val.launchCompletionEvent.flags = 0;
-      ++n;
-    }
-    if (coop) {  // co-residency guarantee for the inter-cluster lockstep
-      attr[n].id = cudaLaunchAttributeCooperative;
-      attr[n].val.cooperative = 1;
-      ++n;
-    }
-    cfg.numAttrs = n;
-    return cudaLaunchKernelEx(&cfg, kernel, tmap, a);
-  };
+  // (A launch-completion event on this launch, waited on by the next staging launches so that the pass owns its SMs
+  // first, was measured in round 2: the pass itself got 3 % slower with the attribute set -- not used.)
   auto launch = [&](bool coop) -> cudaError_t {
-    if (h->pass_resident_state >= 0 && h->pass_resident) {
-      if (launch_with(coop, true) == cudaSuccess) {
-        h->pass_resident_state = 1;
-        return cudaSuccess;
-      }
-      (void)cudaGetLastError();
-      const cudaError_t e = launch_with(coop, false);
-      if (e == cudaSuccess) h->pass_resident_state = -1;  // it was the event attribute the driver refused
-      return e;
-    }
-    return launch_with(coop, false);
+    cfg.numAttrs = coop ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, tmap, a);
   };
   if (a.sync_iters && cooperative) {
     if (launch(true) == cudaSuccess) {
@@ -368,13 +337,24 @@ int launch_stage(gadm_handle h, const gadm::stage::BlockTable& tab, int64_t batc
   auto* dst = reinterpret_cast<uint16_t*>(staged);
   const bool f16 = stage_dtype == GADM_STAGE_F16G;
   float* sc = f16 ? inv_scale : nullptr;
+  const uint32_t bit = 1u << (2 * sizeof(T) + (f16 ? 1 : 0) + (std::is_same<T, __half>::value ? 8 : 0));
   if (!coresident) {  // wide CTAs: the whole GPU when alone, the SMs a 4-CTA-cluster projection grid strands otherwise
-    if (f16)
-      gadm::stage::stage_groups_wide_kernel<T, true><<<grid, gadm::stage::kWideThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad,
-                                                                                                 scale, sc, groups);
-    else
-      gadm::stage::stage_groups_wide_kernel<T, false><<<grid, gadm::stage::kWideThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad,
-                                                                                                  scale, sc, groups);
+    constexpr uint32_t smem = gadm::stage::WideStream<T>::kSmemBytes;
+    auto opt_in = [&](auto kernel) -> int {
+      if (h->attr_stage_wide & bit) return GADM_OK;
+      GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      h->attr_stage_wide |= bit;
+      return GADM_OK;
+    };
+    if (f16) {
+      GADM_TRY_RC(opt_in(gadm::stage::stage_groups_wide_kernel<T, true>));
+      gadm::stage::stage_groups_wide_kernel<T, true><<<grid, gadm::stage::kWideThreads, smem, st>>>(tab, dst, m_cap, row0, d_pad,
+                                                                                                    scale, sc, groups);
+    } else {
+      GADM_TRY_RC(opt_in(gadm::stage::stage_groups_wide_kernel<T, false>));
+      gadm::stage::stage_groups_wide_kernel<T, false><<<grid, gadm::stage::kWideThreads, smem, st>>>(tab, dst, m_cap, row0, d_pad,
+                                                                                                     scale, sc, groups);
+    }
     GADM_LAUNCHED(h);
     return GADM_OK;
   }
@@ -387,7 +367,6 @@ int launch_stage(gadm_handle h, const gadm::stage::BlockTable& tab, int64_t batc
     h->attr_stage |= bit;
     return GADM_OK;
   };
-  const uint32_t bit = 1u << (2 * sizeof(T) + (f16 ? 1 : 0) + (std::is_same<T, __half>::value ? 8 : 0));
   if (f16) {
     GADM_TRY_RC(prefer_max_smem(gadm::stage::stage_groups_kernel<T, true>, bit));
     gadm::stage::stage_groups_kernel<T, true><<<grid, gadm::stage::kNarrowThreads, 0, st>>>(tab, dst, m_cap, row0, d_pad, scale,
@@ -442,20 +421,11 @@ int gadm_destroy(gadm_handle h) {
   if (h && h->scratch) cudaFree(h->scratch);
   if (h && h->hp_stream) cudaStreamDestroy(h->hp_stream);
   if (h) for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-  if (h && h->pass_resident) cudaEventDestroy(h->pass_resident);
   delete h;
   return GADM_OK;
 }
 
 int64_t gadm_launch_count(gadm_handle h) { return h ? h->launches : 0; }
-
-int gadm_wait_pass_resident(gadm_handle h, void* stream) {
-  GADM_REQUIRE(h, "null handle");
-  if (h->pass_resident_state != 1) return 0;  // nothing launched yet / attribute unsupported: no ordering added
-  DeviceGuard guard(h->device);
-  GADM_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), h->pass_resident, 0));
-  return 1;
-}
 
 int gadm_watchdog_code(gadm_handle h, unsigned int* code) {
   GADM_REQUIRE(h && code, "null argument");

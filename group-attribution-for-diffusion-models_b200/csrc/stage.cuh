@@ -27,6 +27,8 @@
 
 #include <cstdint>
 
+#include "gadm_ptx.cuh"
+
 namespace gadm {
 namespace stage {
 
@@ -37,6 +39,7 @@ constexpr int kGroupCols = kGroupKb * 64;     // 32768
 // does not fit beside a projection CTA, so while the 4-CTA-cluster (quad) projection is running it is confined to
 // the 16 SMs that grid cannot use (33 clusters = 132 of 148 SMs) and does not disturb the other 132 at all; alone it
 // spreads over the whole GPU.
+constexpr int kWideBulkDepth = 3, kWideBulkCols = 1024;
 constexpr int kNarrowThreads = 128, kNarrowDepth = 3;
 constexpr int kWideThreads = 256, kWideDepth = 4;
 constexpr int kMaxBlocks = 1024;              // parameter blocks per launch (kernel-parameter space: 24 B each)
@@ -167,14 +170,19 @@ struct ChunkStream {
       for (int i = 0; i < kChunk / 32; ++i) {
         const int64_t c = p0 + i * 32 + lane;
         if (!(c >= cur.lo && c < cur.hi)) cur.seek(c);
-        T v;
-        if (c >= cur.lo && c < cur.hi) v = cur.base[c - cur.lo];
-        else v = static_cast<T>(0.f);
+        const bool in_block = c >= cur.lo && c < cur.hi;
         const uint32_t d = dst + (i * 32 + lane) * sizeof(T);
-        if constexpr (sizeof(T) == 4)
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(d), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
-        else
+        if constexpr (sizeof(T) == 4) {
+          // asynchronous as well (part of this slot's commit group): a plain load here serialised 8 memory round
+          // trips per boundary chunk and held the whole warp -- +25 % staging time on a 270-tensor block table
+          if (in_block) cp_async_4(d, cur.base + (c - cur.lo));
+          else asm volatile("st.shared.b32 [%0], %1;" ::"r"(d), "r"(0u) : "memory");
+        } else {
+          T v;
+          if (in_block) v = cur.base[c - cur.lo];
+          else v = static_cast<T>(0.f);
           asm volatile("st.shared.u16 [%0], %1;" ::"r"(d), "h"(*reinterpret_cast<const unsigned short*>(&v)) : "memory");
+        }
       }
     }
     cp_async_commit();
@@ -238,6 +246,156 @@ struct ChunkStream {
   }
 };
 
+// ---- TMA chunk stream (fp32 sources, wide CTAs) --------------------------------------------------------------------
+// cp.async (LDGSTS) costs the SM 8 cycles per warp instruction whatever its width, i.e. 64 B/clk with 16-byte copies
+// but 16 B/clk with the 4-byte copies that three out of four fp32 rows of odd length need -- ~40 GB/s per SM measured,
+// which is what bounded staging whenever it had few SMs (beside a projection pass it gets 20).  Here the chunks are
+// fetched by the TMA engine instead: one lane issues ONE 1-D bulk copy per 256-column chunk (mbarrier completion, no
+// LSU issue slots, no registers).  Bulk copies need 16-byte aligned addresses and sizes, so a misaligned chunk is
+// fetched as the aligned 1040 bytes that contain it and the consumer shifts by 1-3 words in registers (three
+// LDS.128 and a warp-uniform select).  Chunks that are not interior to a block (the first / last few columns of a
+// parameter tensor, gaps) are filled synchronously element by element as in ChunkStream.
+template <int kThreads, int kDepth, int kCols>
+struct BulkStream {
+  static_assert(kDepth <= 8, "slot metadata is 4 bits per slot in one register");
+  static_assert(kCols % kChunk == 0 && 1024 % kCols == 0, "a slot holds whole 256-column chunks and divides the sample unit");
+  static constexpr int kWarps = kThreads / 32;
+  static constexpr int kSub = kCols / kChunk;
+  static constexpr uint32_t kSlotBytes = kCols * 4 + 16;
+  static constexpr uint32_t kRingBytes = kDepth * kWarps * kSlotBytes;
+  static constexpr uint32_t kSmemBytes = kRingBytes + kDepth * kWarps * 8;  // + one mbarrier per slot
+  BlockCursor<float> cur;
+  uint32_t ring;   // this warp's slot 0; slot r lives kWarps * kSlotBytes further
+  uint32_t bars;   // this warp's mbarrier 0; slot r's is 8 * kWarps bytes further
+  int lane;
+  uint32_t phase = 0;  // bit r: parity the next wait on slot r expects
+  uint32_t meta = 0;   // 4 bits per slot: bit 3 = bulk copy (wait on the mbarrier), bit 2 = element-wise cp.async group,
+                       // bits 0-1 = word shift of a bulk copy
+  __device__ __forceinline__ BulkStream(const BlockTable& t, int64_t ex, uint32_t smem_base)
+      : cur(t, ex), ring(smem_base + (threadIdx.x >> 5) * kSlotBytes),
+        bars(smem_base + kRingBytes + (threadIdx.x >> 5) * 8), lane(threadIdx.x & 31) {
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < kDepth; ++r) mbar_init(bar_addr(r), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ uint32_t slot_addr(int r) const { return ring + r * (kWarps * kSlotBytes); }
+  __device__ __forceinline__ uint32_t bar_addr(int r) const { return bars + r * (kWarps * 8); }
+
+  __device__ __forceinline__ void issue(int64_t p0, int r) {
+    const uint32_t dst = slot_addr(r);
+    if (!(p0 >= cur.lo && p0 < cur.hi)) cur.seek(p0);
+    const bool inside = p0 >= cur.lo && p0 + kCols <= cur.hi;
+    const float* s = cur.base + (p0 - cur.lo);
+    const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(s) >> 2) & 3u;  // words past a 16-byte boundary
+    // the aligned superset reads sh words before and 4 - sh words after the chunk: both must belong to this block's row
+    const bool bulk = inside && (reinterpret_cast<uintptr_t>(s) & 3) == 0 &&
+                      (sh == 0 || (p0 - cur.lo >= 4 && p0 + kCols + 4 <= cur.hi));
+    uint32_t m;
+    if (bulk) {
+      if (lane == 0) {
+        const uint32_t bytes = sh ? kSlotBytes : kCols * 4;
+        mbar_arrive_expect_tx(bar_addr(r), bytes);
+        bulk_copy_global_to_smem(dst, s - sh, bytes, bar_addr(r));
+      }
+      m = 8u | sh;
+    } else {
+      // not interior to a block (a tensor's first / last columns, tensors shorter than a slot, gaps): 4-byte
+      // cp.async per element -- asynchronous like the bulk copy, tracked by a commit group instead of the mbarrier
+#pragma unroll 4
+      for (int i = 0; i < kCols / 32; ++i) {
+        const int64_t c = p0 + i * 32 + lane;
+        if (!(c >= cur.lo && c < cur.hi)) cur.seek(c);
+        const uint32_t d = dst + (i * 32 + lane) * 4;
+        if (c >= cur.lo && c < cur.hi) cp_async_4(d, cur.base + (c - cur.lo));
+        else asm volatile("st.shared.b32 [%0], %1;" ::"r"(d), "r"(0u) : "memory");
+      }
+      cp_async_commit();
+      m = 4u;
+    }
+    meta = (meta & ~(15u << (4 * r))) | (m << (4 * r));
+  }
+
+  // waits until slot r has landed; returns its word shift
+  __device__ __forceinline__ uint32_t acquire(int r) {
+    const uint32_t m = (meta >> (4 * r)) & 15u;
+    if (m & 8u) {
+      mbar_wait(bar_addr(r), (phase >> r) & 1u, 0x57a60000u | static_cast<uint32_t>(r));
+      phase ^= 1u << r;
+    } else if (m & 4u) {
+      cp_async_wait<0>();  // groups complete in order: this slot's and (harmlessly) any later element-wise slot's
+    }
+    __syncwarp();  // element-wise slots: every lane's copies / zero stores are visible
+    return m & 3u;
+  }
+  // this lane's 8 columns (sub * 256 + 8 * lane ...) of the chunk in slot r
+  __device__ __forceinline__ void consume(int r, int sub, uint32_t sh, float (&v)[8]) const {
+    const uint32_t src = slot_addr(r) + sub * (kChunk * 4) + lane * 32;
+    uint32_t q[12];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(src) : "memory");
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]) : "r"(src + 16) : "memory");
+    if (sh == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(q[i]);
+    } else {
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]) : "r"(src + 32) : "memory");
+      if (sh == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(q[i + 1]);
+      } else if (sh == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(q[i + 2]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(q[i + 3]);
+      }
+    }
+  }
+
+  // slots of kCols columns: the warp takes slots s = warp, warp + kWarps, ... of a sequence of n_seq
+  template <typename Start, typename F>
+  __device__ __forceinline__ void for_each_slot(int n_seq, int64_t c_hi, Start&& start, F&& f) {
+    const int w = threadIdx.x >> 5;
+    const int n = n_seq > w ? (n_seq - w + kWarps - 1) / kWarps : 0;
+#pragma unroll
+    for (int i = 0; i < kDepth; ++i)
+      if (i < n) issue(start(w + i * kWarps), i);
+    int r = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t sh = acquire(r);
+      const int64_t p0 = start(w + i * kWarps);
+#pragma unroll
+      for (int sub = 0; sub < kSub; ++sub) {
+        const int64_t p = p0 + sub * kChunk + 8 * lane;
+        if (p < c_hi) {
+          float v[8];
+          consume(r, sub, sh, v);
+          f(p, v);
+        }
+      }
+      __syncwarp();  // every lane has read the slot before it is refilled
+      if (i + kDepth < n) issue(start(w + (i + kDepth) * kWarps), r);
+      r = (r + 1 == kDepth) ? 0 : r + 1;
+    }
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each(int64_t c_lo, int64_t c_hi, F&& f) {
+    const int n_slots = static_cast<int>((c_hi - c_lo + kCols - 1) / kCols);
+    for_each_slot(n_slots, c_hi, [&](int s) { return c_lo + static_cast<int64_t>(s) * kCols; }, f);
+  }
+  // the sample of the scale guess (see ChunkStream): the first 1024 of every 8192 columns
+  template <typename F>
+  __device__ __forceinline__ void for_each_sampled(int64_t c_lo, int64_t c_hi, F&& f) {
+    constexpr int kPer = 1024 / kCols;   // sampled slots per 8192 columns
+    constexpr int kEvery = 8192 / kCols;
+    const int n_slots = static_cast<int>((c_hi - c_lo + kCols - 1) / kCols);
+    const int n_seq = (n_slots / kEvery) * kPer + ((n_slots % kEvery) < kPer ? (n_slots % kEvery) : kPer);
+    for_each_slot(n_seq, c_hi, [&](int s) { return c_lo + static_cast<int64_t>((s / kPer) * kEvery + (s % kPer)) * kCols; }, f);
+  }
+};
+
 template <int kThreads>
 __device__ __forceinline__ float block_max(float v, float* smem) {
   __syncthreads();  // the previous result has been read by everyone
@@ -278,16 +436,16 @@ __device__ __forceinline__ float exp2_int(int s) { return __uint_as_float(static
 // which leaves 4096 registers, 1280 threads and ~15 KB of shared memory per SM.  A staging CTA is sized to fit into
 // exactly that (128 threads, __maxnreg__(32), a 12 KiB cp.async ring), so that staging the next pass on another
 // stream proceeds WHILE a pass is being projected instead of queueing behind it; alone, 16 such CTAs fill an SM.
-template <typename T, bool kF16, int kThreads, int kDepth>
-__device__ __forceinline__ void stage_groups_body(const BlockTable& tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
-                    int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
-  __shared__ float red[kThreads / 32];
-  __shared__ __align__(16) uint8_t ring[ChunkStream<T, kThreads, kDepth>::kRingBytes];
-  const int64_t g = blockIdx.x, b = blockIdx.y;
+// CTA (g, b) of the grid (groups, batch)
+__device__ __forceinline__ int64_t stage_cta_example() { return blockIdx.y; }
+template <typename Stream, bool kF16, int kThreads>
+__device__ __forceinline__ void stage_groups_body(Stream& in, float* red, uint16_t* __restrict__ dst, int64_t m_cap,
+                                                  int64_t row0, int64_t d_pad, float scale, float* __restrict__ inv_scale,
+                                                  int64_t groups_per_row) {
+  const int64_t g = blockIdx.x, b = stage_cta_example();
   const int64_t row = row0 + b;
   const int64_t c_lo = g * kGroupCols;
   const int64_t c_hi = (c_lo + kGroupCols < d_pad) ? c_lo + kGroupCols : d_pad;
-  ChunkStream<T, kThreads, kDepth> in(tab, b, static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
   uint16_t* drow = dst + row * 64;
   float mul = scale;
   float amax = 0.f;
@@ -336,13 +494,27 @@ template <typename T, bool kF16>
 __global__ void __maxnreg__(32)
 stage_groups_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
                     int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
-  stage_groups_body<T, kF16, kNarrowThreads, kNarrowDepth>(tab, dst, m_cap, row0, d_pad, scale, inv_scale, groups_per_row);
+  using Stream = ChunkStream<T, kNarrowThreads, kNarrowDepth>;
+  __shared__ float red[kNarrowThreads / 32];
+  __shared__ __align__(16) uint8_t ring[Stream::kRingBytes];
+  Stream in(tab, stage_cta_example(), static_cast<uint32_t>(__cvta_generic_to_shared(ring)));
+  stage_groups_body<Stream, kF16, kNarrowThreads>(in, red, dst, m_cap, row0, d_pad, scale, inv_scale, groups_per_row);
 }
+
+// wide CTA: fp32 sources through the TMA stream, 2-byte sources through the cp.async stream; dynamic shared memory
+template <typename T>
+struct WideStream { using type = ChunkStream<T, kWideThreads, kWideDepth>; static constexpr uint32_t kSmemBytes = type::kRingBytes; };
+template <>
+struct WideStream<float> { using type = BulkStream<kWideThreads, kWideBulkDepth, kWideBulkCols>; static constexpr uint32_t kSmemBytes = type::kSmemBytes; };
 template <typename T, bool kF16>
 __global__ void __launch_bounds__(kWideThreads)
 stage_groups_wide_kernel(const __grid_constant__ BlockTable tab, uint16_t* __restrict__ dst, int64_t m_cap, int64_t row0,
                          int64_t d_pad, float scale, float* __restrict__ inv_scale, int64_t groups_per_row) {
-  stage_groups_body<T, kF16, kWideThreads, kWideDepth>(tab, dst, m_cap, row0, d_pad, scale, inv_scale, groups_per_row);
+  using Stream = typename WideStream<T>::type;
+  __shared__ float red[kWideThreads / 32];
+  extern __shared__ __align__(16) uint8_t wide_ring[];
+  Stream in(tab, stage_cta_example(), static_cast<uint32_t>(__cvta_generic_to_shared(wide_ring)));
+  stage_groups_body<Stream, kF16, kWideThreads>(in, red, dst, m_cap, row0, d_pad, scale, inv_scale, groups_per_row);
 }
 
 // Timestep accumulator: slab[row0 + b, p] = (accumulate ? slab : 0) + scale * src   (fp32 slab [rows][d_pad]).

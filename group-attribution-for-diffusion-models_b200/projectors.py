@@ -396,8 +396,6 @@ class DeferredProjection:
                 nxt = p._stage(p.stage_rows, self.cur)
                 if nxt.done is not None:  # the pass that last read the other buffer must be over before it is refilled
                     main.wait_event(nxt.done)
-                # ... and the pass just launched owns its SMs before the next staging launches take what is left
-                _lib.check(p._handle.lib.gadm_wait_pass_resident(p._handle.ptr, _lib.stream_ptr(p.device)))
         self.outputs.append(out)
         self.rows = 0
         p._owner = None

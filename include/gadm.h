@@ -109,12 +109,6 @@ int gadm_stage_rows(gadm_handle h, const gadm_block* blocks, int n_blocks, int d
                     void* staged, int stage_dtype, int64_t d_pad, int64_t m_cap, int64_t row0, float* inv_scale,
                     int coresident, void* stream);
 
-/* Makes `stream` wait until every CTA of the projection pass this handle launched last (gadm_project_staged, on any
- * stream) has begun execution -- a launch-completion event, best effort by the driver's definition; no-op before the
- * first pass.  A pipelined caller puts it in front of the staging launches of the next pass: the pass then owns its
- * SMs before the (wide) staging CTAs take what is left, instead of racing them for every SM.  Returns 1 when a wait
- * was enqueued, 0 when there was nothing to wait for (or the driver refused the event attribute), < 0 on error. */
-int gadm_wait_pass_resident(gadm_handle h, void* stream);
 
 /* Timestep accumulator: slab[row0 + b, p] = (accumulate ? slab[row0 + b, p] : 0) + scale * src  for an fp32 slab
  * [slab_rows][d_pad] (32-byte aligned).  Sum K timesteps with scale = 1/K, then stage the slab rows with

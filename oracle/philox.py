@@ -160,7 +160,8 @@ def rademacher_matrix(seed64: int, row0: int, nrows: int, k: int) -> np.ndarray:
 
 def normal_matrix(seed64: int, row0: int, nrows: int, k: int, fmt: str | None = "f16") -> np.ndarray:
     """P[row0:row0+nrows, 0:k] as float32, Box-Muller in float64 rounded to the kernel's operand format: "f16"
-    (the default staging format), "bf16", or None for the unrounded float32 values."""
+    (the default staging format: fp16 numbers that keep 8 significant bits), "bf16", or None for the unrounded
+    float32 values."""
     k0, k1 = _key(seed64)
     p = np.arange(row0, row0 + nrows, dtype=np.uint64)
     j = np.arange(k, dtype=np.uint64)
@@ -177,8 +178,9 @@ def normal_matrix(seed64: int, row0: int, nrows: int, k: int, fmt: str | None = 
     r = np.sqrt(-2.0 * np.log(u1))
     odd = (p & np.uint64(1)).astype(bool)[:, None]
     z = np.where(odd, r * np.sin(theta), r * np.cos(theta)).astype(np.float32)
-    if fmt == "f16":
-        return z.astype(np.float16).astype(np.float32)
+    if fmt == "f16":  # fp16 with an 8-bit significand (philox.cuh::box_muller_pair): + half ulp of the dropped bits, mask
+        bits = z.astype(np.float16).view(np.uint16).astype(np.uint32)
+        return ((bits + 4) & 0xFFF8).astype(np.uint16).view(np.float16).astype(np.float32)
     return round_to_bf16(z) if fmt == "bf16" else z
 
 

@@ -49,7 +49,7 @@ def test_materialize_rademacher_bit_exact():
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("stage_dtype,rel_ulp,same", [("f16", 2.0 ** -10, 0.90), ("bf16", 2.0 ** -7, 0.99)])
+@pytest.mark.parametrize("stage_dtype,rel_ulp,same", [("f16", 2.0 ** -7, 0.98), ("bf16", 2.0 ** -7, 0.99)])
 def test_materialize_normal_matches_box_muller(stage_dtype, rel_ulp, same):
     p = _proj(5000, 512, 7, "normal", stage_dtype=stage_dtype)
     got = p.materialize(11, 2000).cpu().numpy()

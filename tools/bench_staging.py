@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--aligned", action="store_true")
     ap.add_argument("--type", default="normal")
     ap.add_argument("--stage-dtype", default=None)
-    ap.add_argument("--wait-resident", type=int, default=1)
+    ap.add_argument("--blocks", type=int, default=0, help="split the source into this many per-parameter blocks (U-Net like sizes)")
     ap.add_argument("--coresident", type=int, default=None, help="0 wide CTAs, 1 narrow (default: what the API picks)")
     a = ap.parse_args()
     D = (a.D + 3) // 4 * 4 if a.aligned else a.D
@@ -28,7 +28,21 @@ def main():
     rows = 1024 if a.type == "normal" else 512
     p = CudaProjector(D, 4096, 42, ProjectionType(a.type), dev, 32, stage_rows=rows, stage_dtype=a.stage_dtype)
     src = torch.randn(32, D, device=dev) * 1e-3
-    blocks = _as_blocks(src)
+    if a.blocks:  # a mix of tiny (bias / norm) and large (conv / attention weight) tensors, separately allocated
+        import numpy as np
+        rng = np.random.RandomState(0)
+        small = rng.choice([128, 256, 512], size=a.blocks // 2)
+        big_n = a.blocks - len(small)
+        big = rng.dirichlet(np.ones(big_n)) * (D - small.sum())
+        big = np.maximum(1, big.astype(np.int64)); big[-1] += D - small.sum() - big.sum()
+        sizes = np.empty(a.blocks, dtype=np.int64); sizes[0::2] = big[:len(sizes[0::2])]; sizes[1::2] = small[:len(sizes[1::2])]
+        assert sizes.sum() == D and sizes.min() > 0
+        cuts = np.concatenate([[0], np.cumsum(sizes)])
+        parts = [src[:, int(lo):int(hi)].clone() for lo, hi in zip(cuts[:-1], cuts[1:])]
+        del src
+        blocks = _as_blocks(parts)
+    else:
+        blocks = _as_blocks(src)
     s0, s1 = p._stage(rows, 0), p._stage(rows, 1)
     out = torch.empty(rows, 4096, device=dev)
     bytes_per_add = 32 * D * 6
@@ -60,8 +74,6 @@ def main():
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 a0.record(); p._project_rows(s0, rows, 0, out); a1.record()
-            if a.wait_resident:
-                res["wait_enqueued"] = p._handle.lib.gadm_wait_pass_resident(p._handle.ptr, torch.cuda.current_stream().cuda_stream)
             b0.record(); stage_all(s1); b1.record()
         elif order == "queued":  # as in the pipeline: everything is enqueued while an earlier staging still runs
             stage_all(s0)
@@ -70,8 +82,6 @@ def main():
             side.wait_event(ev)
             with torch.cuda.stream(side):
                 a0.record(); p._project_rows(s0, rows, 0, out); a1.record()
-            if a.wait_resident:
-                p._handle.lib.gadm_wait_pass_resident(p._handle.ptr, torch.cuda.current_stream().cuda_stream)
             b0.record(); stage_all(s1); b1.record()
         else:
             b0.record(); stage_all(s1); b1.record()
