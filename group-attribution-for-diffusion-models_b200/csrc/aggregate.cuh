@@ -604,6 +604,49 @@ __global__ void lds_spearman_kernel(const double* __restrict__ pred, const doubl
     rho[job] = has_nan ? __longlong_as_double(0x7ff8000000000000ll) : (sab / sqrt(saa)) / sqrt(sbb);
 }
 
+// Small evaluation sets (m <= kLdsCountRows): ranks by counting "how many are smaller / equal" -- m^2 / 32 steps of
+// broadcast reads per lane, which beats the sorting network's shared-memory round trips and warp barriers up to
+// m ~ 128 (measured at m = 100, K = 2e5: 1.39 ms counting vs 1.68 ms sorting; at m = 1024 the sort is ~7x ahead).
+// Same exact sums, same result bit for bit.
+constexpr int kLdsCountRows = 128;
+__global__ void lds_spearman_count_kernel(const double* __restrict__ pred, const double* __restrict__ y, int64_t m, int64_t K,
+                                    const int32_t* __restrict__ idx, int64_t R, int64_t mr, double* __restrict__ rho) {
+  extern __shared__ __align__(16) unsigned char lds_smem_raw[];
+  double* lds_smem = reinterpret_cast<double*>(lds_smem_raw);  // [warps][2][mr]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t job = static_cast<int64_t>(blockIdx.x) * nw + warp;
+  if (job >= R * K) return;
+  const int64_t e = job / K, k = job % K;
+  double* sa = lds_smem + static_cast<size_t>(warp) * 2 * mr;
+  double* sb = sa + mr;
+  for (int64_t r = lane; r < mr; r += 32) {
+    const int64_t row = idx ? idx[e * mr + r] : r;
+    sa[r] = pred[row * K + k];
+    sb[r] = y[row * K + k];
+  }
+  __syncwarp();
+  bool has_nan = false;
+  for (int64_t r = lane; r < mr; r += 32) has_nan |= (sa[r] != sa[r]) || (sb[r] != sb[r]);
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  const double mean = 0.5 * (static_cast<double>(mr) + 1.0);
+  double sab = 0.0, saa = 0.0, sbb = 0.0;
+  for (int64_t r = lane; r < mr; r += 32) {
+    const double a = sa[r], b = sb[r];
+    int la = 0, ea = 0, lb = 0, eb = 0;
+    for (int64_t t = 0; t < mr; ++t) {
+      const double at = sa[t], bt = sb[t];
+      la += (at < a); ea += (at == a);
+      lb += (bt < b); eb += (bt == b);
+    }
+    const double ra = la + 0.5 * (ea + 1) - mean;  // average rank (1-based) minus the mean rank
+    const double rb = lb + 0.5 * (eb + 1) - mean;
+    sab += ra * rb; saa += ra * ra; sbb += rb * rb;
+  }
+  sab = warp_sum(sab); saa = warp_sum(saa); sbb = warp_sum(sbb);
+  if (lane == 0)  // corrcoef's two-step normalisation; 0/0 -> NaN
+    rho[job] = has_nan ? __longlong_as_double(0x7ff8000000000000ll) : (sab / sqrt(saa)) / sqrt(sbb);
+}
+
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h, pairwise_sum_@TYPE@), restated over a stream of
 // values consumed in order: fewer than 8 -> running sum from -0; up to 128 -> eight strided accumulators combined as
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus the remainder in order; more -> split at n/2 rounded down to a multiple of

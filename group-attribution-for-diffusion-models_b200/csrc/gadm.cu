@@ -38,7 +38,8 @@ struct gadm_ctx {
   uint32_t attr_stage_wide = 0; // same, dynamic shared-memory opt-in of the wide staging kernels
   uint32_t attr_stage = 0;      // bit per staging-kernel instantiation whose carveout preference has been set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start / panel / rest / end
+  cudaStream_t hp_stream2 = nullptr; // second one: the next-block-column updates of the look-ahead
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // start / panel / col / end / rest (even, odd step)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
 
@@ -420,6 +421,7 @@ int gadm_create(gadm_handle* out, int device) {
 int gadm_destroy(gadm_handle h) {
   if (h && h->scratch) cudaFree(h->scratch);
   if (h && h->hp_stream) cudaStreamDestroy(h->hp_stream);
+  if (h && h->hp_stream2) cudaStreamDestroy(h->hp_stream2);
   if (h) for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return GADM_OK;
@@ -724,12 +726,19 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
     h->attr_potrf = true;
   }
   if (info) GADM_CUDA(cudaMemsetAsync(info, 0, sizeof(int), as_stream(stream)));
-  // Look-ahead: the critical path (diagonal block -> panel -> update of the NEXT block column) runs on a
-  // high-priority stream of the handle, the rest of the trailing update on the caller's stream, so that
-  // potrf(b+1) + panel(b+1) overlap with the bulk of the trailing update of step b.  Ordering rules:
-  //   rest(b)  after panel(b)                 (reads the panel)            -- event ev_panel
-  //   next(b)  after rest(b-1)                (both update block column b+1) -- event ev_rest
-  // Events are re-recorded every step: cudaStreamWaitEvent captures the record that is current when it is called.
+  // Look-ahead.  Step s of the right-looking factorisation is split into
+  //   potrf(s)  diagonal block (+ its last rank-128 update A_ss -= L[s,s-1] L[s,s-1]^T, fused into the kernel)
+  //   panel(s)  L[i,s] = A[i,s] L_ss^-T                        for i > s
+  //   col(s)    A[i,s+1] -= L[i,s] L[s+1,s]^T                   for i >= s+2   (block column s+1 below its diagonal block)
+  //   rest(s)   A[i,l]   -= L[i,s] L[l,s]^T                     for l >= s+2, i >= l (lower tiles)
+  // potrf and panel run on a high-priority stream of the handle (the critical path: 46 + 16 us per step), col on a
+  // second one and rest on the caller's stream, so that the small col(s) product (29 us, latency-bound) neither sits
+  // on the critical path nor in front of rest(s).  Ordering (events are re-recorded every step; cudaStreamWaitEvent
+  // captures the record that is current when it is called):
+  //   col(s), rest(s)  after panel(s)                                               -- ev[1]
+  //   panel(s+1)       after col(s)      (col(s) writes what it reads)              -- ev[2]
+  //   potrf(s+2)       after rest(s)     (rest(s) writes A[s+2,s+2])                -- ev[4 + s % 2]
+  //   col(s+1)         after rest(s)     (both write block column s+2)              -- ev[4 + s % 2]
   static const bool lookahead = [] { const char* e = getenv("GADM_CHOL_LOOKAHEAD"); return !(e && atoi(e) == 0); }();
   cudaStream_t user = as_stream(stream);
   cudaStream_t crit = user;
@@ -738,23 +747,33 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
       int least = 0, greatest = 0;
       GADM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
       GADM_CUDA(cudaStreamCreateWithPriority(&h->hp_stream, cudaStreamNonBlocking, greatest));
+      GADM_CUDA(cudaStreamCreateWithPriority(&h->hp_stream2, cudaStreamNonBlocking, greatest));
       for (auto& e : h->ev) GADM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     crit = h->hp_stream;
     GADM_CUDA(cudaEventRecord(h->ev[0], user));
     GADM_CUDA(cudaStreamWaitEvent(crit, h->ev[0], 0));
+    GADM_CUDA(cudaStreamWaitEvent(h->hp_stream2, h->ev[0], 0));
   }
   const bool split = crit != user;
-  bool rest_pending = false;
+  cudaStream_t cols = split ? h->hp_stream2 : user;
+  bool any_col = false;
+  bool col_pending = false;      // col(b-1) recorded in ev[2], not yet waited for by panel(b)
+  bool rest_pending = false;     // rest(b-2) recorded in ev[4], not yet waited for by potrf(b)
+  bool rest_prev = false;        // rest(b-1) recorded in ev[5]: becomes rest_pending at the next step
   for (int64_t b = 0; b < nblk; ++b) {
     const int64_t j0 = b * NB;
     const int nb = (int)((k - j0) < NB ? (k - j0) : NB);
+    if (split && rest_pending) GADM_CUDA(cudaStreamWaitEvent(crit, h->ev[4 + (b & 1)], 0));  // rest(b-2) wrote A_bb
+    const float* prev = (split && b > 0) ? a + j0 * ld + (j0 - NB) : nullptr;
     potrf<<<1, gadm::gemm::kPotrfThreads, gadm::gemm::kPotrfSmem, crit>>>(a + j0 * ld + j0, ld, nb, linv + b * NB * NB,
-                                                                         linv_t + b * NB * NB, info, (int)b);
+                                                                         linv_t + b * NB * NB, info, (int)b, prev);
     GADM_LAUNCHED(h);
     const int64_t rem = k - (j0 + nb);
     if (rem > 0) {
       float* panel = a + (j0 + nb) * ld + j0;
+      if (split && col_pending) GADM_CUDA(cudaStreamWaitEvent(crit, h->ev[2], 0));  // col(b-1) updated this panel's input
+      col_pending = false;
       // panel <- panel * L_jj^-T   (in place: one column tile, each CTA owns its rows)
       GADM_TRY(gadm_gemm_tn(h, panel, ld, linv + b * NB * NB, NB, panel, ld, rem, nb, nb, 1.f, 0.f, 0.f, 0, crit));
       float* trail = a + (j0 + nb) * ld + (j0 + nb);
@@ -764,22 +783,29 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
         continue;
       }
       GADM_CUDA(cudaEventRecord(h->ev[1], crit));  // panel(b) done
-      const int64_t nn = rem < NB ? rem : NB;       // width of the next block column
-      if (rest_pending) GADM_CUDA(cudaStreamWaitEvent(crit, h->ev[2], 0));  // rest(b-1) also wrote block column b+1
-      // next(b): block column b+1 (all remaining rows) -= panel * panel[0:nn]^T
-      GADM_TRY(gadm_gemm_tn(h, panel, ld, panel, ld, trail, ld, rem, nn, nb, -1.f, 1.f, 0.f, 0, crit));
-      rest_pending = false;
+      GADM_CUDA(cudaStreamWaitEvent(user, h->ev[1], 0));
+      const int64_t nn = rem < NB ? rem : NB;  // width of the next block column
+      const bool had_rest = rest_prev;         // rest(b-1) exists (recorded in ev[4 + (b-1) % 2])
+      rest_pending = rest_prev;                // what potrf(b+1) has to wait for is rest(b-1)
+      rest_prev = false;
       if (rem > nn) {
-        // rest(b): the lower triangle right of that column, on the caller's stream
-        GADM_CUDA(cudaStreamWaitEvent(user, h->ev[1], 0));
-        float* p2 = panel + nn * ld;
+        float* p2 = panel + nn * ld;  // panel rows from block b+2 on
+        // col(b): block column b+1 below its diagonal block -= panel[b+2..] * panel[b+1]^T
+        GADM_CUDA(cudaStreamWaitEvent(cols, h->ev[1], 0));
+        if (had_rest) GADM_CUDA(cudaStreamWaitEvent(cols, h->ev[4 + ((b - 1) & 1)], 0));  // rest(b-1) wrote these blocks too
+        GADM_TRY(gadm_gemm_tn(h, p2, ld, panel, ld, trail + nn * ld, ld, rem - nn, nn, nb, -1.f, 1.f, 0.f, 0, cols));
+        GADM_CUDA(cudaEventRecord(h->ev[2], cols));
+        col_pending = true;
+        any_col = true;
+        // rest(b): the lower triangle right of that column
         GADM_TRY(gadm_gemm_tn(h, p2, ld, p2, ld, trail + nn * ld + nn, ld, rem - nn, rem - nn, nb, -1.f, 1.f, 0.f, 1, user));
-        GADM_CUDA(cudaEventRecord(h->ev[2], user));
-        rest_pending = true;
+        GADM_CUDA(cudaEventRecord(h->ev[4 + (b & 1)], user));  // waited for by potrf(b+2): same parity
+        rest_prev = true;
       }
     }
   }
   if (split) {  // join: everything after this call on the caller's stream sees the finished factor
+    if (any_col) GADM_CUDA(cudaStreamWaitEvent(user, h->ev[2], 0));  // the last col(b) (panel(b+1) already waited for it)
     GADM_CUDA(cudaEventRecord(h->ev[3], crit));
     GADM_CUDA(cudaStreamWaitEvent(user, h->ev[3], 0));
   }
@@ -1179,13 +1205,19 @@ int gadm_lds_spearman(gadm_handle h, const double* pred, const double* y, int64_
   GADM_REQUIRE(rows_per_eval > 0 && rows_per_eval <= gadm::agg::kLdsMaxRows, "rows_per_eval %lld out of range (1..%d)",
                (long long)rows_per_eval, gadm::agg::kLdsMaxRows);
   DeviceGuard guard(h->device);
-  const size_t per_warp = gadm::agg::lds_warp_smem_bytes(rows_per_eval);  // <= 14 KiB
+  const bool count = rows_per_eval <= gadm::agg::kLdsCountRows;  // small sets: counting ranks; larger: sorting network
+  const size_t per_warp = count ? (size_t)2 * rows_per_eval * sizeof(double) : gadm::agg::lds_warp_smem_bytes(rows_per_eval);
   int warps = 8;
   while (warps > 1 && (size_t)warps * per_warp > 48 * 1024) warps /= 2;
   const size_t smem = (size_t)warps * per_warp;
   const int64_t jobs = n_eval * k;
-  gadm::agg::lds_spearman_kernel<<<(unsigned)((jobs + warps - 1) / warps), warps * 32, smem, as_stream(stream)>>>(
-      pred, y, m, k, idx, n_eval, rows_per_eval, rho);
+  const unsigned grid = (unsigned)((jobs + warps - 1) / warps);
+  if (count)
+    gadm::agg::lds_spearman_count_kernel<<<grid, warps * 32, smem, as_stream(stream)>>>(pred, y, m, k, idx, n_eval,
+                                                                                        rows_per_eval, rho);
+  else
+    gadm::agg::lds_spearman_kernel<<<grid, warps * 32, smem, as_stream(stream)>>>(pred, y, m, k, idx, n_eval,
+                                                                                  rows_per_eval, rho);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

@@ -562,7 +562,7 @@ __device__ __forceinline__ void smem_tile_mm(const float* A, int lda, const floa
 #endif
 __global__ void __launch_bounds__(kPotrfThreads, 1)
 potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__ linv, float* __restrict__ linv_t,
-                  int* __restrict__ info, int block_index) {
+                  int* __restrict__ info, int block_index, const float* __restrict__ prev) {
   extern __shared__ float potrf_smem[];
   float* L = potrf_smem;                        // [128][kPotrfLd]: the block, then its factor
   float* X = potrf_smem + kPotrfNb * kPotrfLd;  // inverse of the factor
@@ -579,9 +579,18 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
   for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) {
     const int r = idx / kPotrfNb, c = idx % kPotrfNb;
     L[r * kPotrfLd + c] = (r < nb && c < nb) ? A[static_cast<int64_t>(r) * ld + c] : ((r == c) ? 1.f : 0.f);
-    X[r * kPotrfLd + c] = 0.f;
+    // prev: this block row of the previous block column of the factor, L[b, b-1] (nb x 128, pitch ld).  The blocked
+    // Cholesky leaves the last rank-128 update of this diagonal block to this kernel (A_bb -= L[b,b-1] L[b,b-1]^T):
+    // as a separate GEMM launch it sat on the critical path between panel(b-1) and this kernel (29 us per step).
+    X[r * kPotrfLd + c] = (prev != nullptr && r < nb) ? prev[static_cast<int64_t>(r) * ld + c] : 0.f;
   }
   __syncthreads();
+  if (prev != nullptr) {
+    smem_tile_mm<true, true, true>(X, kPotrfLd, X, kPotrfLd, L, kPotrfLd, kPotrfNb, kPotrfNb, kPotrfNb, -1.f);
+    __syncthreads();
+    for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) X[(idx / kPotrfNb) * kPotrfLd + idx % kPotrfNb] = 0.f;
+    __syncthreads();
+  }
 
   POTRF_T(1);
   for (int jb = 0; jb < kPotrfNb / kPotrfSb; ++jb) {

@@ -6,10 +6,6 @@
 # runs alone, so all clusters are resident and the lockstep stays on.
 set -u
 mkdir -p gpurun_out
-python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -c 400 gpurun_out/r02_bench_n1.err
-python bench.py --steps 20 --warmup 5 --no-extra > gpurun_out/r02_bench_n1_steps20.json 2>> gpurun_out/r02_bench_n1.err
-python bench.py --proj-type rademacher --steps 10 --warmup 3 --no-extra --no-e2e --no-cpu-baseline > gpurun_out/r02_bench_n1_rademacher.json 2>> gpurun_out/r02_bench_n1.err
-GADM_STAGE_DTYPE=bf16 python bench.py --steps 10 --warmup 3 --no-extra --no-e2e --no-cpu-baseline > gpurun_out/r02_bench_n1_bf16.json 2>> gpurun_out/r02_bench_n1.err
 export GADM_WATCHDOG_SEC=0 GADM_PROJ_COOPERATIVE=0 GADM_PROJ_UNSAFE_LOCKSTEP=1
 CMD="python bench.py --steps 2 --warmup 3 --no-extra --no-e2e --no-cpu-baseline"
 timeout 400 $CMD > gpurun_out/r02_bench_plain.json 2> gpurun_out/r02_bench_plain.err && \
@@ -31,11 +27,15 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^pr
 tail -n 2 gpurun_out/ncu_normal.log
 CMD="python tools/bench_staging.py --D 4468288"
 timeout 200 $CMD > gpurun_out/plain_staging.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:stage_groups_kernel" -s 4 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:stage_groups_wide_kernel" -s 4 -c 1 \
     -o gpurun_out/r02_prof_stage $CMD > gpurun_out/ncu_stage.log 2>&1
 tail -n 2 gpurun_out/ncu_stage.log
 MS="dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct"
 CMD="python tools/bench_staging.py"
-timeout 300 ncu --metrics $MS --clock-control none -k "regex:stage_groups_kernel" -s 40 -c 4 --csv \
+timeout 300 ncu --metrics $MS --clock-control none -k "regex:stage_groups_wide_kernel" -s 40 -c 4 --csv \
     --log-file gpurun_out/r02_traffic_stage.csv $CMD > gpurun_out/ncu_stage2.log 2>&1
 tail -n 6 gpurun_out/r02_traffic_stage.csv | cut -d, -f5,13- | cut -c1-200
+# Rademacher path: narrow (co-resident) staging kernel
+timeout 300 ncu --metrics $MS --clock-control none -k "regex:stage_groups_kernel" -s 40 -c 4 --csv \
+    --log-file gpurun_out/r02_traffic_stage_narrow.csv python tools/bench_staging.py --type rademacher > gpurun_out/ncu_stage3.log 2>&1
+tail -n 6 gpurun_out/r02_traffic_stage_narrow.csv | cut -d, -f5,13- | cut -c1-200
