@@ -37,6 +37,8 @@ _SIGNATURES = {
                                C.c_float, C.c_int, c_vp]),
     "gadm_gemm_tn_batched": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64,
                                        c_i64, C.c_float, C.c_float, C.c_float, C.c_int, c_vp]),
+    "gadm_cholesky_solve_vec_workspace_bytes": (c_i64, [c_i64]),
+    "gadm_cholesky_solve_vec": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gadm_transpose": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gadm_cholesky_workspace_bytes": (c_i64, [c_i64]),
     "gadm_cholesky": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, C.POINTER(C.c_int), c_vp]),

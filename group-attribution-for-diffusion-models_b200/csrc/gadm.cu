@@ -25,6 +25,7 @@
 #include "ridge.cuh"
 #include "datamodel.cuh"
 #include "gemm.cuh"
+#include "trsv.cuh"
 
 struct gadm_ctx {
   int device = 0;
@@ -35,6 +36,7 @@ struct gadm_ctx {
                                 // flight on different streams of one device never share a barrier
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
   bool attr_gemm = false, attr_gemm_ts = false, attr_potrf = false;  // per-device kernel attributes already set
+  bool attr_trsv = false;
   uint32_t attr_stage_wide = 0; // same, dynamic shared-memory opt-in of the wide staging kernels
   uint32_t attr_stage = 0;      // bit per staging-kernel instantiation whose carveout preference has been set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
@@ -812,6 +814,47 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
   return GADM_OK;
 }
 
+// x = (L L^T)^-1 b for one right-hand side, through the factor and the diagonal-block inverses gadm_cholesky left
+// (csrc/trsv.cuh: one cooperative launch of k / 128 CTAs with point-to-point signalling).
+int64_t gadm_cholesky_solve_vec_workspace_bytes(int64_t k) {
+  const int64_t nblk = (k + 127) / 128;
+  return 1024 + 2 * nblk * nblk * 128 * (int64_t)sizeof(double);  // 2 x nblk arrival counters (nblk <= 64), then the partial products
+}
+
+int gadm_cholesky_solve_vec(gadm_handle h, const float* l, int64_t ld, const void* blocks, int64_t k, const float* b,
+                            float* x, void* workspace, int64_t workspace_bytes, void* stream) {
+  GADM_REQUIRE(h && l && blocks && b && x && workspace && k > 0, "bad argument");
+  GADM_REQUIRE(k % 128 == 0 && ld >= k && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(l) & 15) == 0,
+               "gadm_cholesky_solve_vec needs k %% 128 == 0, ld %% 4 == 0 and a 16-byte aligned factor (k = %lld, ld = %lld)",
+               (long long)k, (long long)ld);
+  const int nblk = (int)(k / 128);
+  GADM_REQUIRE(nblk <= h->num_sms && nblk <= 64, "k = %lld: the %d CTAs of the substitution must be co-resident (and <= 64)",
+               (long long)k, nblk);
+  if (workspace_bytes < gadm_cholesky_solve_vec_workspace_bytes(k))
+    return fail(GADM_ERR_WORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes,
+                (long long)gadm_cholesky_solve_vec_workspace_bytes(k));
+  GADM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = as_stream(stream);
+  auto kernel = gadm::trsv::chol_solve_vec_kernel;
+  if (!h->attr_trsv) {
+    GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::trsv::kSmemBytes));
+    h->attr_trsv = true;
+  }
+  uint32_t* count = reinterpret_cast<uint32_t*>(workspace);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 1024);
+  GADM_CUDA(cudaMemsetAsync(count, 0, 1024, st));
+  const float* linv = reinterpret_cast<const float*>(blocks);
+  const float* linv_t = linv + (int64_t)nblk * 128 * 128;
+  int nb = nblk;
+  void* args[] = {(void*)&l, (void*)&ld, (void*)&nb, (void*)&linv, (void*)&linv_t, (void*)&b, (void*)&x, (void*)&partial,
+                  (void*)&count};
+  GADM_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)nblk), dim3(gadm::trsv::kThreads), args,
+                                        (size_t)gadm::trsv::kSmemBytes, st));
+  GADM_LAUNCHED(h);
+  return GADM_OK;
+}
+
 // L^-1 (and its transpose) of the factor left by gadm_cholesky, by recursive doubling over the diagonal blocks:
 // for two adjacent diagonal groups with inverses X11, X22 and the factor's off-diagonal block L21,
 //   X21 = -X22 (L21 X11)   -- three GEMMs per merge (T^T = X11^T L21^T, X21 = -X22 T, X21^T = -T^T X22^T).
@@ -948,8 +991,8 @@ int gadm_col_mean_scaled(gadm_handle h, const float* s, int64_t t, int64_t n, in
                          const float* col_scale, float* out, void* stream) {
   GADM_REQUIRE(h && s && out && t > 0 && n > 0 && ld >= n, "bad argument");
   DeviceGuard guard(h->device);
-  gadm::gemm::col_mean_scaled_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(s, t, n, ld, row_scale,
-                                                                                               col_scale, out);
+  gadm::gemm::col_mean_scaled_kernel<<<(unsigned)((n + 31) / 32), dim3(32, gadm::gemm::kColMeanLanes), 0, as_stream(stream)>>>(
+      s, t, n, ld, row_scale, col_scale, out);
   GADM_LAUNCHED(h);
   return GADM_OK;
 }

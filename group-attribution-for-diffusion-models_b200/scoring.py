@@ -15,6 +15,7 @@ row: one all-reduce of the Gram matrix, identical factorisation on every rank, l
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import Iterable, Sequence
 
@@ -81,11 +82,12 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, a
     return out
 
 
-def transpose(x: torch.Tensor) -> torch.Tensor:
-    """[R, C] -> [C, R] with a pitch that is a multiple of 4 floats (TMA-loadable)."""
+def transpose(x: torch.Tensor, min_ld: int = 0) -> torch.Tensor:
+    """[R, C] -> [C, R] with a pitch that is a multiple of 4 floats (TMA-loadable) and at least ``min_ld``; the pad
+    columns are zero."""
     x = _check_cuda_f32(x, "x")
     r, c = x.shape
-    ld = -(-r // 4) * 4
+    ld = -(-max(r, min_ld) // 4) * 4
     out = torch.empty(c, ld, dtype=_f32, device=x.device)
     if ld != r:
         out[:, r:].zero_()  # only the <= 3 pad columns (they enter the contraction of the Gram GEMM); a full zero fill
@@ -127,6 +129,69 @@ def scale_rows_cols_(s: torch.Tensor, row_scale: torch.Tensor | None = None, col
                                              col_scale.data_ptr() if col_scale is not None else None,
                                              _lib.stream_ptr(s.device)))
     return s
+
+
+def _gram_plan(n: int, k: int, device) -> tuple[int, int, int] | None:
+    """Wave balance of the lower-triangle Gram GEMM (one 128 x 128 tile per CTA, one CTA per SM).  The k / 128 row tiles
+    give nt (nt + 1) / 2 output tiles: 528 at k = 4096, i.e. 3.57 waves on 148 SMs -- the fourth wave runs 57 % empty.
+    Returns (r0, parts, kc): row tiles [0, r0) fill whole waves with full-contraction CTAs, the remaining row tiles are
+    computed as ``parts`` contraction slices of kc columns each (short CTAs that pack into the last wave) and summed;
+    None when that does not pay."""
+    nt = -(-k // 128)
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    tiles = nt * (nt + 1) // 2
+    full = tiles // sms
+    if k % 128 or full < 1 or n < 8192:
+        return None
+    r0 = int((math.isqrt(8 * full * sms + 1) - 1) // 2)
+    if r0 >= nt or r0 < 1:
+        return None
+    balanced = (r0 * (r0 + 1) // 2 + (nt - r0) * nt) / sms
+    if balanced > 0.95 * -(-tiles // sms):
+        return None
+    parts = min(8, n // 2048)
+    kc = -(-n // parts // 32) * 32
+    return r0, parts, kc
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def gram_lower(phi: torch.Tensor, diag_add: float = 0.0) -> torch.Tensor:
+    """phi [N, k] -> Phi^T Phi + diag_add * I  [k, k], lower block triangle valid (what gadm_cholesky reads);
+    traks.py:149-151.  Transposes (contraction over examples becomes K-major) and runs the 3xTF32 GEMM, wave-balanced
+    per ``_gram_plan``."""
+    phi = _check_cuda_f32(phi, "phi")
+    n, k = phi.shape
+    plan = _gram_plan(n, k, phi.device)
+    if plan is None:
+        phi_t = transpose(phi)
+        return gemm_tn(phi_t, phi_t, lower_only=True, diag_add=diag_add)
+    r0, parts, kc = plan
+    m0 = r0 * 128
+    phi_t = transpose(phi, min_ld=parts * kc)
+    ld = phi_t.stride(0)
+    gram = torch.zeros(k, k, dtype=_f32, device=phi.device)
+    partial = torch.empty(parts, k - m0, k, dtype=_f32, device=phi.device)
+    h = _h(phi)
+    main = torch.cuda.current_stream(phi.device)
+    side = _SIDE_STREAMS.get(phi.device)
+    if side is None:
+        side = _SIDE_STREAMS[phi.device] = torch.cuda.Stream(device=phi.device, priority=-1)
+    side.wait_stream(main)
+    with torch.cuda.device(phi.device):
+        with torch.cuda.stream(side):  # the short CTAs first and with priority: they fill the gaps of the main grid's waves
+            _lib.check(h.lib.gadm_gemm_tn_batched(h.ptr, phi_t[m0:].data_ptr(), ld, kc, phi_t.data_ptr(), ld, kc,
+                                                 partial.data_ptr(), k, (k - m0) * k, k - m0, k, kc, parts, 1.0, 0.0, 0.0, 0,
+                                                 _lib.stream_ptr(phi.device)))
+            torch.sum(partial, dim=0, out=gram[m0:])
+            if diag_add:
+                gram.diagonal()[m0:].add_(diag_add)
+        gemm_tn(phi_t[:m0], phi_t[:m0], out=gram[:m0, :m0], lower_only=True, diag_add=diag_add)
+    main.wait_stream(side)
+    for t in (phi_t, partial, gram):
+        t.record_stream(side)
+    return gram
 
 
 LOCAL = "local"  # pass as ``group`` to score this process's rows alone even when torch.distributed is initialised
@@ -181,8 +246,8 @@ class TrakScorer:
         self.k = None          # size of the factored system (k primal, N_total dual)
         self.L = None
         self.U = None
-        self.X = None          # L^-1 (lower) and
-        self.Xt = None         # L^-T (upper), explicit
+        self._X = None         # L^-1 (lower) and
+        self._Xt = None        # L^-T (upper), explicit -- built on first use (``X`` / ``Xt``)
         self.blocks = None
         self.info = None
         self.dual = False
@@ -218,8 +283,7 @@ class TrakScorer:
             else:
                 gram = gemm_tn(self.phi_all, self.phi_all, lower_only=True, diag_add=self.lam)  # A = Phi Phi^T + lam I
             return self.factor_(gram)
-        phi_t = transpose(phi)  # [k, N]: contraction over examples becomes K-major
-        gram = gemm_tn(phi_t, phi_t, lower_only=True, diag_add=self.lam / world)
+        gram = gram_lower(phi, self.lam / world)  # transposes: the contraction over examples becomes K-major
         if dist is not None:
             allreduce_sum_(gram, self.group)  # one NCCL all-reduce over NVLink (sum of per-rank Grams)
         return self.factor_(gram)
@@ -248,9 +312,36 @@ class TrakScorer:
         return self.factor_(gram)
 
     def factor_(self, gram: torch.Tensor) -> "TrakScorer":
-        """In-place Cholesky of an already regularised symmetric matrix (lower triangle is read), then the explicit
-        triangular inverse."""
-        return self._cholesky_(gram)._tri_inverse_()
+        """In-place Cholesky of an already regularised symmetric matrix (lower triangle is read).  The explicit
+        triangular inverse that the many-row solves use is built on first use: the mean-first score paths solve a
+        single row and go through ``gadm_cholesky_solve_vec`` instead."""
+        self._X = self._Xt = None
+        return self._cholesky_(gram)
+
+    @property
+    def X(self) -> torch.Tensor:
+        if self._X is None:
+            self._tri_inverse_()
+        return self._X
+
+    @property
+    def Xt(self) -> torch.Tensor:
+        if self._Xt is None:
+            self._tri_inverse_()
+        return self._Xt
+
+    def _solve_vec(self, row: torch.Tensor) -> torch.Tensor:
+        """One row times (factored matrix)^-1 by forward / backward substitution in one cooperative launch."""
+        gram = self.L
+        h = _h(gram)
+        b = row.reshape(-1).contiguous().float()
+        x = torch.empty(self.k, dtype=_f32, device=gram.device)
+        ws = torch.empty(int(h.lib.gadm_cholesky_solve_vec_workspace_bytes(self.k)), dtype=torch.uint8, device=gram.device)
+        with torch.cuda.device(gram.device):
+            _lib.check(h.lib.gadm_cholesky_solve_vec(h.ptr, gram.data_ptr(), gram.stride(0), self.blocks.data_ptr(), self.k,
+                                                    b.data_ptr(), x.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    _lib.stream_ptr(gram.device)))
+        return x
 
     def _cholesky_(self, gram: torch.Tensor) -> "TrakScorer":
         self.k = gram.shape[0]
@@ -274,12 +365,12 @@ class TrakScorer:
         gram = self.L
         h = _h(gram)
         ld = -(-self.k // 4) * 4
-        self.X = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
-        self.Xt = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
+        self._X = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
+        self._Xt = torch.empty(self.k, ld, dtype=_f32, device=gram.device)[:, :self.k]
         ws = torch.empty(int(h.lib.gadm_tri_inverse_workspace_bytes(self.k)), dtype=torch.uint8, device=gram.device)
         with torch.cuda.device(gram.device):
             _lib.check(h.lib.gadm_tri_inverse(h.ptr, gram.data_ptr(), gram.stride(0), self.blocks.data_ptr(), self.k,
-                                              self.X.data_ptr(), self.X.stride(0), self.Xt.data_ptr(), self.Xt.stride(0),
+                                              self._X.data_ptr(), self._X.stride(0), self._Xt.data_ptr(), self._Xt.stride(0),
                                               ws.data_ptr(), ws.numel(), _lib.stream_ptr(gram.device)))
         return self
 
@@ -307,6 +398,15 @@ class TrakScorer:
         y = _check_cuda_f32(rows, "rows")
         if y.shape[1] != self.k:
             raise ValueError(f"rows have {y.shape[1]} columns, the factored system has {self.k}")
+        if y.shape[0] <= 2:
+            # the mean-first score paths solve ONE row.  Without the explicit inverse (not built yet): substitution
+            # through the factor in one cooperative launch; with it: two matrix-vector products (HBM-bound, fp64
+            # accumulation, ~20 us each at k = 4096) instead of two GEMMs that run a single 128-row tile through the
+            # whole contraction (84 us each)
+            if (self._X is None and self.k % 128 == 0 and self.k <= 8192 and self.L.stride(0) % 4 == 0
+                    and self.L.data_ptr() % 16 == 0):
+                return torch.stack([self._solve_vec(y[i]) for i in range(y.shape[0])])
+            return torch.stack([matvec_rows(self.Xt, matvec_rows(self.X, y[i])) for i in range(y.shape[0])])
         return gemm_tn(gemm_tn(y, self.X, b_tri="lower"), self.Xt, b_tri="upper")
 
     def solve_rows_blocked(self, rows: torch.Tensor) -> torch.Tensor:

@@ -178,6 +178,14 @@ int gadm_transpose(gadm_handle h, const float* in, int64_t rows, int64_t cols, i
 int64_t gadm_cholesky_workspace_bytes(int64_t k);
 int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, int64_t blocks_bytes, int* info,
                   void* stream);
+/* x = (L L^T)^-1 b for ONE right-hand side b [k] through the factor of gadm_cholesky and its `blocks` workspace: forward
+ * and backward substitution over the 128-blocks in one cooperative launch (k / 128 CTAs, point-to-point signalling).
+ * What the mean-first TRAK score needs (traks.py:152-157: mean_t(gen_t) K^-1 Phi^T) without forming the triangular
+ * inverse.  Requires k % 128 == 0, k <= 8192, ld % 4 == 0, l 16-byte aligned; workspace of
+ * gadm_cholesky_solve_vec_workspace_bytes(k), 16-byte aligned. */
+int64_t gadm_cholesky_solve_vec_workspace_bytes(int64_t k);
+int gadm_cholesky_solve_vec(gadm_handle h, const float* l, int64_t ld, const void* blocks, int64_t k, const float* b,
+                            float* x, void* workspace, int64_t workspace_bytes, void* stream);
 /* x = L^-1 (lower) and xt = L^-T (upper), both [k, k], of the factor left by gadm_cholesky (recursive doubling over
  * the 128-wide diagonal blocks whose inverses are in `blocks`).  rows @ K^-1 is then two GEMMs:
  * gadm_gemm_tn(rows, x) = rows L^-T, gadm_gemm_tn(., xt) = (.) L^-1 -- what torch.inverse + matmul do in

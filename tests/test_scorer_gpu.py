@@ -96,6 +96,34 @@ def test_cholesky_and_solve(k, N):
     assert float((kinv.double() @ Kd - eye).abs().max()) < 1e-3
 
 
+@pytest.mark.parametrize("k,N", [(128, 500), (256, 900), (1024, 3000), (4096, 6000), (8192, 9000)])
+def test_single_row_solve_by_cooperative_substitution(k, N):
+    """gadm_cholesky_solve_vec (one cooperative launch: forward + backward substitution over the 128-blocks with
+    point-to-point signalling) against an fp64 solve and against the explicit-inverse path; it is what the mean-first
+    TRAK score uses, so the triangular inverse is not built for it (traks.py:152-157)."""
+    import gadm_b200 as G
+
+    phi = _rand((N, k), 9)
+    sc = G.TrakScorer(0.5).fit(phi)
+    sc.check()
+    assert sc._X is None                      # fit() no longer builds L^-1 eagerly
+    row = _rand((1, k), 10)
+    Kd = phi.double().T @ phi.double() + 0.5 * torch.eye(k, device=DEV, dtype=torch.float64)
+    want = torch.linalg.solve(Kd, row.double().T).T
+    got = sc.solve_rows(row)
+    assert sc._X is None                      # ... and one row does not trigger it
+    assert got.shape == (1, k)
+    err = float((got.double() - want).abs().max() / want.abs().max())
+    assert err < 5e-5, err
+    again = sc.solve_rows(row)                # deterministic: fixed summation orders, counters reset per launch
+    assert torch.equal(got, again)
+    many = sc.solve_rows(_rand((5, k), 11))   # builds the explicit inverse
+    assert sc._X is not None and many.shape == (5, k)
+    via_inverse = sc.solve_rows(row)          # now the two matrix-vector products
+    assert float((via_inverse.double() - want).abs().max() / want.abs().max()) < 5e-5
+    assert G._lib.get_handle(torch.device(DEV)).watchdog_code() == 0
+
+
 def test_trak_scores_vs_fp64_oracle_and_reference_error():
     import gadm_b200 as G
 

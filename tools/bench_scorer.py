@@ -42,6 +42,10 @@ def main():
         return
     ms, phi_t = timed(lambda: G.transpose(train)); res["transpose_ms"] = ms
     ms, gram = timed(lambda: G.gemm_tn(phi_t, phi_t, lower_only=True, diag_add=0.5)); res["gram_ms"] = ms
+    from gadm_b200.scoring import gram_lower, _gram_plan
+    ms, gram_b = timed(lambda: gram_lower(train, 0.5), iters=3); res["transpose_plus_balanced_gram_ms"] = ms
+    res["gram_plan"] = _gram_plan(a.n, a.k, train.device)
+    res["balanced_gram_max_abs_diff_lower"] = float((torch.tril(gram_b) - torch.tril(gram)).abs().max())
     res["gram_tflops_fp32_equiv_full"] = 2.0 * a.n * a.k * a.k / ms / 1e9
     res["gram_tflops_computed_lower"] = res["gram_tflops_fp32_equiv_full"] * (0.5 + 64.0 / a.k)
     sc = G.TrakScorer(0.5)
