@@ -514,8 +514,9 @@ def side_measurements(dev, rank, world):
         ms = float(t.item())
     gram_flops = 2.0 * N_TRAIN * PROJ_DIM * PROJ_DIM
     out["trak_score"] = {"ms": ms, "n_train": N_TRAIN, "n_gen": N_GEN, "proj_dim": PROJ_DIM, "lam": 0.5,
-                         "what": "Gram (+NCCL all-reduce) -> Cholesky -> triangular inverse -> mean-row solve -> matvec "
-                                 "over the training features (+all-gather), incl. the factorisation check (one D2H)",
+                         "what": "transpose + wave-balanced Gram (+NCCL all-reduce) -> Cholesky -> single-row substitution for "
+                                 "mean_t(gen_t) K^-1 (one cooperative launch, no explicit inverse) -> matvec over the training "
+                                 "features (+all-gather), incl. the factorisation check (one D2H)",
                          "gram_flops": gram_flops, "finite": bool(torch.isfinite(res["trak"]).all())}
     # parity of the sharded path (all-reduce of the Gram, all-gather of the score slices) against the unsharded
     # computation on rank 0, and of both against an fp64 product for a sample of training examples
