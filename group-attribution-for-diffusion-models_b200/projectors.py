@@ -59,6 +59,9 @@ class ProjectionType(str, Enum):
 _PROJ_CODE = {ProjectionType.normal: 0, ProjectionType.rademacher: 1}
 
 
+_STAGE_NARROW = os.environ.get("GADM_STAGE_NARROW", "0") == "1"
+
+
 def _as_blocks(grads: GradsLike):
     """Normalise the accepted inputs to a list of [B, numel] views (one per parameter block)."""
     if isinstance(grads, torch.Tensor):
@@ -340,10 +343,11 @@ class DeferredProjection:
             while done < bsz:
                 take = min(bsz - done, cap - self.rows)
                 stage = self.p._stage(cap, self.cur)
-                # while a pass runs on the side stream: the quad kernel strands 16 SMs, wide staging CTAs use exactly
-                # those; the pair kernels cover every SM, so the staging CTAs must be the narrow, co-resident shape
+                # wide staging CTAs: beside a quad-kernel pass they run on the 20 SMs its 32-cluster grid leaves free;
+                # a pair-kernel pass covers every SM, so they queue behind it and then run at full speed (GADM_STAGE_NARROW=1
+                # selects the narrow shape that runs beside the pair kernel instead -- measured slower)
                 self.p._pack([b[done:done + take] for b in blocks], stage, self.rows, scale,
-                             coresident=self.overlap and self.p._group_for(cap) != 4)
+                             coresident=_STAGE_NARROW and self.overlap and self.p._group_for(cap) != 4)
                 self.rows += take
                 done += take
                 if self.rows == cap:
