@@ -510,7 +510,7 @@ __global__ void shapley_rhs_kernel(const double* __restrict__ colsum, const doub
 // ------------------------------------------------------------------ Spearman / LDS
 // rho[e, k] = Spearman( pred[idx[e, :], k], y[idx[e, :], k] )  (average ranks for ties; NaN when a
 // side is constant or holds a NaN -- scipy.stats.spearmanr semantics).  idx == nullptr: identity over the m rows.
-// One warp per (e, k); m_r <= kLdsMaxRows rows.
+// One warp per (e, k); m_r <= kLdsMaxRows rows (round 1: 1024).
 //
 // Ranks by sorting (round 1 counted "how many are smaller" for every element: O(m^2) comparisons per job): the warp
 // runs a bitonic network over (value, original index) keys in shared memory -- log2(mp) (log2(mp) + 1) / 2 stages of
@@ -519,8 +519,7 @@ __global__ void shapley_rhs_kernel(const double* __restrict__ colsum, const doub
 // rank to the element's original slot.  Twice-ranks are integers <= 2 m, and the three sums of products below are
 // sums of multiples of 1/4 far below 2^53, hence exact in any order: the result is bit-identical to the counting
 // kernel's.
-constexpr int kLdsMaxRows = 1024;
-constexpr int kLdsPerLane = kLdsMaxRows / 32;
+constexpr int kLdsMaxRows = 8192;  // sorting form: 14 bytes of shared memory per (padded) row and warp -> 112 KiB at the cap
 __host__ __device__ inline int64_t lds_pow2(int64_t m) { int64_t p = 32; while (p < m) p <<= 1; return p; }
 __host__ __device__ inline size_t lds_warp_smem_bytes(int64_t mr) {  // keys [mp] f64, order [mp] u16, twice-ranks 2 x [mp] u16
   return static_cast<size_t>(lds_pow2(mr)) * (8 + 2 + 2 + 2);

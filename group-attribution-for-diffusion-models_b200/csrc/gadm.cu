@@ -1253,6 +1253,8 @@ int gadm_lds_spearman(gadm_handle h, const double* pred, const double* y, int64_
   int warps = 8;
   while (warps > 1 && (size_t)warps * per_warp > 48 * 1024) warps /= 2;
   const size_t smem = (size_t)warps * per_warp;
+  if (smem > 48 * 1024)  // one warp per CTA and a large evaluation set: opt in to the large carve-out
+    GADM_CUDA(cudaFuncSetAttribute(gadm::agg::lds_spearman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t jobs = n_eval * k;
   const unsigned grid = (unsigned)((jobs + warps - 1) / warps);
   if (count)

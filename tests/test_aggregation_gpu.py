@@ -98,10 +98,11 @@ def test_spearman_ties_and_constant_input():
     _close(got[:4], want[:4], 1e-12)
 
 
-@pytest.mark.parametrize("m", [2, 3, 31, 32, 33, 100, 511, 1000, 1024])
+@pytest.mark.parametrize("m", [2, 3, 31, 32, 33, 100, 128, 129, 511, 1000, 1024, 3000])
 def test_spearman_sort_ranks_all_sizes(m):
     """lds_spearman_kernel ranks by a warp bitonic sort over (value, index) keys padded to a power of two: every
-    size class (below / at / above a power of two, the 1024-row maximum), heavy ties, resampled rows with duplicates,
+    size class (below / at / above a power of two and the 128-row switch from counting to sorting, beyond round 1's
+    1024-row cap), heavy ties, resampled rows with duplicates,
     against scipy.stats.spearmanr (shapley_lds.py:138-150)."""
     import gadm_b200 as G
     from scipy.stats import spearmanr

@@ -8,7 +8,7 @@ CMD="python tools/bench_aggregation.py --K $K"
 timeout 300 $CMD > gpurun_out/plain_aggregation.log 2>&1 || { tail -5 gpurun_out/plain_aggregation.log; exit 1; }
 tail -n 1 gpurun_out/plain_aggregation.log | cut -c1-900
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active"
-timeout 900 ncu --metrics $M --clock-control none -k "regex:mask_xty_kernel|dgemm_dk_kernel|lds_spearman_kernel|ridge_gcv_score_kernel|mask_gram_kernel|sym_pinv_kernel" \
+timeout 900 ncu --metrics $M --clock-control none -k "regex:mask_xty_kernel|dgemm_dk_kernel|lds_spearman|ridge_gcv_score_kernel|mask_gram_kernel|sym_pinv_kernel" \
     -c 40 --csv --log-file gpurun_out/ncu_aggregation.csv $CMD > gpurun_out/ncu_aggregation.log 2>&1
 tail -n 3 gpurun_out/ncu_aggregation.log
 python - <<'PY'
