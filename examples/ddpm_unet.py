@@ -150,6 +150,23 @@ class DDPMScheduler:
         a = self.alphas_cumprod.to(x.device)[t]
         return a.sqrt()[:, None, None, None] * x + (1 - a).sqrt()[:, None, None, None] * noise
 
+    def inference_timesteps(self, num_inference_steps: int):
+        """Evenly strided, descending (diffusers' DDPMScheduler.set_timesteps, "leading" spacing)."""
+        n_train = self.alphas_cumprod.shape[0]
+        return list(range(0, n_train, n_train // num_inference_steps))[::-1][:num_inference_steps]
+
+    def step(self, eps, t: int, t_prev: int, x, generator=None):
+        """One ancestral DDPM step x_t -> x_{t_prev} for an epsilon-prediction model (fixed-small variance)."""
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[t_prev] if t_prev >= 0 else torch.ones_like(a_t)
+        beta_t = 1 - a_t / a_prev
+        x0 = ((x - (1 - a_t).sqrt() * eps) / a_t.sqrt()).clamp(-1, 1)
+        mean = (a_prev.sqrt() * beta_t / (1 - a_t)) * x0 + ((1 - beta_t).sqrt() * (1 - a_prev) / (1 - a_t)) * x
+        if t_prev < 0:
+            return mean
+        var = (1 - a_prev) / (1 - a_t) * beta_t
+        return mean + var.clamp(min=1e-20).sqrt() * torch.randn(x.shape, device=x.device, dtype=x.dtype, generator=generator)
+
 
 def count_parameters(model) -> int:
     """src/attributions/methods/d_trak_grad.py:183-185."""

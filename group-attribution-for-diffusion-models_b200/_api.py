@@ -11,7 +11,8 @@ from .masks import (counterfactual_split, masks_from_seeds, remove_data_by_datam
                     remove_data_by_uniform)
 from .datamodel import (RidgeCV, compute_datamodel_scores, datamodel, datamodel_ridge_batched,  # noqa: F401
                         ridge_cv_batched)
-from .formats import collect_data, load_lds_test_sets, read_behavior_db, run_traks, save_lds_outputs  # noqa: F401
+from .formats import (collect_data, journey_point_indices, load_lds_test_sets, read_behavior_db, run_traks,  # noqa: F401
+                      save_lds_outputs, write_journey_group_csv)
 from ._lib import GadmError, load_library  # noqa: F401
 
 __all__ = [
@@ -24,6 +25,7 @@ __all__ = [
     "counterfactual_split", "masks_from_seeds", "remove_data_by_datamodel", "remove_data_by_shapley",
     "remove_data_by_uniform",
     "RidgeCV", "datamodel_ridge_batched", "ridge_cv_batched", "datamodel", "compute_datamodel_scores",
-    "collect_data", "load_lds_test_sets", "read_behavior_db", "run_traks", "save_lds_outputs",
+    "collect_data", "journey_point_indices", "load_lds_test_sets", "read_behavior_db", "run_traks", "save_lds_outputs",
+    "write_journey_group_csv",
     "GadmError", "load_library",
 ]

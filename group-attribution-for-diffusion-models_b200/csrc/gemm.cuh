@@ -522,12 +522,20 @@ __device__ __forceinline__ void smem_block_mm(const float* A, int lda, const flo
 template <bool kBT, bool kAccum, bool kLowerOnly>
 __device__ __forceinline__ void smem_tile_mm(const float* A, int lda, const float* B, int ldb, float* Cm, int ldc, int R,
                                              int Cn, int T, float sign) {
-  const int tr = R >> 2, tc = Cn >> 2;
-  for (int idx = threadIdx.x; idx < tr * tc; idx += kPotrfThreads) {
-    const int ti = idx / tc, tj = idx % tc;
-    if (kLowerOnly && tj > ti) continue;
+  // A thread owns rows 4 ti .. 4 ti + 3 and the four columns tj, tj + Cn/4, tj + 2 Cn/4, tj + 3 Cn/4: consecutive
+  // threads then read consecutive B rows (kBT: pitch 129 -> consecutive banks) or consecutive B / C words.  With four
+  // ADJACENT columns per thread (round 1) the B and C accesses of a warp were 4 words apart: 4-way bank conflicts on
+  // 5 of every 8 shared-memory loads, and shared memory is what bounds these products (8 loads per 16 FMAs).
+  const int tr = R >> 2, tcw = Cn >> 2;
+  for (int idx = threadIdx.x; idx < tr * tcw; idx += kPotrfThreads) {
+    const int ti = idx / tcw, tj = idx % tcw;
+    int nj = 4;  // columns of this thread that reach the lower triangle (column <= last row of the tile)
+    if (kLowerOnly) {
+      if (tj > ti * 4 + 3) continue;
+      nj = (ti * 4 + 3 - tj) / tcw + 1;
+      if (nj > 4) nj = 4;
+    }
     const float* a = A + (ti * 4) * lda;
-    const float* b = kBT ? B + (tj * 4) * ldb : B + tj * 4;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -539,7 +547,8 @@ __device__ __forceinline__ void smem_tile_mm(const float* A, int lda, const floa
 #pragma unroll
       for (int i = 0; i < 4; ++i) av[i] = a[i * lda + t];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = kBT ? b[j * ldb + t] : b[t * ldb + j];
+      for (int j = 0; j < 4; ++j)
+        bv[j] = (j < nj) ? (kBT ? B[(tj + j * tcw) * ldb + t] : B[t * ldb + tj + j * tcw]) : 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -549,7 +558,8 @@ __device__ __forceinline__ void smem_tile_mm(const float* A, int lda, const floa
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float* c = Cm + (ti * 4 + i) * ldc + tj * 4 + j;
+        if (j >= nj) continue;
+        float* c = Cm + (ti * 4 + i) * ldc + tj + j * tcw;
         *c = kAccum ? fmaf(sign, acc[i][j], *c) : sign * acc[i][j];
       }
   }

@@ -89,6 +89,25 @@ def save_lds_outputs(output_dir: str, outfile_prefix: str, fit_size: int, attrs_
     return rank
 
 
+def journey_point_indices(num_inference_steps: int, num_journey_points: int) -> np.ndarray:
+    """Sampling-trajectory steps whose latents Journey-TRAK featurises
+    (text_to_image/grad_text_to_image_lora.py:515-523): ``np.arange(1, n, n // num_journey_points)``."""
+    if num_journey_points < 1 or num_journey_points > num_inference_steps:
+        raise ValueError(f"num_journey_points must lie in [1, {num_inference_steps}], got {num_journey_points}")
+    return np.arange(start=1, stop=num_inference_steps, step=num_inference_steps // num_journey_points)
+
+
+def write_journey_group_csv(output_dir: str, generated_image_idx: Sequence[int], step_idx: Sequence[int]) -> str:
+    """``group.csv`` of the generated / generated_journey featurisation: one row per featurised latent with the image
+    it belongs to and its trajectory step (grad_text_to_image_lora.py:526-529; read back by traks.py)."""
+    import pandas as pd
+
+    os.makedirs(output_dir, exist_ok=True)
+    path = os.path.join(output_dir, "group.csv")
+    pd.DataFrame({"generated_image_idx": list(generated_image_idx), "step_idx": list(step_idx)}).to_csv(path, index=True)
+    return path
+
+
 def _group_ids(group_names: Sequence, train_groups: Sequence) -> np.ndarray:
     """traks.py:92-98: index of each training example's group in the group table (-1: not in any group)."""
     lut = {name: i for i, name in enumerate(group_names)}

@@ -78,3 +78,26 @@ def test_featurize_dict_path_equals_flattened_path_and_scores_match_oracle():
         theirs = np.abs(ref32[name].astype(np.float64) - want[name]).max() / scale
         cond = float(np.linalg.cond(phi[:8].double().cpu().numpy().T @ phi[:8].double().cpu().numpy() + 0.5 * np.eye(512)))
         assert ours <= max(8 * theirs, 2e-4), (name, ours, theirs, cond)
+
+
+def test_journey_trak_featurisation_example():
+    """Journey-TRAK end to end on the U-Net (grad_text_to_image_lora.py:485-545,729-770): trajectory latents at the
+    journey points, noise-averaged gradients through DeferredProjection.accumulate, group.csv, journey_trak scores."""
+    import pandas as pd
+    import journey_trak as J
+    from gadm_b200 import journey_point_indices
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30 * 2**30:
+        pytest.skip("needs ~20 GB of free HBM")
+    np.testing.assert_array_equal(journey_point_indices(100, 50), np.arange(1, 100, 2))   # the reference's defaults
+    np.testing.assert_array_equal(journey_point_indices(10, 3), np.array([1, 4, 7]))
+    phi, idx, steps, scores, out_dir = J.main(["--n-train", "12", "--n-images", "2", "--num-inference-steps", "8",
+                                               "--num-journey-points", "4", "--num-journey-noises", "2",
+                                               "--proj-dim", "512", "--batch", "4"])
+    want_steps = list(journey_point_indices(8, 4))
+    assert steps == want_steps * 2 and idx == [0] * len(want_steps) + [1] * len(want_steps)
+    assert phi.shape == (2 * len(want_steps), 512) and bool(torch.isfinite(phi).all())
+    df = pd.read_csv(os.path.join(out_dir, "generated_journey", "group.csv"), index_col=0)
+    assert df["generated_image_idx"].tolist() == idx and df["step_idx"].tolist() == steps
+    assert scores["journey_trak"].shape == (12,) and bool(torch.isfinite(scores["journey_trak"]).all())

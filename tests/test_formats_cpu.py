@@ -53,3 +53,24 @@ def test_records_out_of_order_and_global_key(tmp_path):
     null = tmp_path / "null.jsonl"
     null.write_text(json.dumps({"exp_name": "null_model", "fid": 1.5}) + "\n")
     assert collect_data(read_behavior_db(str(null)), 4, "fid", None, collect_remaining_masks=False).tolist() == [[1.5]]
+
+
+def test_journey_points_and_group_csv(tmp_path):
+    """Journey-TRAK bookkeeping of grad_text_to_image_lora.py:515-529: which trajectory steps are featurised and the
+    group.csv that maps every featurised latent to its generated image."""
+    import pandas as pd
+    import pytest
+
+    from gadm_b200.formats import journey_point_indices, write_journey_group_csv
+
+    np.testing.assert_array_equal(journey_point_indices(100, 50), np.arange(1, 100, 2))  # the reference's settings
+    np.testing.assert_array_equal(journey_point_indices(100, 30), np.arange(1, 100, 3))  # 33 points, as upstream yields
+    np.testing.assert_array_equal(journey_point_indices(7, 7), np.arange(1, 7))
+    with pytest.raises(ValueError):
+        journey_point_indices(10, 0)
+    with pytest.raises(ValueError):
+        journey_point_indices(10, 11)
+    path = write_journey_group_csv(str(tmp_path / "generated_journey"), [0, 0, 1, 1], [1, 3, 1, 3])
+    df = pd.read_csv(path, index_col=0)
+    assert df.columns.tolist() == ["generated_image_idx", "step_idx"]
+    assert df.index.tolist() == [0, 1, 2, 3] and df["step_idx"].tolist() == [1, 3, 1, 3]
