@@ -570,6 +570,46 @@ __device__ __forceinline__ void smem_tile_mm(const float* A, int lda, const floa
 #else
 #define POTRF_T(i) do { } while (0)
 #endif
+// C (128 x 128, lower 4 x 4 tiles incl. the diagonal ones) -= P P^T for a 128 x 128 P, all in shared memory: the
+// 528 needed tiles are enumerated along the triangle and dealt round-robin, so every thread owns one tile (16 threads
+// two) -- the generic routine above deals the full 32 x 32 tile grid and skips the upper half, which leaves a quarter
+// of the threads with two tiles and a quarter with none (this product sits on the critical path of every step).
+__device__ __forceinline__ void smem_syrk_lower_128(const float* P, int ldp, float* Cm, int ldc) {
+  constexpr int kTiles = 32 * 33 / 2;
+  for (int idx = threadIdx.x; idx < kTiles; idx += kPotrfThreads) {
+    int ti = static_cast<int>((sqrtf(8.f * static_cast<float>(idx) + 1.f) - 1.f) * 0.5f);
+    while (ti * (ti + 1) / 2 > idx) --ti;            // guard the float square root at tile-row boundaries
+    while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+    const int tj = idx - ti * (ti + 1) / 2;          // tj <= ti
+    const float* a = P + (ti * 4) * ldp;
+    const float* b = P + (tj * 4) * ldp;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < kPotrfNb; ++t) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = a[i * ldp + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = b[j * ldp + t];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float* c = Cm + (ti * 4 + i) * ldc + tj * 4 + j;
+        *c = *c - acc[i][j];
+      }
+  }
+}
+
 __global__ void __launch_bounds__(kPotrfThreads, 1)
 potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__ linv, float* __restrict__ linv_t,
                   int* __restrict__ info, int block_index, const float* __restrict__ prev) {
@@ -596,7 +636,7 @@ potrf_diag_kernel(float* __restrict__ A, int64_t ld, int nb, float* __restrict__
   }
   __syncthreads();
   if (prev != nullptr) {
-    smem_tile_mm<true, true, true>(X, kPotrfLd, X, kPotrfLd, L, kPotrfLd, kPotrfNb, kPotrfNb, kPotrfNb, -1.f);
+    smem_syrk_lower_128(X, kPotrfLd, L, kPotrfLd);
     __syncthreads();
     for (int idx = tid; idx < kPotrfNb * kPotrfNb; idx += kPotrfThreads) X[(idx / kPotrfNb) * kPotrfLd + idx % kPotrfNb] = 0.f;
     __syncthreads();
