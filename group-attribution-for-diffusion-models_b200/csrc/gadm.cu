@@ -37,6 +37,7 @@ struct gadm_ctx {
   int quad_clusters = -1;       // co-resident clusters of 4 CTAs for the quad projection kernel (lazy)
   bool attr_gemm = false, attr_gemm_ts = false, attr_potrf = false;  // per-device kernel attributes already set
   bool attr_trsv = false;
+  bool attr_gemm_ts2 = false;
   uint32_t attr_stage_wide = 0; // same, dynamic shared-memory opt-in of the wide staging kernels
   uint32_t attr_stage = 0;      // bit per staging-kernel instantiation whose carveout preference has been set
   cudaStream_t hp_stream = nullptr;  // high-priority stream for the Cholesky critical path (lazy)
@@ -665,6 +666,34 @@ int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t str
   dim3 grid((unsigned)((n + gadm::gemm::kBN - 1) / gadm::gemm::kBN), (unsigned)((m + gadm::gemm::kBM - 1) / gadm::gemm::kBM),
             (unsigned)batch);
   GADM_REQUIRE(grid.y < 65536, "too many row tiles (%u)", grid.y);
+  // CTA-pair variant (256 x 128 tiles, B split between the two CTAs): opt-in while it is being measured
+  static const bool use_2cta = [] { const char* e = getenv("GADM_GEMM_2CTA"); return e && atoi(e) == 1; }();
+  if (use_ts && use_2cta && m > gadm::gemm::kBM) {
+    CUtensorMap tbh;
+    GADM_TRY(make_tmap_3d_f32(h, &tbh, b, (uint64_t)k, (uint64_t)n, (uint64_t)batch, (uint64_t)ldb * 4, sb, gadm::gemm::kBK,
+                              gadm::gemm::kBN / 2));
+    auto kernel = gadm::gemm::gemm_tn_3xtf32_ts2_kernel;
+    if (!h->attr_gemm_ts2) {
+      GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kT2SmemBytes));
+      h->attr_gemm_ts2 = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2u * (unsigned)((m + 2 * gadm::gemm::kBM - 1) / (2 * gadm::gemm::kBM)), grid.x, (unsigned)batch);
+    cfg.blockDim = dim3(gadm::gemm::kT2Threads);
+    cfg.dynamicSmemBytes = gadm::gemm::kT2SmemBytes;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GADM_REQUIRE(cfg.gridDim.y < 65536, "too many column tiles (%u)", cfg.gridDim.y);
+    GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tbh, args));
+    h->launches++;
+    return GADM_OK;
+  }
   if (use_ts) {
     auto kernel = gadm::gemm::gemm_tn_3xtf32_ts_kernel;
     if (!h->attr_gemm_ts) {  // the attribute is per device: remembered in the handle, not in a process-wide static

@@ -428,6 +428,211 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 2) tmem_dealloc<1>(tmem_base, kTsTmemCols);
 }
 
+// ------------------------------------------------------------------ "TS2" variant: CTA pair (cta_group::2)
+// The TS kernel above is still bounded by shared-memory bandwidth (128 KiB per k-block at 128 B/clk = 1024 clocks for
+// 768 clocks of tf32 math).  Here two CTAs of a cluster compute a 256 x 128 output tile together: each owns 128 rows
+// (its A tile, split into its own tensor memory) and HALF of the B tile (64 rows), and one thread of the leader CTA
+// issues tcgen05.mma.cta_group::2 with M = 256 -- the tensor cores of both SMs read both halves of B.  Per CTA and
+// k-block the tensor core then reads 3 x 8 KiB, the splitter moves 32 KiB and TMA writes 24 KiB: 80 KiB = 640 clocks,
+// below the math time, and the B traffic from L2 halves.
+// Barriers: raw_full / empty / acc_full are per CTA (the commits are multicast to both); split_full and acc_empty live
+// in the leader and collect the arrivals of both CTAs' splitter / epilogue warps.
+constexpr int kT2Stages = 6;                               // shared-memory ring (TMA prefetch distance)
+constexpr int kT2ASlots = 4;                               // tensor-memory ring of split A tiles: 256 accumulator + 4 x 64 columns
+constexpr int kT2HalfB = kTileBytes / 2;                   // 64 rows of the B tile
+constexpr int kT2StageBytes = kTileBytes + 2 * kT2HalfB;   // rawA | rawB half (= hi, read in place) | lo B half
+constexpr int kT2SmemBytes = kT2Stages * kT2StageBytes + 256 + 1024;
+constexpr int kT2SplitGroups = 2;                          // groups of 4 splitter warps that alternate k-blocks
+constexpr int kT2Threads = (kFirstSplitWarp + kT2SplitGroups * kSplitWarps) * 32;
+
+// grid = (2 * row-tile pairs, column tiles, batch), cluster = (2, 1, 1)
+__global__ void __launch_bounds__(kT2Threads, 1)
+gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh,
+                          const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (even row tile), 1 = the row tile below it
+  // the pair leaves together: only when even its lower row tile (tile_m | 1) lies above the diagonal
+  if (a.lower_only && tile_n * kBN > (tile_m | 1) * kBM + (kBM - 1)) return;
+  const bool store = !(a.lower_only && tile_n * kBN > tile_m * kBM + (kBM - 1));  // the leader's tile may be above it
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kT2Stages * kT2StageBytes;
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };
+  auto split_full = [&](int s) { return bar_base + 8u * (kT2Stages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kT2Stages + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (3 * kT2Stages + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (3 * kT2Stages + 2 + b); };
+  auto aslot_empty = [&](int t) { return bar_base + 8u * (3 * kT2Stages + 4 + t); };  // per CTA: its own tensor memory
+  const uint32_t tmem_slot = bar_base + 8u * (3 * kT2Stages + 4 + kT2ASlots);
+  auto raw_a = [&](int s) { return smem_base + s * kT2StageBytes; };
+  auto hi_b = [&](int s) { return smem_base + s * kT2StageBytes + kTileBytes; };
+  auto lo_b = [&](int s) { return smem_base + s * kT2StageBytes + kTileBytes + kT2HalfB; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int kb0, kb1;
+  kblock_range(a, tile_n, kb0, kb1);
+  const int nkb = kb1 - kb0;
+  const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
+
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_bh); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kT2Stages; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(split_full(s), 2 * kSplitWarps);  // used in the leader only
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 2 * kEpiWarps);     // used in the leader only
+    }
+    for (int t = 0; t < kT2ASlots; ++t) mbar_init(aslot_empty(t), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2>(tmem_slot, kTsTmemCols);
+  tcgen05_fence_before();
+  cluster_arrive_wait();  // both CTAs' barriers are initialised before anybody arrives remotely
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kT2Stages;
+        const uint32_t ph = (kb / kT2Stages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u, 0x2900 + s);
+        mbar_arrive_expect_tx(raw_full(s), kTileBytes + kT2HalfB);
+        tma_load_3d(raw_a(s), &tmap_a, raw_full(s), (kb0 + kb) * kBK, tile_m * kBM, blockIdx.z);
+        tma_load_3d(hi_b(s), &tmap_bh, raw_full(s), (kb0 + kb) * kBK, tile_n * kBN + static_cast<int>(rank) * (kBN / 2),
+                    blockIdx.z);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 2 * kBM, kBN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(acc_empty(buf), ((c >> 1) & 1u) ^ 1u, 0x2d00 + buf);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        const int kb_end = (c + 1) * kChunkKB < nkb ? (c + 1) * kChunkKB : nkb;
+        for (int kb = c * kChunkKB; kb < kb_end; ++kb) {
+          const int s = kb % kT2Stages;
+          const uint32_t ph = (kb / kT2Stages) & 1u;
+          mbar_wait(split_full(s), ph, 0x2a00 + s);
+          tcgen05_fence_after();
+          const uint64_t dhb = umma_desc_kmajor_sw128(hi_b(s)), dlb = umma_desc_kmajor_sw128(lo_b(s));
+          const int ts = kb % kT2ASlots;
+          const uint32_t a_hi = tmem_base + kTsACol0 + ts * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint32_t first = (kb == c * kChunkKB && k == 0) ? 0u : 1u;
+            umma_tf32_ts_cg2(d_tmem, a_lo + k * kUmmaK, dhb + 2u * k, idesc, first);  // small terms first
+            umma_tf32_ts_cg2(d_tmem, a_hi + k * kUmmaK, dlb + 2u * k, idesc, 1u);
+            umma_tf32_ts_cg2(d_tmem, a_hi + k * kUmmaK, dhb + 2u * k, idesc, 1u);
+          }
+          umma_commit_cg2_mcast(empty_bar(s), 0x3);
+          umma_commit_cg2_mcast(aslot_empty(ts), 0x3);
+        }
+        umma_commit_cg2_mcast(acc_full(buf), 0x3);
+      }
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstSplitWarp) {
+    const int e = warp - kFirstEpiWarp;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(acc_full(buf), (c >> 1) & 1u, 0x2b00 + buf);
+      tcgen05_fence_after();
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBN + half * 64;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t0 + j * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(v[i]));
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(acc_empty(buf)); else mbar_arrive_cluster(mapa(acc_empty(buf), 0));
+      }
+    }
+    const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
+    const int64_t col0 = static_cast<int64_t>(tile_n) * kBN + half * 64;
+    if (store && row < a.M) {
+      float* crow = a.C + static_cast<int64_t>(blockIdx.z) * a.stride_c + row * a.ldc;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const int64_t col = col0 + i;
+        if (col < a.N) {
+          float r = a.alpha * acc[i];
+          if (a.beta != 0.f) r += a.beta * crow[col];
+          if (col == row) r += a.diag_add;
+          crow[col] = r;
+        }
+      }
+    }
+  } else if (warp >= kFirstSplitWarp) {
+    // two groups of four warps take alternate k-blocks: one k-block is a chain of dependent steps (LDS -> split ->
+    // tcgen05.st -> wait::st -> fence -> arrive) that a single group cannot overlap with the next k-block's
+    const int q = warp & 3;
+    const int group = (warp - kFirstSplitWarp) / kSplitWarps;
+    const int t = (threadIdx.x - kFirstSplitWarp * 32) & (kSplitWarps * 32 - 1);
+    const int row = q * 32 + lane;
+    for (int kb = group; kb < nkb; kb += kT2SplitGroups) {
+      const int s = kb % kT2Stages;
+      const uint32_t ph = (kb / kT2Stages) & 1u;
+      mbar_wait(raw_full(s), ph, 0x2c00 + s);
+      const int ts = kb % kT2ASlots;
+      mbar_wait(aslot_empty(ts), ((kb / kT2ASlots) & 1u) ^ 1u, 0x2e00 + ts);  // the MMAs that read this A slot are done
+      tcgen05_fence_after();
+      {
+        uint32_t x[32], lo[32];
+        const uint32_t rbase = raw_a(s) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = ld_shared_v4(rbase + ((c ^ (row & 7)) << 4));
+          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { uint32_t hi; split_tf32(x[i], hi, lo[i]); }
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kTsACol0 + ts * 64;
+        tmem_st_32x32b_x32(ta, x);
+        tmem_st_32x32b_x32(ta + 32, lo);
+      }
+      const uint32_t raw = hi_b(s);
+#pragma unroll
+      for (int i = 0; i < kT2HalfB / 16 / (kSplitWarps * 32); ++i) {
+        const uint32_t off = (static_cast<uint32_t>(i) * (kSplitWarps * 32) + t) * 16u;
+        const uint4 v = ld_shared_v4(raw + off);
+        uint4 hi, lo;
+        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+        split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+        st_shared_v4(raw + kT2HalfB + off, lo);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(split_full(s)); else mbar_arrive_cluster(mapa(split_full(s), 0));
+      }
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_arrive_wait();  // the peer's tensor memory / barriers are not touched after this point
+  if (warp == 2) tmem_dealloc<2>(tmem_base, kTsTmemCols);
+}
+
 // ------------------------------------------------------------------ helpers around the GEMM
 
 // out[c, r] = in[r, c]; in: [R, C] pitch ld_in; out: [C, R_pad] pitch ld_out (columns R..ld_out untouched).

@@ -443,3 +443,24 @@ def test_failed_or_ill_conditioned_factorisation_is_an_error_not_garbage(tmp_pat
     with pytest.raises(G.GadmError):
         G.compute_gradient_scores(args, outdir=str(tmp_path / "out"))
     assert not (tdir / f"kernel_train_f=loss_t=uniform_k=10_d={k}.npy").exists()
+
+
+def test_cta_pair_gemm_variant_matches_fp64():
+    """The opt-in CTA-pair GEMM (GADM_GEMM_2CTA=1: 256 x 128 tiles over a cluster of two CTAs, tcgen05.mma.cta_group::2
+    with the A operand in each CTA's tensor memory and the B tile split between them) against fp64 over ragged shapes,
+    odd row-tile counts, lower-only and triangular-B modes and beta accumulation.  The switch is read once per process,
+    hence the subprocess."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GADM_GEMM_2CTA="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "check_gemm_2cta.py"), "--quick"], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["env"] == "1" and res["watchdog"] == 0
+    assert res["worst_rel_err"] < 3e-6, res
+    assert res["beta_err"] < 1e-3, res
