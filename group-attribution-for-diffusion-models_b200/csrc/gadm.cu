@@ -666,19 +666,21 @@ int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t str
   dim3 grid((unsigned)((n + gadm::gemm::kBN - 1) / gadm::gemm::kBN), (unsigned)((m + gadm::gemm::kBM - 1) / gadm::gemm::kBM),
             (unsigned)batch);
   GADM_REQUIRE(grid.y < 65536, "too many row tiles (%u)", grid.y);
-  // CTA-pair variant (256 x 128 tiles, B split between the two CTAs): opt-in while it is being measured
-  static const bool use_2cta = [] { const char* e = getenv("GADM_GEMM_2CTA"); return e && atoi(e) == 1; }();
-  if (use_ts && use_2cta && m > gadm::gemm::kBM) {
-    CUtensorMap tbh;
-    GADM_TRY(make_tmap_3d_f32(h, &tbh, b, (uint64_t)k, (uint64_t)n, (uint64_t)batch, (uint64_t)ldb * 4, sb, gadm::gemm::kBK,
-                              gadm::gemm::kBN / 2));
+  // CTA-pair variant (256 x 256 tiles, N = 256 per MMA instruction): default whenever the problem has more than one
+  // 128-tile in both directions; GADM_GEMM_2CTA=0 selects the single-CTA kernel everywhere
+  static const bool use_2cta = [] { const char* e = getenv("GADM_GEMM_2CTA"); return !(e && atoi(e) == 0); }();
+  // (long contractions only: for the rank-128 updates of the blocked Cholesky and the small merges of the triangular
+  // inverse the larger tiles mean fewer, longer CTAs and measured slower -- 2.84 vs 2.67 ms for the factorisation)
+  if (use_ts && use_2cta && m > gadm::gemm::kBM && n > gadm::gemm::kBN && k >= 2048) {
+    // B box: the 128 rows of the 256-column tile that one CTA of the pair holds = the same tensor map as the 1-CTA kernel
     auto kernel = gadm::gemm::gemm_tn_3xtf32_ts2_kernel;
     if (!h->attr_gemm_ts2) {
       GADM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gadm::gemm::kT2SmemBytes));
       h->attr_gemm_ts2 = true;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2u * (unsigned)((m + 2 * gadm::gemm::kBM - 1) / (2 * gadm::gemm::kBM)), grid.x, (unsigned)batch);
+    cfg.gridDim = dim3(2u * (unsigned)((m + 2 * gadm::gemm::kBM - 1) / (2 * gadm::gemm::kBM)),
+                       (unsigned)((n + gadm::gemm::kT2BN - 1) / gadm::gemm::kT2BN), (unsigned)batch);
     cfg.blockDim = dim3(gadm::gemm::kT2Threads);
     cfg.dynamicSmemBytes = gadm::gemm::kT2SmemBytes;
     cfg.stream = as_stream(stream);
@@ -690,7 +692,7 @@ int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t str
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     GADM_REQUIRE(cfg.gridDim.y < 65536, "too many column tiles (%u)", cfg.gridDim.y);
-    GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tbh, args));
+    GADM_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, args));
     h->launches++;
     return GADM_OK;
   }

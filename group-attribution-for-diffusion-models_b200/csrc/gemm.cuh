@@ -428,65 +428,74 @@ gemm_tn_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 2) tmem_dealloc<1>(tmem_base, kTsTmemCols);
 }
 
-// ------------------------------------------------------------------ "TS2" variant: CTA pair (cta_group::2)
-// The TS kernel above is still bounded by shared-memory bandwidth (128 KiB per k-block at 128 B/clk = 1024 clocks for
-// 768 clocks of tf32 math).  Here two CTAs of a cluster compute a 256 x 128 output tile together: each owns 128 rows
-// (its A tile, split into its own tensor memory) and HALF of the B tile (64 rows), and one thread of the leader CTA
-// issues tcgen05.mma.cta_group::2 with M = 256 -- the tensor cores of both SMs read both halves of B.  Per CTA and
-// k-block the tensor core then reads 3 x 8 KiB, the splitter moves 32 KiB and TMA writes 24 KiB: 80 KiB = 640 clocks,
-// below the math time, and the B traffic from L2 halves.
-// Barriers: raw_full / empty / acc_full are per CTA (the commits are multicast to both); split_full and acc_empty live
-// in the leader and collect the arrivals of both CTAs' splitter / epilogue warps.
-constexpr int kT2Stages = 6;                               // shared-memory ring (TMA prefetch distance)
-constexpr int kT2ASlots = 4;                               // tensor-memory ring of split A tiles: 256 accumulator + 4 x 64 columns
-constexpr int kT2HalfB = kTileBytes / 2;                   // 64 rows of the B tile
-constexpr int kT2StageBytes = kTileBytes + 2 * kT2HalfB;   // rawA | rawB half (= hi, read in place) | lo B half
+// ------------------------------------------------------------------ "TS2" variant: CTA pair, 256 x 256 tiles
+// What bounds the TS kernel above is the granularity of its MMA instructions.  Measured on the config-2 Gram: issuing
+// every 128 x 128 x 8 MMA as two 128 x 64 x 8 halves (same arithmetic, bit-identical results) takes 6.16 ms instead of
+// 4.33 -- interleaved over two accumulator column ranges or not -- i.e. ~47 clocks of fixed cost per instruction next
+// to 64 clocks of math: 42 % of the kernel.  (A first CTA-pair variant with 256 x 128 tiles, half the shared-memory
+// traffic, a 6-stage ring and two splitter groups measured 4.04 - 4.26 ms: none of those was the limit.)  This kernel
+// doubles N: a cluster of two CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2, M = 256, N = 256 --
+// each CTA owns 128 rows (its A tile, split into its own tensor memory) and 128 of the 256 B rows (raw + lo tile in
+// its shared memory), one thread of the leader issues the MMAs for both.
+//   shared memory per stage: rawA 16 KiB | rawB half (= hi) 16 KiB | lo B half 16 KiB = 48 KiB, 4 stages;
+//   tensor memory: [0, 256) ONE accumulator (no ping-pong: the MMAs of the next chunk wait until the epilogue has
+//   read the chunk out, ~5 % of a chunk), [256 + 64 s, +64) hi / lo A of stage s;
+//   epilogue: 8 warps x 128 fp32 running sums per thread -- the register file is re-split with setmaxnreg
+//   (epilogue 184, splitter 104, control warps 40 registers per thread).
+// Barriers: raw_full / empty / acc_full are per CTA (commits are multicast to both); split_full and acc_empty live in
+// the leader and collect the arrivals of both CTAs' splitter / epilogue warps.
+constexpr int kT2BN = 256;
+constexpr int kT2Stages = 4;
+constexpr int kT2StageBytes = 3 * kTileBytes;
 constexpr int kT2SmemBytes = kT2Stages * kT2StageBytes + 256 + 1024;
-constexpr int kT2SplitGroups = 2;                          // groups of 4 splitter warps that alternate k-blocks
-constexpr int kT2Threads = (kFirstSplitWarp + kT2SplitGroups * kSplitWarps) * 32;
+constexpr int kT2Threads = kThreads;
 
-// grid = (2 * row-tile pairs, column tiles, batch), cluster = (2, 1, 1)
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
+// grid = (2 * row-tile pairs, 256-column tiles, batch), cluster = (2, 1, 1)
 __global__ void __launch_bounds__(kT2Threads, 1)
-gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh,
+gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                           const Args a) {
   extern __shared__ uint8_t smem_raw[];
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
-  const uint32_t rank = cluster_ctarank();  // 0 = leader (even row tile), 1 = the row tile below it
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;  // 128-row tile of this CTA, 256-column tile of the pair
+  const uint32_t rank = cluster_ctarank();             // 0 = leader (even row tile), 1 = the row tile below it
   // the pair leaves together: only when even its lower row tile (tile_m | 1) lies above the diagonal
-  if (a.lower_only && tile_n * kBN > (tile_m | 1) * kBM + (kBM - 1)) return;
-  const bool store = !(a.lower_only && tile_n * kBN > tile_m * kBM + (kBM - 1));  // the leader's tile may be above it
+  if (a.lower_only && tile_n * kT2BN > (tile_m | 1) * kBM + (kBM - 1)) return;
+  const bool store = !(a.lower_only && tile_n * kT2BN > tile_m * kBM + (kBM - 1));  // the leader's tile may be above it
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kT2Stages * kT2StageBytes;
   auto raw_full = [&](int s) { return bar_base + 8u * s; };
   auto split_full = [&](int s) { return bar_base + 8u * (kT2Stages + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kT2Stages + s); };
-  auto acc_full = [&](int b) { return bar_base + 8u * (3 * kT2Stages + b); };
-  auto acc_empty = [&](int b) { return bar_base + 8u * (3 * kT2Stages + 2 + b); };
-  auto aslot_empty = [&](int t) { return bar_base + 8u * (3 * kT2Stages + 4 + t); };  // per CTA: its own tensor memory
-  const uint32_t tmem_slot = bar_base + 8u * (3 * kT2Stages + 4 + kT2ASlots);
+  const uint32_t acc_full = bar_base + 8u * (3 * kT2Stages);
+  const uint32_t acc_empty = bar_base + 8u * (3 * kT2Stages + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * kT2Stages + 2);
   auto raw_a = [&](int s) { return smem_base + s * kT2StageBytes; };
   auto hi_b = [&](int s) { return smem_base + s * kT2StageBytes + kTileBytes; };
-  auto lo_b = [&](int s) { return smem_base + s * kT2StageBytes + kTileBytes + kT2HalfB; };
+  auto lo_b = [&](int s) { return smem_base + s * kT2StageBytes + 2 * kTileBytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int kb0, kb1;
-  kblock_range(a, tile_n, kb0, kb1);
+  // contraction range: tri_b refers to 128-column blocks of B; a 256-column tile spans two of them
+  const int nkb_all = (a.K + kBK - 1) / kBK;
+  int kb0 = 0, kb1 = nkb_all;
+  if (a.tri_b == 1) { const int e = (2 * tile_n + 2) * (kBN / kBK); kb1 = e < nkb_all ? e : nkb_all; }
+  else if (a.tri_b == 2) { const int b0 = 2 * tile_n * (kBN / kBK); kb0 = b0 < nkb_all ? b0 : nkb_all; }
   const int nkb = kb1 - kb0;
   const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
 
-  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_bh); }
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_b); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kT2Stages; ++s) {
       mbar_init(raw_full(s), 1);
       mbar_init(split_full(s), 2 * kSplitWarps);  // used in the leader only
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 2 * kEpiWarps);     // used in the leader only
-    }
-    for (int t = 0; t < kT2ASlots; ++t) mbar_init(aslot_empty(t), 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 2 * kEpiWarps);          // used in the leader only
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2>(tmem_slot, kTsTmemCols);
@@ -496,26 +505,23 @@ gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp < kFirstEpiWarp) {
+    setmaxnreg_dec<40>();
+    if (warp == 0 && lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kT2Stages;
         const uint32_t ph = (kb / kT2Stages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 0x2900 + s);
-        mbar_arrive_expect_tx(raw_full(s), kTileBytes + kT2HalfB);
+        mbar_arrive_expect_tx(raw_full(s), 2 * kTileBytes);
         tma_load_3d(raw_a(s), &tmap_a, raw_full(s), (kb0 + kb) * kBK, tile_m * kBM, blockIdx.z);
-        tma_load_3d(hi_b(s), &tmap_bh, raw_full(s), (kb0 + kb) * kBK, tile_n * kBN + static_cast<int>(rank) * (kBN / 2),
+        tma_load_3d(hi_b(s), &tmap_b, raw_full(s), (kb0 + kb) * kBK, tile_n * kT2BN + static_cast<int>(rank) * kBN,
                     blockIdx.z);
       }
-    }
-  } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
-      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 2 * kBM, kBN);
+    } else if (warp == 1 && rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 2 * kBM, kT2BN);
       for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        mbar_wait(acc_empty(buf), ((c >> 1) & 1u) ^ 1u, 0x2d00 + buf);
+        mbar_wait(acc_empty, (c & 1u) ^ 1u, 0x2d00);  // both CTAs' epilogues have read chunk c - 1 out
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kBN;
         const int kb_end = (c + 1) * kChunkKB < nkb ? (c + 1) * kChunkKB : nkb;
         for (int kb = c * kChunkKB; kb < kb_end; ++kb) {
           const int s = kb % kT2Stages;
@@ -523,35 +529,33 @@ gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           mbar_wait(split_full(s), ph, 0x2a00 + s);
           tcgen05_fence_after();
           const uint64_t dhb = umma_desc_kmajor_sw128(hi_b(s)), dlb = umma_desc_kmajor_sw128(lo_b(s));
-          const int ts = kb % kT2ASlots;
-          const uint32_t a_hi = tmem_base + kTsACol0 + ts * 64, a_lo = a_hi + 32;
+          const uint32_t a_hi = tmem_base + kTsACol0 + s * 64, a_lo = a_hi + 32;
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint32_t first = (kb == c * kChunkKB && k == 0) ? 0u : 1u;
-            umma_tf32_ts_cg2(d_tmem, a_lo + k * kUmmaK, dhb + 2u * k, idesc, first);  // small terms first
-            umma_tf32_ts_cg2(d_tmem, a_hi + k * kUmmaK, dlb + 2u * k, idesc, 1u);
-            umma_tf32_ts_cg2(d_tmem, a_hi + k * kUmmaK, dhb + 2u * k, idesc, 1u);
+            umma_tf32_ts_cg2(tmem_base, a_lo + k * kUmmaK, dhb + 2u * k, idesc, first);  // small terms first
+            umma_tf32_ts_cg2(tmem_base, a_hi + k * kUmmaK, dlb + 2u * k, idesc, 1u);
+            umma_tf32_ts_cg2(tmem_base, a_hi + k * kUmmaK, dhb + 2u * k, idesc, 1u);
           }
           umma_commit_cg2_mcast(empty_bar(s), 0x3);
-          umma_commit_cg2_mcast(aslot_empty(ts), 0x3);
         }
-        umma_commit_cg2_mcast(acc_full(buf), 0x3);
+        umma_commit_cg2_mcast(acc_full, 0x3);
       }
     }
-  } else if (warp >= kFirstEpiWarp && warp < kFirstSplitWarp) {
+  } else if (warp < kFirstSplitWarp) {
+    setmaxnreg_inc<184>();
     const int e = warp - kFirstEpiWarp;
-    const int q = warp & 3;
-    const int half = e >> 2;
-    float acc[64];
+    const int q = warp & 3;    // TMEM lane quarter this warp may read
+    const int half = e >> 2;   // which 128 of the 256 accumulator columns
+    float acc[128];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
     for (int c = 0; c < nchunks; ++c) {
-      const int buf = c & 1;
-      mbar_wait(acc_full(buf), (c >> 1) & 1u, 0x2b00 + buf);
+      mbar_wait(acc_full, c & 1u, 0x2b00);
       tcgen05_fence_after();
-      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBN + half * 64;
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < 4; ++j) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t0 + j * 32, v);
         tmem_ld_wait();
@@ -561,15 +565,17 @@ gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (rank == 0) mbar_arrive(acc_empty(buf)); else mbar_arrive_cluster(mapa(acc_empty(buf), 0));
+        if (rank == 0) mbar_arrive(acc_empty); else mbar_arrive_cluster(mapa(acc_empty, 0));
       }
     }
     const int64_t row = static_cast<int64_t>(tile_m) * kBM + q * 32 + lane;
-    const int64_t col0 = static_cast<int64_t>(tile_n) * kBN + half * 64;
-    if (store && row < a.M) {
+    const int64_t col0 = static_cast<int64_t>(tile_n) * kT2BN + half * 128;
+    // lower_only keeps the single-CTA kernel's contract at 128-block granularity: blocks above the diagonal untouched
+    const bool store_half = store && !(a.lower_only && (2 * tile_n + half) > tile_m);
+    if (store_half && row < a.M) {
       float* crow = a.C + static_cast<int64_t>(blockIdx.z) * a.stride_c + row * a.ldc;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
+      for (int i = 0; i < 128; ++i) {
         const int64_t col = col0 + i;
         if (col < a.N) {
           float r = a.alpha * acc[i];
@@ -579,20 +585,15 @@ gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
       }
     }
-  } else if (warp >= kFirstSplitWarp) {
-    // two groups of four warps take alternate k-blocks: one k-block is a chain of dependent steps (LDS -> split ->
-    // tcgen05.st -> wait::st -> fence -> arrive) that a single group cannot overlap with the next k-block's
+  } else {
+    setmaxnreg_dec<104>();
     const int q = warp & 3;
-    const int group = (warp - kFirstSplitWarp) / kSplitWarps;
-    const int t = (threadIdx.x - kFirstSplitWarp * 32) & (kSplitWarps * 32 - 1);
+    const int t = threadIdx.x - kFirstSplitWarp * 32;
     const int row = q * 32 + lane;
-    for (int kb = group; kb < nkb; kb += kT2SplitGroups) {
+    for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kT2Stages;
       const uint32_t ph = (kb / kT2Stages) & 1u;
       mbar_wait(raw_full(s), ph, 0x2c00 + s);
-      const int ts = kb % kT2ASlots;
-      mbar_wait(aslot_empty(ts), ((kb / kT2ASlots) & 1u) ^ 1u, 0x2e00 + ts);  // the MMAs that read this A slot are done
-      tcgen05_fence_after();
       {
         uint32_t x[32], lo[32];
         const uint32_t rbase = raw_a(s) + row * 128;
@@ -603,19 +604,19 @@ gemm_tn_3xtf32_ts2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) { uint32_t hi; split_tf32(x[i], hi, lo[i]); }
-        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kTsACol0 + ts * 64;
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kTsACol0 + s * 64;
         tmem_st_32x32b_x32(ta, x);
         tmem_st_32x32b_x32(ta + 32, lo);
       }
       const uint32_t raw = hi_b(s);
-#pragma unroll
-      for (int i = 0; i < kT2HalfB / 16 / (kSplitWarps * 32); ++i) {
+#pragma unroll 8
+      for (int i = 0; i < kTileBytes / 16 / (kSplitWarps * 32); ++i) {
         const uint32_t off = (static_cast<uint32_t>(i) * (kSplitWarps * 32) + t) * 16u;
         const uint4 v = ld_shared_v4(raw + off);
         uint4 hi, lo;
         split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
         split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-        st_shared_v4(raw + kT2HalfB + off, lo);
+        st_shared_v4(raw + kTileBytes + off, lo);
       }
       tmem_st_wait();
       fence_proxy_async_smem();

@@ -132,16 +132,20 @@ def scale_rows_cols_(s: torch.Tensor, row_scale: torch.Tensor | None = None, col
 
 
 def _gram_plan(n: int, k: int, device) -> tuple[int, int, int] | None:
-    """Wave balance of the lower-triangle Gram GEMM (one 128 x 128 tile per CTA, one CTA per SM).  The k / 128 row tiles
-    give nt (nt + 1) / 2 output tiles: 528 at k = 4096, i.e. 3.57 waves on 148 SMs -- the fourth wave runs 57 % empty.
+    """Wave balance of the lower-triangle Gram GEMM.  With the single-CTA kernel (one 128 x 128 tile per SM) k = 4096
+    gives 528 output tiles = 3.57 waves on 148 SMs and the fourth wave runs 57 % empty; with the CTA-pair kernel
+    (256 x 256 tiles, 74 pairs) it is 136 tiles = 1.84 waves, where slicing does not pay (k = 8192: 7.13 waves, it does).
     Returns (r0, parts, kc): row tiles [0, r0) fill whole waves with full-contraction CTAs, the remaining row tiles are
     computed as ``parts`` contraction slices of kc columns each (short CTAs that pack into the last wave) and summed;
     None when that does not pay."""
-    nt = -(-k // 128)
-    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    # long contractions run on the CTA-pair kernel: 256 x 256 tiles, one per pair of SMs (gadm.cu, GADM_GEMM_2CTA)
+    pair = os.environ.get("GADM_GEMM_2CTA", "1") != "0" and n >= 2048 and k > 128
+    tile = 256 if pair else 128
+    nt = -(-k // tile)
+    sms = torch.cuda.get_device_properties(device).multi_processor_count // (2 if pair else 1)
     tiles = nt * (nt + 1) // 2
     full = tiles // sms
-    if k % 128 or full < 1 or n < 8192:
+    if k % tile or full < 1 or n < 8192:
         return None
     r0 = int((math.isqrt(8 * full * sms + 1) - 1) // 2)
     if r0 >= nt or r0 < 1:
@@ -151,7 +155,7 @@ def _gram_plan(n: int, k: int, device) -> tuple[int, int, int] | None:
         return None
     parts = min(8, n // 2048)
     kc = -(-n // parts // 32) * 32
-    return r0, parts, kc
+    return r0 * (tile // 128), parts, kc  # r0 in 128-row tiles
 
 
 _SIDE_STREAMS: dict = {}

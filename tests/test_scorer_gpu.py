@@ -446,21 +446,28 @@ def test_failed_or_ill_conditioned_factorisation_is_an_error_not_garbage(tmp_pat
 
 
 def test_cta_pair_gemm_variant_matches_fp64():
-    """The opt-in CTA-pair GEMM (GADM_GEMM_2CTA=1: 256 x 128 tiles over a cluster of two CTAs, tcgen05.mma.cta_group::2
-    with the A operand in each CTA's tensor memory and the B tile split between them) against fp64 over ragged shapes,
-    odd row-tile counts, lower-only and triangular-B modes and beta accumulation.  The switch is read once per process,
-    hence the subprocess."""
+    """The CTA-pair GEMM (256 x 256 tiles over a cluster of two CTAs, tcgen05.mma.cta_group::2 with M = N = 256, the A
+    operand in each CTA's tensor memory and the B tile split between them; the default for contractions >= 2048)
+    against fp64 over ragged shapes, odd row-tile counts, lower-only and triangular-B modes and beta accumulation --
+    and bit-identical to the single-CTA kernel (GADM_GEMM_2CTA=0), which accumulates every element in the same order.
+    The switch is read once per process, hence the subprocesses."""
     import json
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, GADM_GEMM_2CTA="1")
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "check_gemm_2cta.py"), "--quick"], env=env,
-                         capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    runs = {}
+    for flag in ("1", "0"):
+        env = dict(os.environ, GADM_GEMM_2CTA=flag)
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "check_gemm_2cta.py"), "--quick"], env=env,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        runs[flag] = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    res = runs["1"]
     assert res["env"] == "1" and res["watchdog"] == 0
     assert res["worst_rel_err"] < 3e-6, res
-    assert res["beta_err"] < 1e-3, res
+    assert res["beta_err"] < 2e-3, res
+    for key, val in res.items():
+        if key != "env":
+            assert runs["0"][key] == val, (key, val, runs["0"][key])  # same bits -> same error figures

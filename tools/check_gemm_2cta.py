@@ -1,6 +1,7 @@
-"""Check the CTA-pair GEMM variant (GADM_GEMM_2CTA=1) against fp64 and time the config-2 Gram with it.
+"""Check the CTA-pair GEMM (256 x 256 tiles, default for contractions >= 2048; GADM_GEMM_2CTA=0 disables it) against
+fp64 and time the config-2 Gram with it.
 
-    GADM_GEMM_2CTA=1 python tools/check_gemm_2cta.py
+    python tools/check_gemm_2cta.py [--quick]
 """
 import json
 import os
@@ -15,9 +16,10 @@ dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
 res = {"env": os.environ.get("GADM_GEMM_2CTA")}
 worst = 0.0
-for (m, n, k, lower, tri) in [(256, 128, 64, False, None), (384, 256, 96, False, None), (1000, 520, 300, False, None),
-                              (1024, 1024, 4096, True, None), (640, 640, 640, False, "lower"), (640, 640, 640, False, "upper"),
-                              (130, 70, 33, False, None), (2048, 2048, 50000 if "--quick" not in sys.argv else 5000, True, None)]:
+for (m, n, k, lower, tri) in [(384, 256, 2048, False, None), (1000, 520, 2100, False, None), (130, 300, 2048, False, None),
+                              (1024, 1024, 4096, True, None), (700, 2560, 2560, False, "lower"), (700, 2560, 2560, False, "upper"),
+                              (256, 128, 64, False, None),  # short contraction: the single-CTA kernel
+                              (2048, 2048, 50000 if "--quick" not in sys.argv else 5000, True, None)]:
     a = torch.randn(m, k, device=dev, generator=g)
     b = torch.randn(n, k, device=dev, generator=g)
     if tri == "lower":
@@ -41,7 +43,7 @@ for (m, n, k, lower, tri) in [(256, 128, 64, False, None), (384, 256, 96, False,
 res["worst_rel_err"] = worst
 res["watchdog"] = G._lib.get_handle(torch.device(dev)).watchdog_code()
 # beta / accumulate
-a = torch.randn(512, 777, device=dev, generator=g); b = torch.randn(384, 777, device=dev, generator=g)
+a = torch.randn(512, 2304, device=dev, generator=g); b = torch.randn(384, 2304, device=dev, generator=g)
 c0 = torch.randn(512, 384, device=dev, generator=g)
 out = G.gemm_tn(a, b, out=c0.clone(), alpha=-1.0, beta=1.0)
 res["beta_err"] = float((out.double() - (c0.double() - a.double() @ b.double().T)).abs().max())
