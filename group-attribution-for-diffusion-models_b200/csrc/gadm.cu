@@ -855,10 +855,10 @@ int64_t gadm_cholesky_solve_vec_workspace_bytes(int64_t k) {
 int gadm_cholesky_solve_vec(gadm_handle h, const float* l, int64_t ld, const void* blocks, int64_t k, const float* b,
                             float* x, void* workspace, int64_t workspace_bytes, void* stream) {
   GADM_REQUIRE(h && l && blocks && b && x && workspace && k > 0, "bad argument");
-  GADM_REQUIRE(k % 128 == 0 && ld >= k && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(l) & 15) == 0,
-               "gadm_cholesky_solve_vec needs k %% 128 == 0, ld %% 4 == 0 and a 16-byte aligned factor (k = %lld, ld = %lld)",
+  GADM_REQUIRE(ld >= k && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(l) & 15) == 0,
+               "gadm_cholesky_solve_vec needs ld %% 4 == 0 and a 16-byte aligned factor (k = %lld, ld = %lld)",
                (long long)k, (long long)ld);
-  const int nblk = (int)(k / 128);
+  const int nblk = (int)((k + 127) / 128);
   GADM_REQUIRE(nblk <= h->num_sms && nblk <= 64, "k = %lld: the %d CTAs of the substitution must be co-resident (and <= 64)",
                (long long)k, nblk);
   if (workspace_bytes < gadm_cholesky_solve_vec_workspace_bytes(k))
@@ -877,7 +877,7 @@ int gadm_cholesky_solve_vec(gadm_handle h, const float* l, int64_t ld, const voi
   GADM_CUDA(cudaMemsetAsync(count, 0, 1024, st));
   const float* linv = reinterpret_cast<const float*>(blocks);
   const float* linv_t = linv + (int64_t)nblk * 128 * 128;
-  int nb = nblk;
+  int nb = (int)k;  // the kernel derives the block count and the size of the last block from k
   void* args[] = {(void*)&l, (void*)&ld, (void*)&nb, (void*)&linv, (void*)&linv_t, (void*)&b, (void*)&x, (void*)&partial,
                   (void*)&count};
   GADM_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)nblk), dim3(gadm::trsv::kThreads), args,

@@ -16,8 +16,8 @@
 //
 // Per step the critical path is one 128 x 128 matrix-vector product from shared memory plus one signal (fence +
 // atomic + polling load), ~3 us; every block of L is read exactly once (k^2 / 2 floats in each direction).
-// Deterministic: fixed summation orders everywhere.  Requires k % 128 == 0, 16-byte aligned L with ld % 4 == 0, and
-// all k / 128 CTAs co-resident (cooperative launch).
+// Deterministic: fixed summation orders everywhere.  Requires a 16-byte aligned L with ld % 4 == 0 and all
+// ceil(k / 128) CTAs co-resident (cooperative launch); k need not be a multiple of 128 (the last block is padded).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -38,12 +38,14 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int kPending>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-// 128 x 128 block (row pitch ld floats) -> shared memory [128][128], asynchronously, by the whole CTA
-__device__ __forceinline__ void fetch_block(float* dst, const float* src, int64_t ld) {
+// 128 x 128 block (row pitch ld floats) -> shared memory [128][128], asynchronously, by the whole CTA; rows >= rows_valid
+// (the last block row of a system whose size is not a multiple of 128) are written as zeros
+__device__ __forceinline__ void fetch_block(float* dst, const float* src, int64_t ld, int rows_valid = kB) {
   const uint32_t d0 = smem_u32(dst);
   for (int i = threadIdx.x; i < kB * kB / 4; i += kThreads) {
     const int r = i >> 5, q = i & 31;  // row, 16-byte chunk
-    cp16(d0 + (r * kB + q * 4) * 4, src + static_cast<int64_t>(r) * ld + q * 4);
+    if (r < rows_valid) cp16(d0 + (r * kB + q * 4) * 4, src + static_cast<int64_t>(r) * ld + q * 4);
+    else *reinterpret_cast<float4*>(dst + r * kB + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   cp_commit();
 }
@@ -99,9 +101,11 @@ __device__ __forceinline__ void signal(uint32_t* counter) {
   }
 }
 
-// grid = k / 128 CTAs (cooperative).  partial: [2][nblk][nblk][128] doubles; count: [2][nblk] words, zeroed.
+// grid = ceil(k / 128) CTAs (cooperative).  partial: [2][nblk][nblk][128] doubles; count: [2][nblk] words, zeroed.
+// k % 128 != 0: the last block is padded -- potrf_diag_kernel pads its diagonal block with the identity, the padded
+// rows of L read as zeros here, b as zero, and the padded part of x is not stored.
 __global__ void __launch_bounds__(kThreads)
-chol_solve_vec_kernel(const float* __restrict__ L, int64_t ld, int nblk, const float* __restrict__ linv,
+chol_solve_vec_kernel(const float* __restrict__ L, int64_t ld, int k, const float* __restrict__ linv,
                       const float* __restrict__ linv_t, const float* __restrict__ b, float* __restrict__ x,
                       double* __restrict__ partial, uint32_t* __restrict__ count) {
   extern __shared__ __align__(16) float trsv_smem[];
@@ -111,6 +115,9 @@ chol_solve_vec_kernel(const float* __restrict__ L, int64_t ld, int nblk, const f
   float* vec = rhs + kB;   // y_c, later x_c
   float* prod = vec + kB;  // one block product
   const int c = blockIdx.x, tid = threadIdx.x;
+  const int nblk = (k + kB - 1) / kB;
+  const int last_rows = k - (nblk - 1) * kB;  // valid rows of the last block
+  auto rows_of = [&](int blk) { return blk == nblk - 1 ? last_rows : kB; };
   double* part_f = partial;
   double* part_b = partial + static_cast<size_t>(nblk) * nblk * kB;
   uint32_t* cnt_f = count;
@@ -118,10 +125,10 @@ chol_solve_vec_kernel(const float* __restrict__ L, int64_t ld, int nblk, const f
 
   // ---------------- forward: L y = b
   fetch_block(buf0, linv + static_cast<size_t>(c) * kB * kB, kB);  // before the wait: it does not depend on anything
-  if (c + 1 < nblk) fetch_block(buf1, L + static_cast<int64_t>(c + 1) * kB * ld + static_cast<int64_t>(c) * kB, ld);
+  if (c + 1 < nblk) fetch_block(buf1, L + static_cast<int64_t>(c + 1) * kB * ld + static_cast<int64_t>(c) * kB, ld, rows_of(c + 1));
   wait_count(cnt_f + c, static_cast<uint32_t>(c), 0x7501);
   if (tid < kB) {
-    double s = static_cast<double>(b[c * kB + tid]);
+    double s = tid < rows_of(c) ? static_cast<double>(b[c * kB + tid]) : 0.0;
     for (int j = 0; j < c; ++j) s -= __ldcg(part_f + (static_cast<size_t>(c) * nblk + j) * kB + tid);
     rhs[tid] = static_cast<float>(s);
   }
@@ -133,7 +140,7 @@ chol_solve_vec_kernel(const float* __restrict__ L, int64_t ld, int nblk, const f
     float* cur = ((j - c) & 1) ? buf1 : buf0;
     float* nxt = ((j - c) & 1) ? buf0 : buf1;
     if (j + 1 < nblk) {
-      fetch_block(nxt, L + static_cast<int64_t>(j + 1) * kB * ld + static_cast<int64_t>(c) * kB, ld);
+      fetch_block(nxt, L + static_cast<int64_t>(j + 1) * kB * ld + static_cast<int64_t>(c) * kB, ld, rows_of(j + 1));
       cp_wait<1>();
     } else {
       cp_wait<0>();
@@ -148,7 +155,7 @@ chol_solve_vec_kernel(const float* __restrict__ L, int64_t ld, int nblk, const f
   // ---------------- backward: L^T x = y   (vec holds y_c)
   __syncthreads();
   fetch_block(buf0, linv_t + static_cast<size_t>(c) * kB * kB, kB);
-  if (c > 0) fetch_block(buf1, L + static_cast<int64_t>(c) * kB * ld + static_cast<int64_t>(c - 1) * kB, ld);
+  if (c > 0) fetch_block(buf1, L + static_cast<int64_t>(c) * kB * ld + static_cast<int64_t>(c - 1) * kB, ld, rows_of(c));
   wait_count(cnt_b + c, static_cast<uint32_t>(nblk - 1 - c), 0x7502);
   if (tid < kB) {
     double s = static_cast<double>(vec[tid]);
@@ -159,12 +166,12 @@ chol_solve_vec_kernel(const float* __restrict__ L, int64_t ld, int nblk, const f
   __syncthreads();
   block_matvec<false>(buf0, rhs, vec);  // x_c = Linv_c^T rhs  (linv_t holds the transposed inverse)
   __syncthreads();
-  if (tid < kB) x[c * kB + tid] = vec[tid];
+  if (tid < rows_of(c)) x[c * kB + tid] = vec[tid];
   for (int j = c - 1; j >= 0; --j) {
     float* cur = ((c - j) & 1) ? buf1 : buf0;
     float* nxt = ((c - j) & 1) ? buf0 : buf1;
     if (j > 0) {
-      fetch_block(nxt, L + static_cast<int64_t>(c) * kB * ld + static_cast<int64_t>(j - 1) * kB, ld);
+      fetch_block(nxt, L + static_cast<int64_t>(c) * kB * ld + static_cast<int64_t>(j - 1) * kB, ld, rows_of(c));
       cp_wait<1>();
     } else {
       cp_wait<0>();

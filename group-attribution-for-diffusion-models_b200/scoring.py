@@ -407,8 +407,7 @@ class TrakScorer:
             # through the factor in one cooperative launch; with it: two matrix-vector products (HBM-bound, fp64
             # accumulation, ~20 us each at k = 4096) instead of two GEMMs that run a single 128-row tile through the
             # whole contraction (84 us each)
-            if (self._X is None and self.k % 128 == 0 and self.k <= 8192 and self.L.stride(0) % 4 == 0
-                    and self.L.data_ptr() % 16 == 0):
+            if self._X is None and self.k <= 8192 and self.L.stride(0) % 4 == 0 and self.L.data_ptr() % 16 == 0:
                 return torch.stack([self._solve_vec(y[i]) for i in range(y.shape[0])])
             return torch.stack([matvec_rows(self.Xt, matvec_rows(self.X, y[i])) for i in range(y.shape[0])])
         return gemm_tn(gemm_tn(y, self.X, b_tri="lower"), self.Xt, b_tri="upper")

@@ -181,7 +181,7 @@ int gadm_cholesky(gadm_handle h, float* a, int64_t ld, int64_t k, void* blocks, 
 /* x = (L L^T)^-1 b for ONE right-hand side b [k] through the factor of gadm_cholesky and its `blocks` workspace: forward
  * and backward substitution over the 128-blocks in one cooperative launch (k / 128 CTAs, point-to-point signalling).
  * What the mean-first TRAK score needs (traks.py:152-157: mean_t(gen_t) K^-1 Phi^T) without forming the triangular
- * inverse.  Requires k % 128 == 0, k <= 8192, ld % 4 == 0, l 16-byte aligned; workspace of
+ * inverse.  Requires k <= 8192, ld % 4 == 0, l 16-byte aligned (k need not be a multiple of 128); workspace of
  * gadm_cholesky_solve_vec_workspace_bytes(k), 16-byte aligned. */
 int64_t gadm_cholesky_solve_vec_workspace_bytes(int64_t k);
 int gadm_cholesky_solve_vec(gadm_handle h, const float* l, int64_t ld, const void* blocks, int64_t k, const float* b,

@@ -96,7 +96,8 @@ def test_cholesky_and_solve(k, N):
     assert float((kinv.double() @ Kd - eye).abs().max()) < 1e-3
 
 
-@pytest.mark.parametrize("k,N", [(128, 500), (256, 900), (1024, 3000), (4096, 6000), (8192, 9000)])
+@pytest.mark.parametrize("k,N", [(128, 500), (256, 900), (1024, 3000), (4096, 6000), (8192, 9000), (77, 300), (300, 900),
+                                 (1000, 2500)])
 def test_single_row_solve_by_cooperative_substitution(k, N):
     """gadm_cholesky_solve_vec (one cooperative launch: forward + backward substitution over the 128-blocks with
     point-to-point signalling) against an fp64 solve and against the explicit-inverse path; it is what the mean-first
