@@ -145,3 +145,24 @@ def test_by_class_mask_samplers_match_reference_functions(golden_dir):
         rem, removed = masks.remove_data_by_shapley(len(labels), seed, by_class=True, labels=labels)
         np.testing.assert_array_equal(rem, g[f"shapley_rem_{seed}"])
         np.testing.assert_array_equal(removed, g[f"shapley_removed_{seed}"])
+
+
+def test_f16_projection_matrix_keeps_eight_significant_bits():
+    """P for F16G staging is an fp16 number whose three low mantissa bits are zero (csrc/philox.cuh::box_muller_pair:
+    half-ulp bias, then mask), i.e. it carries the 8 significant bits of the bf16 path; it never differs from the
+    bf16-rounded value by more than one bf16 ulp, and sign / magnitude statistics are untouched."""
+    from oracle import philox
+
+    s = philox.seed64_of(42, 0)
+    f16 = philox.normal_matrix(s, 0, 512, 96, "f16")
+    bf16 = philox.normal_matrix(s, 0, 512, 96, "bf16")
+    raw = philox.normal_matrix(s, 0, 512, 96, None)
+    bits = f16.astype(np.float16).view(np.uint16)
+    assert (f16.astype(np.float16).astype(np.float32) == f16).all()       # representable in fp16
+    assert ((bits & 7) == 0).all()                                        # 8 significant bits
+    normal = np.abs(raw) >= 2.0 ** -14                                    # fp16 subnormals have a coarser grid
+    # round to fp16 (11 bits), then half-up to 8 bits: at most half an 8-bit ulp plus half an 11-bit ulp
+    assert (np.abs(f16 - raw)[normal] <= np.abs(raw)[normal] * 2.0 ** -8 * 1.13).all()
+    assert (np.abs(f16 - bf16)[normal] <= np.abs(raw)[normal] * 2.0 ** -7).all()
+    assert (np.sign(f16) == np.sign(raw))[normal].all()
+    assert abs(float(f16.std()) - float(raw.std())) < 2e-3 and abs(float(f16.mean()) - float(raw.mean())) < 1e-3
