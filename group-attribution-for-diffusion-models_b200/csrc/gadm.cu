@@ -671,7 +671,8 @@ int gadm_gemm_tn_batched(gadm_handle h, const float* a, int64_t lda, int64_t str
   static const bool use_2cta = [] { const char* e = getenv("GADM_GEMM_2CTA"); return !(e && atoi(e) == 0); }();
   // (long contractions only: for the rank-128 updates of the blocked Cholesky and the small merges of the triangular
   // inverse the larger tiles mean fewer, longer CTAs and measured slower -- 2.84 vs 2.67 ms for the factorisation)
-  if (use_ts && use_2cta && m > gadm::gemm::kBM && n > gadm::gemm::kBN && k >= 2048) {
+  static const int64_t min_k = [] { const char* e = getenv("GADM_GEMM_2CTA_MINK"); return e ? (int64_t)atol(e) : (int64_t)2048; }();
+  if (use_ts && use_2cta && m > gadm::gemm::kBM && n > gadm::gemm::kBN && k >= min_k) {
     // B box: the 128 rows of the 256-column tile that one CTA of the pair holds = the same tensor map as the 1-CTA kernel
     auto kernel = gadm::gemm::gemm_tn_3xtf32_ts2_kernel;
     if (!h->attr_gemm_ts2) {
